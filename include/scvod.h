@@ -1,0 +1,163 @@
+/*
+ * scvod.h — C-ABI of the B200-native SCV-OD dynamic-removal hot path.
+ *
+ * The reference (Yixin-F/DR-Using-SCV-OD) has no plugin/FFI layer: the boundary it offers is the
+ * public surface of `class SSC` (reference include/ssc.h:55-104) driven by src/main.cpp:9-10.  This
+ * header is the seam that sits *under* those methods: a maintainer of the reference re-implements
+ * the bodies of SSC::process / segment / recognize / tracking / segDF by calling these entry points
+ * (see INTEGRATION.md for the exact stubs), and `PatchWork<PointT>::estimate_ground`
+ * (reference include/patchwork.h:278-398) by calling scvod_ground().
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are caller-owned HOST memory unless the name says _dev
+ *   - a scan is an AoS array of float[4] = {x, y, z, intensity} (the four fields of pcl::PointXYZI the
+ *     reference reads; reference include/utility.h:96-106, src/ssc.cpp:157-184)
+ *   - every function returns 0 on success, <0 on error; scvod_last_error() gives the message
+ *   - one context per GPU / host thread (the reference's SSC is non-reentrant: static SSC::id,
+ *     reference src/ssc.cpp:28)
+ *   - there is NO CPU fallback: every compute entry point fails with SCVOD_ERR_CUDA when no sm_100
+ *     device is usable.
+ */
+#ifndef SCVOD_H_
+#define SCVOD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCVOD_OK 0
+#define SCVOD_ERR_ARG (-1)
+#define SCVOD_ERR_CUDA (-2)
+#define SCVOD_ERR_CAPACITY (-3)
+#define SCVOD_ERR_STATE (-4)
+
+/* Per-input-point outcome classes (derived from reference
+ * include/patchwork.h:302-310,436,331 and src/ssc.cpp:161-172,445-466,479-499,1323-1421). */
+enum scvod_point_class {
+  SCVOD_PT_DROPPED_LOW = 0,     /* z < -1.8*sensor_height (patchwork.h:302-310)            */
+  SCVOD_PT_DROPPED_RANGE = 1,   /* r outside (2.7, 80]    (patchwork.h:436)                */
+  SCVOD_PT_DROPPED_SPARSE = 2,  /* patch with <= 10 points (patchwork.h:331)               */
+  SCVOD_PT_GROUND = 3,          /* cloud_out of estimate_ground                            */
+  SCVOD_PT_GATED_OUT = 4,       /* outside the SSC range/angle/azimuth window (ssc.cpp:161-172) */
+  SCVOD_PT_UNCLUSTERED = 5,     /* cluster erased by bounding-box refine (ssc.cpp:445-466) */
+  SCVOD_PT_STATIC = 6,          /* member of a cluster whose state != 1                    */
+  SCVOD_PT_DYNAMIC = 7          /* member of a cluster with state == 1 (ssc.cpp:1324,1348) */
+};
+
+/* The subset of Utility's parameter block that the path reads (reference include/utility.h:209-236,
+ * 238-240; defaults at :283-313).  Field names follow the reference (trailing '_' dropped). */
+typedef struct scvod_params {
+  float sensor_height;
+  float min_dis, max_dis;
+  float min_angle, max_angle;
+  float min_azimuth, max_azimuth;
+  float range_res, sector_res, azimuth_res;
+  float refine_height;
+  float max_z, min_z;
+  float car_square;
+  int32_t iteration;
+  int32_t toBeClass;
+  int32_t search_c;
+  float intensity_diff;
+  float intensity_cov;
+  float occupancy;
+  int32_t building, tree, car;
+} scvod_params;
+
+/* Grid dimensions exactly as SSC::SSC computes them in float (reference src/ssc.cpp:36-39). */
+typedef struct scvod_grid {
+  int32_t range_num, sector_num, azimuth_num, bin_num;
+} scvod_grid;
+
+typedef struct scvod_ctx scvod_ctx;
+
+/* ---- parameter helpers --------------------------------------------------------------------- */
+/* config/semantickitti.yaml and config/parkinglot.yaml of the reference (+ utility.h defaults). */
+void scvod_params_semantickitti(scvod_params* p);
+void scvod_params_parkinglot(scvod_params* p);
+int scvod_grid_dims(const scvod_params* p, scvod_grid* g); /* ssc.cpp:36-39 */
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* max_points: capacity per scan; max_batch: scans processed per launch group. */
+int scvod_create(const scvod_params* p, int device, int max_points, int max_batch, scvod_ctx** out);
+int scvod_destroy(scvod_ctx* ctx);
+const char* scvod_last_error(void);
+int scvod_num_kernel_launches(const scvod_ctx* ctx, int64_t* out); /* kernels launched so far */
+
+/* ---- stage entry points (single scan, host buffers; replace the bodies named on each line) --- */
+
+/* PatchWork::estimate_ground (patchwork.h:278-398) as called by SSC::extractGroudByPatchWork
+ * (ssc.cpp:88-96).  Outputs are ORIGINAL point indices in the reference's output order.
+ * ground_idx/nonground_idx must hold n ints each. */
+int scvod_ground(scvod_ctx* ctx, const float* xyzi, int n, int32_t* ground_idx, int32_t* n_ground,
+                 int32_t* nonground_idx, int32_t* n_nonground);
+
+/* SSC::makeApriVec (ssc.cpp:155-195) + Utility polar helpers (utility.h:346-392) on an arbitrary
+ * cloud.  pass[i]=1 when the point survives the three gates; the index arrays are written for every
+ * point (gated-out points included, as the arithmetic is the same).  Any output may be NULL. */
+int scvod_bin(scvod_ctx* ctx, const float* xyzi, int n, uint8_t* pass, int32_t* voxel_idx,
+              int32_t* range_idx, int32_t* sector_idx, int32_t* azimuth_idx, float* range,
+              float* angle, float* azimuth);
+
+/* ---- frame pipeline (the hot path proper) ---------------------------------------------------- */
+
+/* SSC::process + segment + recognize (ssc.cpp:224-251, 637-656, 834-895) for nscans scans in
+ * one batched pass, appending nscans frames to the context's frame_set (ssc.cpp:1435-1444).
+ * offsets has nscans+1 entries (point offsets into xyzi). */
+int scvod_push_scans(scvod_ctx* ctx, const float* xyzi, const int64_t* offsets, int nscans);
+
+/* Same, with the scans already resident in device memory (float4 per point). */
+int scvod_push_scans_dev(scvod_ctx* ctx, const void* xyzi_dev, const int64_t* offsets, int nscans);
+
+/* SSC::tracking chain of SSC::segDF (ssc.cpp:1448-1452, 1250-1426) over all frames pushed so far
+ * and not yet tracked.  poses: 6 floats per frame {x,y,z,roll,pitch,yaw} = the Pose fields
+ * tracking() reads (utility.h:77-93).  first_frame = index of the first pose's frame. */
+int scvod_track(scvod_ctx* ctx, const float* poses6, int nposes);
+
+int scvod_num_frames(const scvod_ctx* ctx);
+int scvod_reset_frames(scvod_ctx* ctx); /* SSC::reset + frame_set.clear() */
+
+/* Per-input-point outcome class (enum scvod_point_class) of frame f; cls holds n_in bytes. */
+int scvod_frame_labels(scvod_ctx* ctx, int frame, uint8_t* cls, int n);
+
+/* frame inspection — sizes: counts[0]=n_in, [1]=n_ground, [2]=n_nonground, [3]=n_apri (cloud_use),
+ * [4]=n_voxels (hash_cloud.size()), [5]=clusters after CVC, [6]=after intensity refine,
+ * [7]=after bounding-box refine, [8]=clusters now (after tracking mutations). */
+int scvod_frame_counts(scvod_ctx* ctx, int frame, int32_t counts[9]);
+int scvod_frame_ground_order(scvod_ctx* ctx, int frame, int32_t* ground_src, int32_t* nonground_src);
+/* apri_vec (ssc.cpp:177-193): src = original point index of apri entry m. Any output may be NULL. */
+int scvod_frame_apri(scvod_ctx* ctx, int frame, int32_t* src, int32_t* voxel_idx);
+/* hash_cloud (ssc.cpp:253-289) sorted by ascending voxel_idx; center is 3 floats per voxel;
+ * tri is 3 ints per voxel (range_idx, sector_idx, azimuth_idx of the first inserted point);
+ * label is the voxel's cluster label now. */
+int scvod_frame_voxels(scvod_ctx* ctx, int frame, int32_t* voxel_idx, int32_t* count, float* av,
+                       float* cov, float* center, int32_t* tri, int32_t* label);
+/* cluster name of each apri entry at stage 0 (after clusterAndCreateFrame), 1 (after
+ * refineClusterByIntensity), 2 (after refineClusterByBoundingBox; -1 = erased). */
+int scvod_frame_point_cluster(scvod_ctx* ctx, int frame, int stage, int32_t* name);
+/* cluster_set in iteration order: bbox = {min.x,min.y,min.z,max.x,max.y,max.z}. cap = array capacity. */
+int scvod_frame_clusters(scvod_ctx* ctx, int frame, int cap, int32_t* name, int32_t* type,
+                         int32_t* state, int32_t* npts, int32_t* nvox, float* bbox);
+
+/* Static submap of frames [f0,f1): xyz+intensity of every point whose class is not DYNAMIC,
+ * transformed to the map frame with the frame's pose (SSC::saveSegCloud mode 3 semantics,
+ * ssc.cpp:531-555).  Written to device memory for the NCCL all-gather; returns the point count. */
+int scvod_static_submap_dev(scvod_ctx* ctx, int f0, int f1, const float* poses6, void* out_xyzi_dev,
+                            int64_t cap_points, int64_t* n_points);
+
+/* ---- helpers shared by tests and the bench ---------------------------------------------------- */
+/* trans_next.inverse() * trans_pre of SSC::tracking (ssc.cpp:1255-1257) as 12 floats row-major 3x4. */
+void scvod_relative_pose(const float pose_next6[6], const float pose_pre6[6], float T[12]);
+
+/* Deterministic synthetic 64-beam-style scan: rings x cols rays cast into a
+ * procedural street scene. Writes up to rings*cols points; returns the count in *n and the ego
+ * pose in pose6 (may be NULL). No libm calls: identical bytes on every host. */
+int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n,
+                     float* pose6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCVOD_H_ */
