@@ -1,0 +1,293 @@
+"""scvod_b200 — host-side Python mirror of the reference's SSC interface over the C-ABI of
+``libscvod_b200.so`` (include/scvod.h).
+
+The reference (Yixin-F/DR-Using-SCV-OD) is a C++ program whose public surface is ``class SSC``
+(reference include/ssc.h:7-105): ``process`` -> ``segment`` -> ``recognize`` per scan, then ``tracking``
+over consecutive frames, driven by ``segDF`` (reference src/ssc.cpp:1428-1452).  This module keeps
+those names and argument meanings; every call goes through ctypes into the CUDA library.  There is no
+CPU fallback: importing works without a GPU (so the symbol table can be checked), computing does not.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscvod_b200.so")
+
+# enum scvod_point_class (include/scvod.h)
+PT_DROPPED_LOW, PT_DROPPED_RANGE, PT_DROPPED_SPARSE, PT_GROUND, PT_GATED_OUT, PT_UNCLUSTERED, PT_STATIC, PT_DYNAMIC = range(8)
+
+
+class Params(ctypes.Structure):
+    """scvod_params: the Utility fields the path reads (reference include/utility.h:209-240)."""
+
+    _fields_ = (
+        [(n, ctypes.c_float) for n in (
+            "sensor_height", "min_dis", "max_dis", "min_angle", "max_angle", "min_azimuth", "max_azimuth",
+            "range_res", "sector_res", "azimuth_res", "refine_height", "max_z", "min_z", "car_square")]
+        + [(n, ctypes.c_int32) for n in ("iteration", "toBeClass", "search_c")]
+        + [(n, ctypes.c_float) for n in ("intensity_diff", "intensity_cov", "occupancy")]
+        + [(n, ctypes.c_int32) for n in ("building", "tree", "car")]
+    )
+
+
+class Grid(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("range_num", "sector_num", "azimuth_num", "bin_num")]
+
+
+EXPORTS = (
+    "scvod_params_semantickitti", "scvod_params_parkinglot", "scvod_grid_dims", "scvod_create", "scvod_destroy",
+    "scvod_last_error", "scvod_num_kernel_launches", "scvod_set_option", "scvod_ground", "scvod_bin", "scvod_push_scans",
+    "scvod_push_scans_dev", "scvod_track", "scvod_num_frames", "scvod_reset_frames", "scvod_frame_labels",
+    "scvod_labels_range", "scvod_frame_counts", "scvod_frame_ground_order", "scvod_frame_apri", "scvod_frame_voxels",
+    "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
+    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan",
+)
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libscvod_b200.so; raises (loudly) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                "(or __graft_entry__.build()); there is no CPU fallback for the SCV-OD path")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.scvod_last_error.restype = ctypes.c_char_p
+        lib.scvod_relative_pose.restype = None
+        lib.scvod_params_semantickitti.restype = None
+        lib.scvod_params_parkinglot.restype = None
+        _lib = lib
+    return _lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class ScvodError(RuntimeError):
+    pass
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise ScvodError(f"scvod error {rc}: {load_library().scvod_last_error().decode()}")
+    return rc
+
+
+def semantickitti_params() -> Params:
+    p = Params()
+    load_library().scvod_params_semantickitti(ctypes.byref(p))
+    return p
+
+
+def parkinglot_params() -> Params:
+    p = Params()
+    load_library().scvod_params_parkinglot(ctypes.byref(p))
+    return p
+
+
+def grid_dims(p: Params) -> Grid:
+    g = Grid()
+    _check(load_library().scvod_grid_dims(ctypes.byref(p), ctypes.byref(g)))
+    return g
+
+
+def synth_scan(seed: int, scan_id: int, rings: int = 64, cols: int = 1800):
+    """Deterministic synthetic scan. Returns (xyzi float32 [n,4], pose6 float32 [6])."""
+    buf = np.empty((rings * cols, 4), np.float32)
+    n = ctypes.c_int(0)
+    pose = np.zeros(6, np.float32)
+    _check(load_library().scvod_synth_scan(ctypes.c_uint64(seed), int(scan_id), int(rings), int(cols), _ptr(buf), ctypes.byref(n), _ptr(pose)))
+    return np.ascontiguousarray(buf[: n.value]), pose
+
+
+def relative_pose(pose_next: np.ndarray, pose_pre: np.ndarray) -> np.ndarray:
+    T = np.zeros(12, np.float32)
+    a = np.ascontiguousarray(pose_next, np.float32)
+    b = np.ascontiguousarray(pose_pre, np.float32)
+    load_library().scvod_relative_pose(_ptr(a), _ptr(b), _ptr(T))
+    return T.reshape(3, 4)
+
+
+class SSC:
+    """Mirror of the reference's ``class SSC`` for the hot path (reference include/ssc.h:55-104).
+
+    ``process(clouds)`` runs process+segment+recognize for a list of scans (the per-scan loop of segDF,
+    src/ssc.cpp:1435-1444) in batched GPU passes; ``tracking(poses)`` runs the frame chain
+    (src/ssc.cpp:1450-1452); ``segDF(clouds, poses)`` does both and returns per-point classes.
+    """
+
+    def __init__(self, params: Optional[Params] = None, device: int = 0, max_points: int = 131072, max_batch: int = 16):
+        self._lib = load_library()
+        self.params = params if params is not None else semantickitti_params()
+        g = grid_dims(self.params)
+        self.range_num, self.sector_num, self.azimuth_num, self.bin_num = g.range_num, g.sector_num, g.azimuth_num, g.bin_num
+        self._ctx = ctypes.c_void_p()
+        _check(self._lib.scvod_create(ctypes.byref(self.params), int(device), int(max_points), int(max_batch), ctypes.byref(self._ctx)))
+        self.frame_sizes: List[int] = []
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.scvod_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        _check(self._lib.scvod_set_option(self._ctx, key.encode(), int(value)))
+
+    # -- per-scan stages ------------------------------------------------------------------------
+    def process(self, clouds: Sequence[np.ndarray]):
+        """process + segment + recognize for each cloud ([n,4] float32 xyzi); appends to frame_set."""
+        clouds = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds]
+        if not clouds:
+            return
+        off = np.zeros(len(clouds) + 1, np.int64)
+        off[1:] = np.cumsum([len(c) for c in clouds])
+        flat = np.concatenate(clouds, axis=0) if len(clouds) > 1 else clouds[0]
+        self.process_flat(flat, off)
+
+    def process_flat(self, flat: np.ndarray, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        _check(self._lib.scvod_push_scans(self._ctx, _ptr(flat), _ptr(offsets), len(offsets) - 1))
+        self.frame_sizes.extend(int(x) for x in np.diff(offsets))
+
+    def process_device(self, dev_ptr: int, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        _check(self._lib.scvod_push_scans_dev(self._ctx, ctypes.c_void_p(dev_ptr), _ptr(offsets), len(offsets) - 1))
+        self.frame_sizes.extend(int(x) for x in np.diff(offsets))
+
+    def extractGroudByPatchWork(self, cloud: np.ndarray):
+        """PatchWork::estimate_ground: returns (ground_idx, nonground_idx) in the reference's output order."""
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+        n = len(cloud)
+        g = np.empty(max(n, 1), np.int32)
+        ng = np.empty(max(n, 1), np.int32)
+        cg, cng = ctypes.c_int32(), ctypes.c_int32()
+        _check(self._lib.scvod_ground(self._ctx, _ptr(cloud), n, _ptr(g), ctypes.byref(cg), _ptr(ng), ctypes.byref(cng)))
+        return g[: cg.value].copy(), ng[: cng.value].copy()
+
+    def last_patch_records(self, slot: int = 0) -> np.ndarray:
+        rec = np.zeros((504, 12), np.float32)
+        _check(self._lib.scvod_last_patch_records(self._ctx, slot, _ptr(rec)))
+        return rec
+
+    def makeApriVec(self, cloud: np.ndarray) -> dict:
+        """Polar binning of an arbitrary cloud: dict of pass, voxel_idx, range_idx, sector_idx, azimuth_idx, range, angle, azimuth."""
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+        n = len(cloud)
+        out = {
+            "pass": np.zeros(n, np.uint8), "voxel_idx": np.zeros(n, np.int32), "range_idx": np.zeros(n, np.int32),
+            "sector_idx": np.zeros(n, np.int32), "azimuth_idx": np.zeros(n, np.int32), "range": np.zeros(n, np.float32),
+            "angle": np.zeros(n, np.float32), "azimuth": np.zeros(n, np.float32),
+        }
+        _check(self._lib.scvod_bin(self._ctx, _ptr(cloud), n, _ptr(out["pass"]), _ptr(out["voxel_idx"]), _ptr(out["range_idx"]),
+                                   _ptr(out["sector_idx"]), _ptr(out["azimuth_idx"]), _ptr(out["range"]), _ptr(out["angle"]), _ptr(out["azimuth"])))
+        return out
+
+    def atan2f_device(self, y: np.ndarray, x: np.ndarray) -> np.ndarray:
+        y = np.ascontiguousarray(y, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(y)
+        _check(self._lib.scvod_atan2f_device(self._ctx, _ptr(y), _ptr(x), _ptr(out), ctypes.c_int64(y.size)))
+        return out
+
+    # -- frame chain ------------------------------------------------------------------------------
+    def tracking(self, poses: np.ndarray):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        _check(self._lib.scvod_track(self._ctx, _ptr(poses), len(poses)))
+
+    def segDF(self, clouds: Sequence[np.ndarray], poses: np.ndarray) -> List[np.ndarray]:
+        f0 = self.num_frames
+        self.process(clouds)
+        self.tracking(poses)
+        return [self.frame_labels(f) for f in range(f0, self.num_frames)]
+
+    def reset(self):
+        _check(self._lib.scvod_reset_frames(self._ctx))
+        self.frame_sizes = []
+
+    @property
+    def num_frames(self) -> int:
+        return int(self._lib.scvod_num_frames(self._ctx))
+
+    @property
+    def kernel_launches(self) -> int:
+        v = ctypes.c_int64()
+        _check(self._lib.scvod_num_kernel_launches(self._ctx, ctypes.byref(v)))
+        return v.value
+
+    # -- results / inspection -----------------------------------------------------------------------
+    def frame_counts(self, f: int) -> np.ndarray:
+        c = np.zeros(9, np.int32)
+        _check(self._lib.scvod_frame_counts(self._ctx, f, _ptr(c)))
+        return c
+
+    def frame_labels(self, f: int) -> np.ndarray:
+        n = int(self.frame_counts(f)[0])
+        cls = np.zeros(max(n, 1), np.uint8)
+        _check(self._lib.scvod_frame_labels(self._ctx, f, _ptr(cls), n))
+        return cls[:n]
+
+    def labels_range(self, f0: int, f1: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        total = sum(self.frame_sizes[f0:f1])
+        if out is None:
+            out = np.zeros(max(total, 1), np.uint8)
+        _check(self._lib.scvod_labels_range(self._ctx, f0, f1, _ptr(out), ctypes.c_int64(out.size)))
+        return out[:total]
+
+    def frame_ground_order(self, f: int):
+        c = self.frame_counts(f)
+        g = np.zeros(max(int(c[1]), 1), np.int32)
+        ng = np.zeros(max(int(c[2]), 1), np.int32)
+        _check(self._lib.scvod_frame_ground_order(self._ctx, f, _ptr(g), _ptr(ng)))
+        return g[: c[1]], ng[: c[2]]
+
+    def frame_apri(self, f: int):
+        m = int(self.frame_counts(f)[3])
+        src = np.zeros(max(m, 1), np.int32)
+        vid = np.zeros(max(m, 1), np.int32)
+        _check(self._lib.scvod_frame_apri(self._ctx, f, _ptr(src), _ptr(vid)))
+        return src[:m], vid[:m]
+
+    def frame_voxels(self, f: int) -> dict:
+        v = int(self.frame_counts(f)[4])
+        cap = max(v, 1)
+        out = {"voxel_idx": np.zeros(cap, np.int32), "count": np.zeros(cap, np.int32), "av": np.zeros(cap, np.float32),
+               "cov": np.zeros(cap, np.float32), "center": np.zeros((cap, 3), np.float32), "tri": np.zeros((cap, 3), np.int32),
+               "label": np.zeros(cap, np.int32)}
+        _check(self._lib.scvod_frame_voxels(self._ctx, f, _ptr(out["voxel_idx"]), _ptr(out["count"]), _ptr(out["av"]), _ptr(out["cov"]),
+                                            _ptr(out["center"]), _ptr(out["tri"]), _ptr(out["label"])))
+        return {k: a[:v] for k, a in out.items()}
+
+    def frame_point_cluster(self, f: int, stage: int) -> np.ndarray:
+        m = int(self.frame_counts(f)[3])
+        name = np.zeros(max(m, 1), np.int32)
+        _check(self._lib.scvod_frame_point_cluster(self._ctx, f, stage, _ptr(name)))
+        return name[:m]
+
+    def frame_clusters(self, f: int) -> dict:
+        cap = max(int(self.frame_counts(f)[8]), 1)
+        out = {"name": np.zeros(cap, np.int32), "type": np.zeros(cap, np.int32), "state": np.zeros(cap, np.int32),
+               "npts": np.zeros(cap, np.int32), "nvox": np.zeros(cap, np.int32), "bbox": np.zeros((cap, 6), np.float32)}
+        n = _check(self._lib.scvod_frame_clusters(self._ctx, f, cap, _ptr(out["name"]), _ptr(out["type"]), _ptr(out["state"]),
+                                                  _ptr(out["npts"]), _ptr(out["nvox"]), _ptr(out["bbox"])))
+        return {k: a[:n] for k, a in out.items()}
+
+    def static_submap_device(self, f0: int, f1: int, poses: np.ndarray, out_dev_ptr: int, cap_points: int) -> int:
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        n = ctypes.c_int64()
+        _check(self._lib.scvod_static_submap_dev(self._ctx, f0, f1, _ptr(poses), ctypes.c_void_p(out_dev_ptr), ctypes.c_int64(cap_points), ctypes.byref(n)))
+        return n.value

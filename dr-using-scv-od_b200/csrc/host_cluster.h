@@ -1,0 +1,65 @@
+// host_cluster.h — host-side mirror of the reference's cluster-level bookkeeping.
+//
+// The GPU produces everything that is per-point or per-voxel (ground labels, voxel indices, the
+// occupancy descriptor, voxel adjacency, connected components, similarity edges, re-binned tracking
+// hits).  What remains is the reference's *sequential* cluster logic, whose results depend on
+// libstdc++ container iteration order (std::unordered_map<int, Cluster>, reference include/utility.h:180;
+// SURVEY.md hard part 6).  It is kept on the host with the same containers and the same insertion
+// sequence as the reference so that cluster names, fusion order and tracking decisions come out
+// identical; the data it touches is O(voxels + clusters) per scan, not O(points).
+#pragma once
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/scvod.h"
+
+namespace scvod {
+
+struct P4 {
+  float x, y, z, w;
+};
+
+// Cluster (reference include/utility.h:142-162) at voxel granularity. Voxels are compact ids, which are
+// monotone in voxel_idx, so every sort / lexicographic comparison gives the reference's order.
+struct HCluster {
+  int track_id = -1, name = -1, type = -1, state = -1;
+  float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+  std::vector<int> occupy_voxels;
+  std::vector<int> part_end;    // ends (in occupy_voxels) of the initial CVC components concatenated by fusion
+  int npts = 0;                 // occupy_pts.size()
+  bool pts_valid = false;       // occupy_pts materialised (car clusters only)
+  std::vector<int> occupy_pts;  // apri indices, reference order
+  std::vector<P4> carried;      // transformed clouds appended by tracking (ssc.cpp:1382)
+};
+
+// per-scan inputs from the GPU (host copies)
+struct ScanTables {
+  int M = 0, V = 0, n_events = 0, n_edges = 0;
+  const int32_t* vox_cnt = nullptr;   // [V]
+  const int32_t* vox_root = nullptr;  // [V] CCL root (min compact id of the component)
+  const int32_t* vox_nbr = nullptr;   // [V][27]
+  const float* vox_bbox = nullptr;    // [V][6]
+  const int32_t* ev_cid = nullptr;    // [n_events]
+  const int32_t* edges = nullptr;     // [n_edges][2] (root_from, root_to)
+};
+
+struct FrameClusters {
+  int max_name = 0;
+  std::vector<int> vox_label;  // hash_cloud[v].label
+  std::unordered_map<int, HCluster> cluster_set;
+  int n_clusters[3] = {0, 0, 0};
+  std::vector<int> vox_name_stage[3];  // per-voxel cluster name after CVC / intensity refine / bbox refine (inspection)
+};
+
+// SSC::clusterAndCreateFrame + refineClusterByIntensity + refineClusterByBoundingBox + recognize
+// (reference src/ssc.cpp:299-393, 571-635, 437-467, 834-895) on the GPU-produced tables.
+// Returns false when the replayed partition disagrees with the GPU components (internal error).
+bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClusters& out, bool keep_stages);
+
+// trans_next.inverse() * trans_pre (ssc.cpp:1255-1257) — 12 floats, row-major 3x4
+void relative_pose(const float pose_next[6], const float pose_pre[6], float T[12]);
+// pcl::getTransformation(x,y,z,roll,pitch,yaw) as 12 floats
+void pose_matrix(const float pose[6], float T[12]);
+
+}  // namespace scvod

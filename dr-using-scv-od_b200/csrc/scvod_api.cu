@@ -1,0 +1,1058 @@
+// scvod_api.cu — the extern "C" layer declared in include/scvod.h: context, device memory, the batched
+// frame pipeline (GPU stages + host cluster bookkeeping) and the tracking chain.
+//
+// There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "host_cluster.h"
+#include "scvod_internal.h"
+
+using namespace scvod;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                             \
+  do {                                                                                                       \
+    cudaError_t e__ = (call);                                                                                \
+    if (e__ != cudaSuccess) return fail(SCVOD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// device data that must outlive the batch: what tracking, labelling, the submap and inspection read
+struct PersistBatch {
+  int nscans = 0;
+  int64_t total = 0;
+  std::vector<int64_t> off;
+  DevBuf<float4> pts, apri_xyzi;
+  DevBuf<uint8_t> cls;
+  DevBuf<int32_t> apri_src, apri_cid, apri_vid, word_rank, vox_off, vox_pts, vox_cnt, ground_src, ng_src;
+  DevBuf<uint32_t> bitmap;
+  // inspection-only
+  DevBuf<int32_t> vox_vid, vox_tri;
+  DevBuf<float> vox_av, vox_cov, vox_center;
+  void release() {
+    pts.release();
+    apri_xyzi.release();
+    cls.release();
+    apri_src.release();
+    apri_cid.release();
+    apri_vid.release();
+    word_rank.release();
+    vox_off.release();
+    vox_pts.release();
+    vox_cnt.release();
+    ground_src.release();
+    ng_src.release();
+    bitmap.release();
+    vox_vid.release();
+    vox_tri.release();
+    vox_av.release();
+    vox_cov.release();
+    vox_center.release();
+  }
+};
+
+struct FrameHost {
+  int batch = -1, slot = -1;
+  int64_t base = 0;
+  int n_in = 0, n_ground = 0, n_ng = 0, n_apri = 0, n_vox = 0;
+  FrameClusters fc;
+  std::vector<int32_t> vox_cnt;
+  // lazily fetched CSR (tracking splits / car point lists)
+  bool have_csr = false;
+  std::vector<int32_t> vox_off, vox_pts;
+  bool labels_current = false;
+};
+
+}  // namespace
+
+struct scvod_ctx {
+  HostParams hp;
+  int device = 0;
+  int max_points = 0, max_batch = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  int host_threads = 1;
+  bool inspect = true;
+
+  BatchDev ws;  // transient workspace (pointers into the DevBufs below and into the current PersistBatch)
+  DevBuf<int64_t> d_off;
+  DevBuf<int16_t> d_patch_of, d_slot_patch;
+  DevBuf<int32_t> d_patch_cnt, d_patch_off, d_patch_cur, d_sorted_idx, d_slot_pos, d_slot_apos, d_slot_vid, d_patch_out,
+      d_patch_out_off, d_scan_counts, d_apri_rank, d_vox_cur, d_vox_pts_tmp, d_vox_nbr, d_vox_root, d_ev_cid, d_edge_buf;
+  DevBuf<uint64_t> d_bucket_kv, d_edge_hash;
+  DevBuf<float> d_patch_dbg, d_vox_bbox, d_T;
+  // pinned host mirrors of what the host logic reads per batch
+  PinBuf<int32_t> h_scan_counts, h_vox_cnt, h_vox_root, h_vox_nbr, h_ev_cid, h_edge_buf;
+  PinBuf<float> h_vox_bbox;
+  // tracking buffers
+  DevBuf<int32_t> d_sel, d_hit;
+  DevBuf<float4> d_carried, d_tout;
+  PinBuf<int32_t> h_sel, h_hit;
+  PinBuf<P4> h_carried, h_tout;
+  DevBuf<uint8_t> d_vox_cls;
+  PinBuf<uint8_t> h_vox_cls;
+  DevBuf<unsigned long long> d_counter;
+
+  std::vector<std::unique_ptr<PersistBatch>> batches;
+  std::vector<FrameHost> frames;
+  int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
+  int track_name = 0;  // SSC::name (ssc.h:49)
+};
+
+static void params_common(scvod_params* p) {
+  // Utility() defaults (reference include/utility.h:283-313) for keys a YAML file may omit
+  p->sensor_height = 2.0f;
+  p->min_dis = 0.0f;
+  p->max_dis = 50.0f;
+  p->min_angle = 0.0f;
+  p->max_angle = 360.0f;
+  p->min_azimuth = -30.0f;
+  p->max_azimuth = 60.0f;
+  p->range_res = 0.2f;
+  p->sector_res = 1.2f;
+  p->azimuth_res = 2.0f;
+  p->refine_height = -1.0f;
+  p->max_z = 1.0f;
+  p->min_z = -1.0f;
+  p->car_square = 2.0f;
+  p->iteration = 3;
+  p->toBeClass = 1;
+  p->search_c = 2;
+  p->intensity_diff = 50.f;
+  p->intensity_cov = 20.f;
+  p->occupancy = 0.6f;
+  p->building = 0;
+  p->tree = 1;
+  p->car = 2;
+}
+
+extern "C" void scvod_params_semantickitti(scvod_params* p) {  // reference config/semantickitti.yaml:24-53
+  params_common(p);
+  p->sensor_height = 1.73f;
+  p->refine_height = -0.2f;
+  p->max_z = 0.8f;
+  p->min_z = -1.2f;
+  p->car_square = 30.0f;
+  p->min_dis = 1.5f;
+  p->max_dis = 30.0f;
+  p->min_angle = 0.0f;
+  p->max_angle = 360.0f;
+  p->min_azimuth = -40.0f;
+  p->max_azimuth = 80.0f;
+  p->range_res = 0.4f;
+  p->sector_res = 1.2f;
+  p->azimuth_res = 2.0f;
+  p->iteration = 3;
+  p->toBeClass = 10;
+  p->search_c = 2;
+  p->intensity_diff = 2.0f;
+  p->intensity_cov = 1.0f;
+  p->occupancy = 0.4f;
+}
+
+extern "C" void scvod_params_parkinglot(scvod_params* p) {  // reference config/parkinglot.yaml:23-50 (+ utility.h defaults)
+  params_common(p);
+  p->sensor_height = 1.83f;
+  p->min_dis = 0.8f;
+  p->max_dis = 40.0f;
+  p->min_angle = 0.0f;
+  p->max_angle = 360.0f;
+  p->min_azimuth = -30.0f;
+  p->max_azimuth = 60.0f;
+  p->range_res = 0.4f;
+  p->sector_res = 1.2f;
+  p->azimuth_res = 2.0f;
+  p->iteration = 3;
+  p->toBeClass = 6;
+  p->search_c = 2;
+  p->intensity_diff = 2.0f;
+  p->intensity_cov = 1.0f;
+  p->occupancy = 0.8f;
+}
+
+extern "C" int scvod_grid_dims(const scvod_params* p, scvod_grid* g) {  // reference src/ssc.cpp:36-39 (float arithmetic)
+  if (!p || !g) return fail(SCVOD_ERR_ARG, "null argument");
+  g->range_num = (int)std::ceil((p->max_dis - p->min_dis) / p->range_res);
+  g->sector_num = (int)std::ceil((p->max_angle - p->min_angle) / p->sector_res);
+  g->azimuth_num = (int)std::ceil((p->max_azimuth - p->min_azimuth) / p->azimuth_res);
+  g->bin_num = g->range_num * g->sector_num * g->azimuth_num;
+  return SCVOD_OK;
+}
+
+extern "C" const char* scvod_last_error(void) { return g_err.c_str(); }
+
+extern "C" void scvod_relative_pose(const float pose_next6[6], const float pose_pre6[6], float T[12]) {
+  relative_pose(pose_next6, pose_pre6, T);
+}
+
+static int alloc_workspace(scvod_ctx* c) {
+  const size_t P = (size_t)c->max_points * c->max_batch;  // total points per batch
+  const size_t S = (size_t)c->max_batch;
+  BatchDev& w = c->ws;
+  w.cap_points = (int)P;
+  w.cap_scans = (int)S;
+  w.edge_cap = 16384;
+  w.hash_cap = 65536;
+  CU(c->d_off.alloc(S + 1));
+  CU(c->d_patch_of.alloc(P));
+  CU(c->d_slot_patch.alloc(P));
+  CU(c->d_patch_cnt.alloc(S * kNumPatches));
+  CU(c->d_patch_off.alloc(S * (kNumPatches + 1)));
+  CU(c->d_patch_cur.alloc(S * kNumPatches));
+  CU(c->d_bucket_kv.alloc(P));
+  CU(c->d_sorted_idx.alloc(P));
+  CU(c->d_slot_pos.alloc(P));
+  CU(c->d_slot_apos.alloc(P));
+  CU(c->d_slot_vid.alloc(P));
+  CU(c->d_patch_out.alloc(S * kNumPatches * 4));
+  CU(c->d_patch_out_off.alloc(S * (kNumPatches + 1) * 3));
+  CU(c->d_patch_dbg.alloc(S * kNumPatches * 12));
+  CU(c->d_scan_counts.alloc(S * 8 + 8));
+  CU(c->d_apri_rank.alloc(P));
+  CU(c->d_vox_cur.alloc(P));
+  CU(c->d_vox_pts_tmp.alloc(P));
+  CU(c->d_vox_nbr.alloc(P * 27));
+  CU(c->d_vox_root.alloc(P));
+  CU(c->d_vox_bbox.alloc(P * 6));
+  CU(c->d_ev_cid.alloc(P));
+  CU(c->d_edge_buf.alloc(S * w.edge_cap * 2));
+  CU(c->d_edge_hash.alloc(S * w.hash_cap));
+  CU(c->d_T.alloc(16));
+  CU(c->d_counter.alloc(1));
+  w.off = c->d_off.p;
+  w.patch_of = c->d_patch_of.p;
+  w.slot_patch = c->d_slot_patch.p;
+  w.patch_cnt = c->d_patch_cnt.p;
+  w.patch_off = c->d_patch_off.p;
+  w.patch_cur = c->d_patch_cur.p;
+  w.bucket_kv = c->d_bucket_kv.p;
+  w.sorted_idx = c->d_sorted_idx.p;
+  w.slot_pos = c->d_slot_pos.p;
+  w.slot_apos = c->d_slot_apos.p;
+  w.slot_vid = c->d_slot_vid.p;
+  w.patch_out = c->d_patch_out.p;
+  w.patch_out_off = c->d_patch_out_off.p;
+  w.patch_dbg = c->d_patch_dbg.p;
+  w.scan_counts = c->d_scan_counts.p;
+  w.apri_rank = c->d_apri_rank.p;
+  w.vox_cur = c->d_vox_cur.p;
+  w.vox_pts_tmp = c->d_vox_pts_tmp.p;
+  w.vox_nbr = c->d_vox_nbr.p;
+  w.vox_root = c->d_vox_root.p;
+  w.vox_bbox = c->d_vox_bbox.p;
+  w.ev_cid = c->d_ev_cid.p;
+  w.edge_buf = c->d_edge_buf.p;
+  w.edge_hash = reinterpret_cast<int32_t*>(c->d_edge_hash.p);
+  CU(c->h_scan_counts.alloc(S * 8 + 8));
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_create(const scvod_params* p, int device, int max_points, int max_batch, scvod_ctx** out) {
+  if (!p || !out || max_points <= 0 || max_batch <= 0) return fail(SCVOD_ERR_ARG, "bad arguments to scvod_create");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return fail(SCVOD_ERR_CUDA, "no CUDA device: the SCV-OD path has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SCVOD_ERR_ARG, "device index out of range");
+  CU(cudaSetDevice(device));
+  std::unique_ptr<scvod_ctx> c(new scvod_ctx());
+  c->hp.p = *p;
+  scvod_grid g;
+  scvod_grid_dims(p, &g);
+  c->hp.g.range_num = g.range_num;
+  c->hp.g.sector_num = g.sector_num;
+  c->hp.g.azimuth_num = g.azimuth_num;
+  c->hp.g.bin_num = g.bin_num;
+  c->hp.g.key_off = g.range_num * g.sector_num + g.sector_num + 1;  // all three indices == -1 (ssc.cpp:185-188)
+  c->hp.g.key_count = g.bin_num + c->hp.g.key_off;
+  c->hp.g.words = (c->hp.g.key_count + 31) / 32;
+  c->device = device;
+  c->max_points = max_points;
+  c->max_batch = max_batch;
+  unsigned hc = std::thread::hardware_concurrency();
+  c->host_threads = hc ? (int)std::min<unsigned>(hc, 32u) : 4;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  int rc = alloc_workspace(c.get());
+  if (rc != SCVOD_OK) return rc;
+  *out = c.release();
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_destroy(scvod_ctx* c) {
+  if (!c) return SCVOD_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->batches)
+    if (b) b->release();
+  c->d_off.release(); c->d_patch_of.release(); c->d_slot_patch.release(); c->d_patch_cnt.release(); c->d_patch_off.release();
+  c->d_patch_cur.release(); c->d_sorted_idx.release(); c->d_slot_pos.release(); c->d_slot_apos.release(); c->d_slot_vid.release();
+  c->d_patch_out.release(); c->d_patch_out_off.release(); c->d_scan_counts.release(); c->d_apri_rank.release(); c->d_vox_cur.release();
+  c->d_vox_pts_tmp.release(); c->d_vox_nbr.release(); c->d_vox_root.release(); c->d_ev_cid.release(); c->d_edge_buf.release();
+  c->d_bucket_kv.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
+  c->h_scan_counts.release(); c->h_vox_cnt.release(); c->h_vox_root.release(); c->h_vox_nbr.release(); c->h_ev_cid.release();
+  c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_sel.release(); c->d_hit.release(); c->d_carried.release(); c->d_tout.release();
+  c->h_sel.release(); c->h_hit.release(); c->h_carried.release(); c->h_tout.release(); c->d_vox_cls.release(); c->h_vox_cls.release();
+  c->d_counter.release();
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_num_kernel_launches(const scvod_ctx* c, int64_t* out) {
+  if (!c || !out) return fail(SCVOD_ERR_ARG, "null argument");
+  *out = c->launches;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_set_option(scvod_ctx* c, const char* key, int value) {
+  if (!c || !key) return fail(SCVOD_ERR_ARG, "null argument");
+  std::string k(key);
+  if (k == "inspect")
+    c->inspect = value != 0;
+  else if (k == "host_threads")
+    c->host_threads = std::max(1, value);
+  else
+    return fail(SCVOD_ERR_ARG, "unknown option " + k);
+  return SCVOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched frame pipeline
+// ---------------------------------------------------------------------------------------------
+static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int64_t* offsets, int nscans) {
+  cudaStream_t st = c->stream;
+  const int64_t total = offsets[nscans] - offsets[0];
+  int max_n = 0;
+  std::vector<int64_t> off(nscans + 1);
+  for (int s = 0; s <= nscans; ++s) off[s] = offsets[s] - offsets[0];
+  for (int s = 0; s < nscans; ++s) {
+    int64_t n = off[s + 1] - off[s];
+    if (n < 0 || n > c->max_points) return fail(SCVOD_ERR_CAPACITY, "scan larger than max_points");
+    max_n = std::max<int>(max_n, (int)n);
+  }
+  if (total > (int64_t)c->ws.cap_points) return fail(SCVOD_ERR_CAPACITY, "batch larger than workspace");
+
+  std::unique_ptr<PersistBatch> pb(new PersistBatch());
+  pb->nscans = nscans;
+  pb->total = total;
+  pb->off = off;
+  const size_t T = (size_t)std::max<int64_t>(total, 1);
+  CU(pb->pts.alloc(T));
+  CU(pb->apri_xyzi.alloc(T));
+  CU(pb->cls.alloc(T));
+  CU(pb->apri_src.alloc(T));
+  CU(pb->apri_cid.alloc(T));
+  CU(pb->apri_vid.alloc(T));
+  CU(pb->vox_off.alloc(T));
+  CU(pb->vox_pts.alloc(T));
+  CU(pb->vox_cnt.alloc(T));
+  CU(pb->ground_src.alloc(T));
+  CU(pb->ng_src.alloc(T));
+  CU(pb->bitmap.alloc((size_t)nscans * c->hp.g.words));
+  CU(pb->word_rank.alloc((size_t)nscans * c->hp.g.words));
+  CU(pb->vox_vid.alloc(T));
+  CU(pb->vox_tri.alloc(3 * T));
+  CU(pb->vox_av.alloc(T));
+  CU(pb->vox_cov.alloc(T));
+  CU(pb->vox_center.alloc(3 * T));
+
+  BatchDev& w = c->ws;
+  w.pts = pb->pts.p;
+  w.apri_xyzi = pb->apri_xyzi.p;
+  w.cls = pb->cls.p;
+  w.apri_src = pb->apri_src.p;
+  w.apri_cid = pb->apri_cid.p;
+  w.apri_vid = pb->apri_vid.p;
+  w.vox_off = pb->vox_off.p;
+  w.vox_pts = pb->vox_pts.p;
+  w.vox_cnt = pb->vox_cnt.p;
+  w.ground_src = pb->ground_src.p;
+  w.ng_src = pb->ng_src.p;
+  w.bitmap = pb->bitmap.p;
+  w.word_rank = pb->word_rank.p;
+  w.vox_vid = pb->vox_vid.p;
+  w.vox_tri = pb->vox_tri.p;
+  w.vox_av = pb->vox_av.p;
+  w.vox_cov = pb->vox_cov.p;
+  w.vox_center = pb->vox_center.p;
+
+  CU(cudaMemcpyAsync(w.off, off.data(), sizeof(int64_t) * (nscans + 1), cudaMemcpyHostToDevice, st));
+  if (total > 0)
+    CU(cudaMemcpyAsync(w.pts, (const char*)xyzi + sizeof(float) * 4 * offsets[0], sizeof(float4) * total,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(w.scan_counts, 0, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), st));
+  c->launches += launch_ground(c->hp, w, nscans, max_n, st);
+  c->launches += launch_descriptor(c->hp, w, nscans, max_n, st);
+  c->launches += launch_cluster_prep(c->hp, w, nscans, max_n, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_scan_counts.p, w.scan_counts, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int32_t* sc = c->h_scan_counts.p;
+  if (sc[(size_t)w.cap_scans * 8] & 1) return fail(SCVOD_ERR_CAPACITY, "a PatchWork patch holds more points than the largest fit tile");
+
+  // per-scan table sizes -> packed host copies
+  std::vector<int64_t> vbase(nscans + 1, 0), ebase(nscans + 1, 0), gbase(nscans + 1, 0);
+  for (int s = 0; s < nscans; ++s) {
+    int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
+    if (G < 0 || G > w.edge_cap) return fail(SCVOD_ERR_CAPACITY, "similarity edge table overflow");
+    if (sc[s * 8 + 4] > 0)
+      return fail(SCVOD_ERR_STATE,
+                  "scan contains points whose curved-voxel index is -1 (range==min_dis, angle==0 or azimuth==min_azimuth): "
+                  "clustering of aliased voxels is not supported yet");
+    vbase[s + 1] = vbase[s] + V;
+    ebase[s + 1] = ebase[s] + E;
+    gbase[s + 1] = gbase[s] + G;
+  }
+  CU(c->h_vox_cnt.alloc(std::max<int64_t>(1, vbase[nscans])));
+  CU(c->h_vox_root.alloc(std::max<int64_t>(1, vbase[nscans])));
+  CU(c->h_vox_nbr.alloc(std::max<int64_t>(1, vbase[nscans] * 27)));
+  CU(c->h_vox_bbox.alloc(std::max<int64_t>(1, vbase[nscans] * 6)));
+  CU(c->h_ev_cid.alloc(std::max<int64_t>(1, ebase[nscans])));
+  CU(c->h_edge_buf.alloc(std::max<int64_t>(1, gbase[nscans] * 2)));
+  for (int s = 0; s < nscans; ++s) {
+    int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
+    int64_t b = off[s];
+    if (V > 0) {
+      CU(cudaMemcpyAsync(c->h_vox_cnt.p + vbase[s], w.vox_cnt + b, sizeof(int32_t) * V, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(c->h_vox_root.p + vbase[s], w.vox_root + b, sizeof(int32_t) * V, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(c->h_vox_nbr.p + vbase[s] * 27, w.vox_nbr + b * 27, sizeof(int32_t) * V * 27, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(c->h_vox_bbox.p + vbase[s] * 6, w.vox_bbox + b * 6, sizeof(float) * V * 6, cudaMemcpyDeviceToHost, st));
+    }
+    if (E > 0) CU(cudaMemcpyAsync(c->h_ev_cid.p + ebase[s], w.ev_cid + b, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, st));
+    if (G > 0)
+      CU(cudaMemcpyAsync(c->h_edge_buf.p + gbase[s] * 2, w.edge_buf + (size_t)s * w.edge_cap * 2, sizeof(int32_t) * G * 2,
+                         cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+
+  // host cluster bookkeeping, one scan per task
+  const int batch_id = (int)c->batches.size();
+  const size_t f0 = c->frames.size();
+  c->frames.resize(f0 + nscans);
+  std::atomic<int> next(0);
+  std::atomic<int> bad(0);
+  auto worker = [&]() {
+    for (;;) {
+      int s = next.fetch_add(1);
+      if (s >= nscans) break;
+      FrameHost& fr = c->frames[f0 + s];
+      fr.batch = batch_id;
+      fr.slot = s;
+      fr.base = off[s];
+      fr.n_in = (int)(off[s + 1] - off[s]);
+      fr.n_ground = sc[s * 8 + 0];
+      fr.n_ng = sc[s * 8 + 1];
+      fr.n_apri = sc[s * 8 + 2];
+      fr.n_vox = sc[s * 8 + 3];
+      ScanTables t;
+      t.M = fr.n_apri;
+      t.V = fr.n_vox;
+      t.n_events = sc[s * 8 + 5];
+      t.n_edges = sc[s * 8 + 7];
+      t.vox_cnt = c->h_vox_cnt.p + vbase[s];
+      t.vox_root = c->h_vox_root.p + vbase[s];
+      t.vox_nbr = c->h_vox_nbr.p + vbase[s] * 27;
+      t.vox_bbox = c->h_vox_bbox.p + vbase[s] * 6;
+      t.ev_cid = c->h_ev_cid.p + ebase[s];
+      t.edges = c->h_edge_buf.p + gbase[s] * 2;
+      fr.vox_cnt.assign(t.vox_cnt, t.vox_cnt + t.V);
+      if (!segment_and_recognize(c->hp.p, t, fr.fc, c->inspect)) bad.store(1);
+    }
+  };
+  int nt = std::min(c->host_threads, nscans);
+  if (nt <= 1) {
+    worker();
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < nt; ++i) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+  }
+  c->batches.push_back(std::move(pb));
+  if (bad.load()) return fail(SCVOD_ERR_STATE, "internal: replayed cluster partition differs from the GPU components");
+  return SCVOD_OK;
+}
+
+static int push_scans_impl(scvod_ctx* c, const void* xyzi, bool on_device, const int64_t* offsets, int nscans) {
+  if (!c || !offsets || nscans < 0 || (!xyzi && nscans > 0 && offsets[nscans] > offsets[0]))
+    return fail(SCVOD_ERR_ARG, "bad arguments to scvod_push_scans");
+  CU(cudaSetDevice(c->device));
+  int s = 0;
+  while (s < nscans) {
+    int e = s;
+    int64_t pts = 0;
+    while (e < nscans && (e - s) < c->max_batch && pts + (offsets[e + 1] - offsets[e]) <= (int64_t)c->ws.cap_points) {
+      pts += offsets[e + 1] - offsets[e];
+      ++e;
+    }
+    if (e == s) return fail(SCVOD_ERR_CAPACITY, "scan larger than the batch workspace");
+    int rc = push_batch(c, xyzi, on_device, offsets + s, e - s);
+    if (rc != SCVOD_OK) return rc;
+    s = e;
+  }
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_push_scans(scvod_ctx* c, const float* xyzi, const int64_t* offsets, int nscans) {
+  return push_scans_impl(c, xyzi, false, offsets, nscans);
+}
+extern "C" int scvod_push_scans_dev(scvod_ctx* c, const void* xyzi_dev, const int64_t* offsets, int nscans) {
+  return push_scans_impl(c, xyzi_dev, true, offsets, nscans);
+}
+
+extern "C" int scvod_num_frames(const scvod_ctx* c) { return c ? (int)c->frames.size() : 0; }
+
+extern "C" int scvod_reset_frames(scvod_ctx* c) {
+  if (!c) return fail(SCVOD_ERR_ARG, "null ctx");
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->batches)
+    if (b) b->release();
+  c->batches.clear();
+  c->frames.clear();
+  c->tracked = 0;
+  c->track_name = 0;
+  return SCVOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tracking (SSC::tracking, reference src/ssc.cpp:1250-1426)
+// ---------------------------------------------------------------------------------------------
+static int fetch_csr(scvod_ctx* c, FrameHost& fr) {
+  if (fr.have_csr) return SCVOD_OK;
+  PersistBatch& pb = *c->batches[fr.batch];
+  fr.vox_off.resize(fr.n_vox + 1);
+  fr.vox_pts.resize(std::max(1, fr.n_apri));
+  if (fr.n_vox > 0) CU(cudaMemcpyAsync(fr.vox_off.data(), pb.vox_off.p + fr.base, sizeof(int32_t) * fr.n_vox, cudaMemcpyDeviceToHost, c->stream));
+  if (fr.n_apri > 0) CU(cudaMemcpyAsync(fr.vox_pts.data(), pb.vox_pts.p + fr.base, sizeof(int32_t) * fr.n_apri, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  fr.vox_off[fr.n_vox] = fr.n_apri;
+  fr.have_csr = true;
+  return SCVOD_OK;
+}
+
+// occupy_pts of a cluster in the reference's order: each initial CVC component contributes its points in
+// ascending apri index (ssc.cpp:360-380); fusion concatenates components (ssc.cpp:617).
+static void materialise_pts(const FrameHost& fr, HCluster& cl) {
+  if (cl.pts_valid) return;
+  cl.occupy_pts.clear();
+  int start = 0;
+  for (int pe : cl.part_end) {
+    size_t b0 = cl.occupy_pts.size();
+    for (int i = start; i < pe; ++i) {
+      int v = cl.occupy_voxels[i];
+      cl.occupy_pts.insert(cl.occupy_pts.end(), fr.vox_pts.begin() + fr.vox_off[v], fr.vox_pts.begin() + fr.vox_off[v + 1]);
+    }
+    std::sort(cl.occupy_pts.begin() + b0, cl.occupy_pts.end());
+    start = pe;
+  }
+  cl.pts_valid = true;
+}
+
+static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float* pose_pre, const float* pose_next) {
+  const scvod_params& P = c->hp.p;
+  float T[12];
+  relative_pose(pose_next, pose_pre, T);
+  int rc = fetch_csr(c, pre);
+  if (rc) return rc;
+  // car clusters of frame_pre_ in cluster_set order (ssc.cpp:1261-1264)
+  std::vector<HCluster*> cars;
+  for (auto& cs : pre.fc.cluster_set)
+    if (cs.second.type == P.car) cars.push_back(&cs.second);
+  size_t K = 0, KC = 0;
+  for (HCluster* cl : cars) {
+    materialise_pts(pre, *cl);
+    K += cl->occupy_pts.size() + cl->carried.size();
+    KC += cl->carried.size();
+  }
+  std::vector<size_t> cstart(cars.size() + 1, 0);
+  if (K > 0) {
+    CU(c->h_sel.alloc(K));
+    CU(c->h_hit.alloc(K));
+    CU(c->h_tout.alloc(K));
+    CU(c->h_carried.alloc(std::max<size_t>(KC, 1)));
+    CU(c->d_sel.alloc(K));
+    CU(c->d_hit.alloc(K));
+    CU(c->d_tout.alloc(K));
+    CU(c->d_carried.alloc(std::max<size_t>(KC, 1)));
+    size_t k = 0, kc = 0;
+    for (size_t i = 0; i < cars.size(); ++i) {
+      cstart[i] = k;
+      for (int m : cars[i]->occupy_pts) c->h_sel.p[k++] = m;
+      for (const P4& q : cars[i]->carried) {
+        c->h_carried.p[kc] = q;
+        c->h_sel.p[k++] = -1 - (int)kc;
+        ++kc;
+      }
+    }
+    cstart[cars.size()] = k;
+    PersistBatch& pbp = *c->batches[pre.batch];
+    PersistBatch& pbn = *c->batches[next.batch];
+    CU(cudaMemcpyAsync(c->d_T.p, T, sizeof(float) * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_sel.p, c->h_sel.p, sizeof(int32_t) * K, cudaMemcpyHostToDevice, c->stream));
+    if (KC) CU(cudaMemcpyAsync(c->d_carried.p, c->h_carried.p, sizeof(P4) * KC, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, c->d_carried.p, c->d_sel.p, (int)K, c->d_T.p,
+                                pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words,
+                                c->d_tout.p, c->d_hit.p, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_hit.p, c->d_hit.p, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_tout.p, c->d_tout.p, sizeof(P4) * K, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+
+  std::vector<int>& nlabel = next.fc.vox_label;
+  auto& nset = next.fc.cluster_set;
+  for (size_t ci = 0; ci < cars.size(); ++ci) {
+    HCluster& cc = *cars[ci];
+    if (cc.type != P.car) continue;  // (type is only rewritten for the cluster being processed)
+    if (cc.track_id == -1) {
+      cc.track_id = c->track_name;
+      c->track_name++;
+    }
+    std::unordered_map<int, std::vector<int>> remap_name;  // label -> hit voxels (ssc.cpp:1277-1317)
+    for (size_t k = cstart[ci]; k < cstart[ci + 1]; ++k) {
+      int v = c->h_hit.p[k];
+      if (v < 0) continue;
+      int lab = nlabel[v];
+      if (lab == -1) continue;
+      auto l_find = remap_name.find(lab);
+      if (l_find == remap_name.end()) {
+        std::vector<int> vec;
+        vec.emplace_back(v);
+        remap_name.insert(std::make_pair(lab, vec));
+      } else {
+        l_find->second.emplace_back(v);
+      }
+    }
+    for (auto& re : remap_name) {
+      std::sort(re.second.begin(), re.second.end());
+      re.second.erase(std::unique(re.second.begin(), re.second.end()), re.second.end());
+    }
+    if (remap_name.size() == 0) {
+      cc.state = 1;
+    } else if (remap_name.size() == 1) {
+      auto it = remap_name.begin();
+      float ratio = (float)it->second.size() / (float)nset[it->first].occupy_voxels.size();
+      if (ratio < P.occupancy) {
+        if (nset[it->first].type == P.car) {
+          cc.state = 1;
+        } else {
+          cc.state = 0;
+          cc.type = nset[it->first].type;
+          HCluster cluster_new;
+          cluster_new.track_id = cc.track_id;
+          cluster_new.name = next.fc.max_name++;
+          cluster_new.type = nset[it->first].type;
+          cluster_new.occupy_voxels = it->second;
+          HCluster& src = nset[it->first];
+          for (int v : cluster_new.occupy_voxels) {  // reduceVec (utility.h:445-450)
+            src.occupy_voxels.erase(std::remove(src.occupy_voxels.begin(), src.occupy_voxels.end(), v), src.occupy_voxels.end());
+          }
+          int np = 0;
+          for (int v : it->second) {
+            nlabel[v] = cluster_new.name;
+            np += next.vox_cnt[v];
+            cluster_new.part_end.push_back((int)cluster_new.part_end.size() + 1);  // one voxel per part: ptIdx order (ssc.cpp:1367)
+          }
+          cluster_new.npts = np;
+          src.npts -= np;
+          src.part_end.clear();  // point order of a split non-car cluster is never read again
+          src.part_end.push_back((int)src.occupy_voxels.size());
+          nset.insert(std::make_pair(cluster_new.name, cluster_new));
+        }
+      } else {
+        if (nset[it->first].type == P.car) {
+          cc.state = 0;
+          HCluster& dst = nset[it->first];
+          dst.track_id = cc.track_id;
+          const P4* tp = c->h_tout.p + cstart[ci];
+          dst.carried.insert(dst.carried.end(), tp, tp + (cstart[ci + 1] - cstart[ci]));  // *cloud += *cluster (ssc.cpp:1382)
+        }
+      }
+    } else {
+      cc.state = 0;
+      HCluster cluster_new;
+      cluster_new.track_id = cc.track_id;
+      cluster_new.name = next.fc.max_name++;
+      cluster_new.type = P.car;
+      rc = fetch_csr(c, next);
+      if (rc) return rc;
+      cluster_new.pts_valid = true;
+      for (auto& re : remap_name) {
+        if (nset[re.first].type == P.car &&
+            ((float)re.second.size() / (float)nset[re.first].occupy_voxels.size()) >= P.occupancy) {
+          HCluster& src = nset[re.first];
+          materialise_pts(next, src);
+          cluster_new.occupy_pts.insert(cluster_new.occupy_pts.end(), src.occupy_pts.begin(), src.occupy_pts.end());
+          cluster_new.occupy_voxels.insert(cluster_new.occupy_voxels.end(), src.occupy_voxels.begin(), src.occupy_voxels.end());
+          cluster_new.npts += src.npts;
+          nset.erase(re.first);
+        }
+      }
+      cluster_new.part_end.push_back((int)cluster_new.occupy_voxels.size());
+      for (int v : cluster_new.occupy_voxels) nlabel[v] = cluster_new.name;
+      nset.insert(std::make_pair(cluster_new.name, cluster_new));
+    }
+  }
+  pre.labels_current = false;
+  next.labels_current = false;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
+  if (!c || !poses6) return fail(SCVOD_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int nf = std::min<int>((int)c->frames.size(), nposes);
+  for (int i = c->tracked; i + 1 < nf; ++i) {
+    int rc = track_pair(c, c->frames[i], c->frames[i + 1], poses6 + 6 * i, poses6 + 6 * (i + 1));
+    if (rc) return rc;
+    c->tracked = i + 1;
+  }
+  return SCVOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// labels
+// ---------------------------------------------------------------------------------------------
+static int refresh_labels(scvod_ctx* c, int f) {
+  FrameHost& fr = c->frames[f];
+  if (fr.labels_current) return SCVOD_OK;
+  PersistBatch& pb = *c->batches[fr.batch];
+  const int V = std::max(1, fr.n_vox);
+  CU(c->h_vox_cls.alloc(V));
+  CU(c->d_vox_cls.alloc(V));
+  std::memset(c->h_vox_cls.p, SCVOD_PT_UNCLUSTERED, V);
+  for (auto& cs : fr.fc.cluster_set) {
+    uint8_t v = (cs.second.state == 1) ? SCVOD_PT_DYNAMIC : SCVOD_PT_STATIC;
+    for (int vx : cs.second.occupy_voxels) c->h_vox_cls.p[vx] = v;
+  }
+  CU(cudaMemcpyAsync(c->d_vox_cls.p, c->h_vox_cls.p, V, cudaMemcpyHostToDevice, c->stream));
+  c->launches += launch_final_labels(pb.apri_src.p + fr.base, pb.apri_cid.p + fr.base, c->d_vox_cls.p, fr.n_apri, pb.cls.p + fr.base, c->stream);
+  CU(cudaGetLastError());
+  fr.labels_current = true;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_labels(scvod_ctx* c, int frame, uint8_t* cls, int n) {
+  if (!c || !cls || frame < 0 || frame >= (int)c->frames.size()) return fail(SCVOD_ERR_ARG, "bad frame index");
+  CU(cudaSetDevice(c->device));
+  FrameHost& fr = c->frames[frame];
+  if (n < fr.n_in) return fail(SCVOD_ERR_ARG, "label buffer too small");
+  int rc = refresh_labels(c, frame);
+  if (rc) return rc;
+  PersistBatch& pb = *c->batches[fr.batch];
+  if (fr.n_in > 0) CU(cudaMemcpyAsync(cls, pb.cls.p + fr.base, fr.n_in, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SCVOD_OK;
+}
+
+// labels of frames [f0,f1) into one host buffer (concatenated in frame order)
+extern "C" int scvod_labels_range(scvod_ctx* c, int f0, int f1, uint8_t* cls, int64_t cap) {
+  if (!c || !cls || f0 < 0 || f1 > (int)c->frames.size() || f0 > f1) return fail(SCVOD_ERR_ARG, "bad frame range");
+  CU(cudaSetDevice(c->device));
+  int64_t pos = 0;
+  for (int f = f0; f < f1; ++f) {
+    FrameHost& fr = c->frames[f];
+    if (pos + fr.n_in > cap) return fail(SCVOD_ERR_ARG, "label buffer too small");
+    int rc = refresh_labels(c, f);
+    if (rc) return rc;
+    PersistBatch& pb = *c->batches[fr.batch];
+    if (fr.n_in > 0) CU(cudaMemcpyAsync(cls + pos, pb.cls.p + fr.base, fr.n_in, cudaMemcpyDeviceToHost, c->stream));
+    pos += fr.n_in;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float* poses6, void* out_xyzi_dev, int64_t cap_points,
+                                       int64_t* n_points) {
+  if (!c || !poses6 || !out_xyzi_dev || !n_points || f0 < 0 || f1 > (int)c->frames.size() || f0 > f1)
+    return fail(SCVOD_ERR_ARG, "bad arguments to scvod_static_submap_dev");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
+  for (int f = f0; f < f1; ++f) {
+    FrameHost& fr = c->frames[f];
+    int rc = refresh_labels(c, f);
+    if (rc) return rc;
+    float T[12];
+    pose_matrix(poses6 + 6 * f, T);
+    // d_T is reused per frame: stream order keeps each copy ahead of its kernel
+    CU(cudaMemcpyAsync(c->d_T.p, T, sizeof(float) * 12, cudaMemcpyHostToDevice, c->stream));
+    PersistBatch& pb = *c->batches[fr.batch];
+    c->launches += launch_submap(pb.pts.p + fr.base, pb.cls.p + fr.base, fr.n_in, c->d_T.p, (float4*)out_xyzi_dev, c->d_counter.p,
+                                 cap_points, c->stream);
+    CU(cudaStreamSynchronize(c->stream));  // T lives on the host stack
+  }
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, c->d_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *n_points = (int64_t)std::min<unsigned long long>(cnt, (unsigned long long)cap_points);
+  return cnt > (unsigned long long)cap_points ? fail(SCVOD_ERR_CAPACITY, "submap buffer too small") : SCVOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inspection
+// ---------------------------------------------------------------------------------------------
+#define FRAME_OR_FAIL()                                                                                  \
+  if (!c || frame < 0 || frame >= (int)c->frames.size()) return fail(SCVOD_ERR_ARG, "bad frame index"); \
+  CU(cudaSetDevice(c->device));                                                                          \
+  FrameHost& fr = c->frames[frame];                                                                      \
+  PersistBatch& pb = *c->batches[fr.batch];                                                              \
+  (void)pb;
+
+template <typename T>
+static int d2h(scvod_ctx* c, T* dst, const T* src, size_t n) {
+  if (!dst || n == 0) return SCVOD_OK;
+  CU(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost, c->stream));
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_counts(scvod_ctx* c, int frame, int32_t counts[9]) {
+  FRAME_OR_FAIL();
+  counts[0] = fr.n_in;
+  counts[1] = fr.n_ground;
+  counts[2] = fr.n_ng;
+  counts[3] = fr.n_apri;
+  counts[4] = fr.n_vox;
+  counts[5] = fr.fc.n_clusters[0];
+  counts[6] = fr.fc.n_clusters[1];
+  counts[7] = fr.fc.n_clusters[2];
+  counts[8] = (int)fr.fc.cluster_set.size();
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_ground_order(scvod_ctx* c, int frame, int32_t* ground_src, int32_t* nonground_src) {
+  FRAME_OR_FAIL();
+  int rc = d2h(c, ground_src, pb.ground_src.p + fr.base, fr.n_ground);
+  if (rc) return rc;
+  rc = d2h(c, nonground_src, pb.ng_src.p + fr.base, fr.n_ng);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_apri(scvod_ctx* c, int frame, int32_t* src, int32_t* voxel_idx) {
+  FRAME_OR_FAIL();
+  int rc = d2h(c, src, pb.apri_src.p + fr.base, fr.n_apri);
+  if (rc) return rc;
+  rc = d2h(c, voxel_idx, pb.apri_vid.p + fr.base, fr.n_apri);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_voxels(scvod_ctx* c, int frame, int32_t* voxel_idx, int32_t* count, float* av, float* cov, float* center,
+                                  int32_t* tri, int32_t* label) {
+  FRAME_OR_FAIL();
+  int rc = 0;
+  rc |= d2h(c, voxel_idx, pb.vox_vid.p + fr.base, fr.n_vox);
+  rc |= d2h(c, count, pb.vox_cnt.p + fr.base, fr.n_vox);
+  rc |= d2h(c, av, pb.vox_av.p + fr.base, fr.n_vox);
+  rc |= d2h(c, cov, pb.vox_cov.p + fr.base, fr.n_vox);
+  rc |= d2h(c, center, pb.vox_center.p + 3 * fr.base, (size_t)fr.n_vox * 3);
+  rc |= d2h(c, tri, pb.vox_tri.p + 3 * fr.base, (size_t)fr.n_vox * 3);
+  if (rc) return SCVOD_ERR_CUDA;
+  CU(cudaStreamSynchronize(c->stream));
+  if (label) std::memcpy(label, fr.fc.vox_label.data(), sizeof(int32_t) * fr.n_vox);
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_point_cluster(scvod_ctx* c, int frame, int stage, int32_t* name) {
+  FRAME_OR_FAIL();
+  if (stage < 0 || stage > 2 || !name) return fail(SCVOD_ERR_ARG, "bad stage");
+  if ((int)fr.fc.vox_name_stage[stage].size() != fr.n_vox) return fail(SCVOD_ERR_STATE, "stage names not kept (inspect option off)");
+  std::vector<int32_t> cid(std::max(1, fr.n_apri));
+  int rc = d2h(c, cid.data(), pb.apri_cid.p + fr.base, fr.n_apri);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  for (int m = 0; m < fr.n_apri; ++m) name[m] = cid[m] >= 0 ? fr.fc.vox_name_stage[stage][cid[m]] : -1;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_frame_clusters(scvod_ctx* c, int frame, int cap, int32_t* name, int32_t* type, int32_t* state, int32_t* npts,
+                                    int32_t* nvox, float* bbox) {
+  FRAME_OR_FAIL();
+  int i = 0;
+  for (auto& cs : fr.fc.cluster_set) {
+    if (i >= cap) break;
+    if (name) name[i] = cs.first;
+    if (type) type[i] = cs.second.type;
+    if (state) state[i] = cs.second.state;
+    if (npts) npts[i] = cs.second.npts;
+    if (nvox) nvox[i] = (int)cs.second.occupy_voxels.size();
+    if (bbox)
+      for (int d = 0; d < 3; ++d) {
+        bbox[6 * i + d] = cs.second.bb_min[d];
+        bbox[6 * i + 3 + d] = cs.second.bb_max[d];
+      }
+    ++i;
+  }
+  return (int)fr.fc.cluster_set.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-stage entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int scvod_ground(scvod_ctx* c, const float* xyzi, int n, int32_t* ground_idx, int32_t* n_ground, int32_t* nonground_idx,
+                            int32_t* n_nonground) {
+  if (!c || (!xyzi && n > 0) || !ground_idx || !n_ground || !nonground_idx || !n_nonground || n < 0)
+    return fail(SCVOD_ERR_ARG, "bad arguments to scvod_ground");
+  if (n > c->max_points) return fail(SCVOD_ERR_CAPACITY, "scan larger than max_points");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  DevBuf<float4> pts, apri_xyzi;
+  DevBuf<uint8_t> cls;
+  DevBuf<int32_t> apri_src, apri_vid, gsrc, ngsrc;
+  const size_t T = (size_t)std::max(n, 1);
+  CU(pts.alloc(T));
+  CU(apri_xyzi.alloc(T));
+  CU(cls.alloc(T));
+  CU(apri_src.alloc(T));
+  CU(apri_vid.alloc(T));
+  CU(gsrc.alloc(T));
+  CU(ngsrc.alloc(T));
+  BatchDev w = c->ws;
+  w.pts = pts.p;
+  w.apri_xyzi = apri_xyzi.p;
+  w.cls = cls.p;
+  w.apri_src = apri_src.p;
+  w.apri_vid = apri_vid.p;
+  w.ground_src = gsrc.p;
+  w.ng_src = ngsrc.p;
+  int64_t off[2] = {0, n};
+  CU(cudaMemcpyAsync(w.off, off, sizeof(off), cudaMemcpyHostToDevice, st));
+  if (n) CU(cudaMemcpyAsync(w.pts, xyzi, sizeof(float4) * n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(w.scan_counts, 0, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), st));
+  c->launches += launch_ground(c->hp, w, 1, n, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_scan_counts.p, w.scan_counts, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (c->h_scan_counts.p[(size_t)w.cap_scans * 8] & 1) return fail(SCVOD_ERR_CAPACITY, "a PatchWork patch holds more points than the largest fit tile");
+  *n_ground = c->h_scan_counts.p[0];
+  *n_nonground = c->h_scan_counts.p[1];
+  if (*n_ground) CU(cudaMemcpyAsync(ground_idx, gsrc.p, sizeof(int32_t) * *n_ground, cudaMemcpyDeviceToHost, st));
+  if (*n_nonground) CU(cudaMemcpyAsync(nonground_idx, ngsrc.p, sizeof(int32_t) * *n_nonground, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  pts.release(); apri_xyzi.release(); cls.release(); apri_src.release(); apri_vid.release(); gsrc.release(); ngsrc.release();
+  return SCVOD_OK;
+}
+
+// debug view of the per-patch plane fits of the most recent ground pass of scan slot `slot`:
+// 12 floats per patch: normal[3], mean[3], singular values[3], d, decision, npts (0 rows for skipped patches)
+extern "C" int scvod_last_patch_records(scvod_ctx* c, int slot, float* rec504x12) {
+  if (!c || !rec504x12 || slot < 0 || slot >= c->max_batch) return fail(SCVOD_ERR_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(rec504x12, c->ws.patch_dbg + (size_t)slot * kNumPatches * 12, sizeof(float) * kNumPatches * 12, cudaMemcpyDeviceToHost));
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_bin(scvod_ctx* c, const float* xyzi, int n, uint8_t* pass, int32_t* voxel_idx, int32_t* range_idx,
+                         int32_t* sector_idx, int32_t* azimuth_idx, float* range, float* angle, float* azimuth) {
+  if (!c || (!xyzi && n > 0) || n < 0) return fail(SCVOD_ERR_ARG, "bad arguments to scvod_bin");
+  CU(cudaSetDevice(c->device));
+  if (n == 0) return SCVOD_OK;
+  cudaStream_t st = c->stream;
+  DevBuf<float4> pts;
+  DevBuf<uint8_t> dpass;
+  DevBuf<int32_t> dvid, dri, dsi, dei;
+  DevBuf<float> dr, da_, daz;
+  CU(pts.alloc(n));
+  CU(dpass.alloc(n));
+  CU(dvid.alloc(n));
+  CU(dri.alloc(n));
+  CU(dsi.alloc(n));
+  CU(dei.alloc(n));
+  CU(dr.alloc(n));
+  CU(da_.alloc(n));
+  CU(daz.alloc(n));
+  CU(cudaMemcpyAsync(pts.p, xyzi, sizeof(float4) * n, cudaMemcpyHostToDevice, st));
+  c->launches += launch_bin_only(c->hp, pts.p, n, dpass.p, dvid.p, dri.p, dsi.p, dei.p, dr.p, da_.p, daz.p, st);
+  CU(cudaGetLastError());
+  int rc = 0;
+  rc |= d2h(c, pass, dpass.p, n);
+  rc |= d2h(c, voxel_idx, dvid.p, n);
+  rc |= d2h(c, range_idx, dri.p, n);
+  rc |= d2h(c, sector_idx, dsi.p, n);
+  rc |= d2h(c, azimuth_idx, dei.p, n);
+  rc |= d2h(c, range, dr.p, n);
+  rc |= d2h(c, angle, da_.p, n);
+  rc |= d2h(c, azimuth, daz.p, n);
+  CU(cudaStreamSynchronize(st));
+  pts.release(); dpass.release(); dvid.release(); dri.release(); dsi.release(); dei.release(); dr.release(); da_.release(); daz.release();
+  return rc ? SCVOD_ERR_CUDA : SCVOD_OK;
+}
+
+// device port of glibc atan2f evaluated on the GPU (test hook for the libm-parity check)
+extern "C" int scvod_atan2f_device(scvod_ctx* c, const float* y, const float* x, float* out, int64_t n) {
+  if (!c || !y || !x || !out || n < 0) return fail(SCVOD_ERR_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  if (n == 0) return SCVOD_OK;
+  DevBuf<float> dy, dx, dout;
+  CU(dy.alloc(n));
+  CU(dx.alloc(n));
+  CU(dout.alloc(n));
+  CU(cudaMemcpyAsync(dy.p, y, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(dx.p, x, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+  c->launches += launch_atan2f_probe(dy.p, dx.p, dout.p, n, c->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  dy.release(); dx.release(); dout.release();
+  return SCVOD_OK;
+}

@@ -1,0 +1,100 @@
+// scvod_internal.h — shared declarations between the CUDA kernels (scvod_kernels.cu), the C-ABI
+// layer (scvod_api.cpp) and the host-side cluster logic (host_cluster.cpp).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/scvod.h"
+
+namespace scvod {
+
+// PatchWork concentric zone model constants (reference include/patchwork.h:48-51,83-94,115-129).
+constexpr int kNumZones = 4;
+constexpr int kNumPatches = 504;  // 2*16 + 4*32 + 4*54 + 4*32
+constexpr int kMinPatchPts = 10;  // num_min_pts_: patches need > 10 points (patchwork.h:331)
+constexpr int kFitSmall = 2048;   // points per patch handled by the small-tile fit kernel
+constexpr int kFitLarge = 11000;  // ... by the large-tile fit kernel (20 B/pt of shared memory)
+
+struct GridSpec {
+  int range_num, sector_num, azimuth_num, bin_num;
+  int key_off;    // voxel_idx + key_off >= 0 for every reachable (aliased) index, ssc.cpp:185-188
+  int key_count;  // number of distinct keys
+  int words;      // bitmap words per scan
+};
+
+// Per-batch device workspace. All per-point arrays are indexed by the batch-global point position
+// (scan s occupies [off[s], off[s+1])); per-apri arrays reuse the same positions (M_s <= N_s).
+struct BatchDev {
+  int cap_points = 0;  // total points capacity of the batch
+  int cap_scans = 0;
+  // inputs
+  float4* pts = nullptr;      // xyzi
+  int64_t* off = nullptr;     // [cap_scans+1]
+  // ground stage
+  int16_t* patch_of = nullptr;     // per point: patch id or -1/-2 (dropped low / range)
+  int32_t* patch_cnt = nullptr;    // [scans][504]
+  int32_t* patch_off = nullptr;    // [scans][505] exclusive (relative to scan base)
+  int32_t* patch_cur = nullptr;    // [scans][504] scatter cursors
+  uint64_t* bucket_kv = nullptr;   // per bucket slot: (zkey<<32 | local idx)
+  int32_t* sorted_idx = nullptr;   // per bucket slot after sort: local point idx
+  int32_t* slot_pos = nullptr;     // per bucket slot: role<<30 | local position in ground / nonground list
+  int32_t* slot_apos = nullptr;    // per bucket slot: local position in apri list or -1
+  int32_t* slot_vid = nullptr;     // per bucket slot: voxel_idx (apri points)
+  int16_t* slot_patch = nullptr;   // per bucket slot: patch id
+  int32_t* patch_out = nullptr;    // [scans][504][4]: n_ground, n_nonground, n_apri, quirk count
+  int32_t* patch_out_off = nullptr;  // [scans][505][3] exclusive offsets
+  float* patch_dbg = nullptr;      // [scans][504][12] normal, mean, sv, d, decision, npts (debug/inspection)
+  int32_t* scan_counts = nullptr;  // [scans][8]: n_ground, n_ng, n_apri, n_voxels, n_quirk, n_events, n_comp, n_edges
+  // outputs of the ground stage
+  int32_t* ground_src = nullptr;  // per scan base: original idx in cloud_out order
+  int32_t* ng_src = nullptr;      // ... in cloud_nonground order
+  uint8_t* cls = nullptr;         // per point outcome class
+  // apri arrays (indexed by scan base + m)
+  int32_t* apri_src = nullptr;
+  int32_t* apri_vid = nullptr;
+  float4* apri_xyzi = nullptr;
+  int32_t* apri_cid = nullptr;   // compact voxel id
+  int32_t* apri_rank = nullptr;  // rank of the point inside its voxel (ascending m)
+  // voxel structures
+  uint32_t* bitmap = nullptr;     // [scans][words]
+  int32_t* word_rank = nullptr;   // [scans][words] exclusive popcount prefix
+  int32_t* vox_cnt = nullptr;     // per scan base + cid
+  int32_t* vox_off = nullptr;     // per scan base + cid (exclusive, relative to scan base); +1 slack handled by cnt
+  int32_t* vox_cur = nullptr;
+  int32_t* vox_pts_tmp = nullptr;  // unsorted fill
+  int32_t* vox_pts = nullptr;      // CSR point ids (m), ascending inside each voxel
+  int32_t* vox_vid = nullptr;
+  float* vox_av = nullptr;
+  float* vox_cov = nullptr;
+  float* vox_center = nullptr;  // 3 per voxel
+  int32_t* vox_tri = nullptr;   // 3 per voxel
+  int32_t* vox_nbr = nullptr;   // 27 per voxel: compact ids in findVoxelNeighbors order, -1 = absent
+  int32_t* vox_root = nullptr;  // CCL root (min compact id of the component)
+  float* vox_bbox = nullptr;    // 6 per voxel (per-voxel bbox; reduced per component on the host)
+  int32_t* ev_cid = nullptr;    // clustering events: compact voxel id of every apri point with rank < 3, in m order
+  int32_t* edge_buf = nullptr;  // [scans][edge_cap][2] directed similar-intensity component edges (roots)
+  int32_t* edge_hash = nullptr; // [scans][hash_cap] dedupe table
+  int edge_cap = 0, hash_cap = 0;
+};
+
+struct HostParams {
+  scvod_params p;
+  GridSpec g;
+};
+
+// kernel launch wrappers (scvod_kernels.cu). All asynchronous on `stream`. Return launch count.
+int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
+int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
+int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
+int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t* pass, int32_t* vid, int32_t* ri, int32_t* si,
+                    int32_t* ei, float* range, float* angle, float* azimuth, void* stream);
+// tracking: gather (sel >= 0: own apri point; sel < 0: carried[-1-sel]) -> transform by T -> bin -> lookup in next frame
+int launch_track(const HostParams& hp, const float4* own_xyzi, const float4* carried, const int32_t* sel, int k, const float* T12_dev,
+                 const uint32_t* next_bitmap, const int32_t* next_word_rank, float4* out_xyzi, int32_t* out_hit, void* stream);
+int launch_final_labels(const int32_t* apri_src, const int32_t* apri_cid, const uint8_t* vox_cls, int m, uint8_t* cls, void* stream);
+int launch_submap(const float4* pts, const uint8_t* cls, int n, const float* T12_dev, float4* out, unsigned long long* counter,
+                  long long cap, void* stream);
+int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
+
+}  // namespace scvod

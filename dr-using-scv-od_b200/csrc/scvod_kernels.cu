@@ -1,0 +1,1284 @@
+// scvod_kernels.cu — hand-written sm_100a kernels for the SCV-OD hot path.
+//
+// Stages (reference file:line each one replaces):
+//   ground     PatchWork::estimate_ground            include/patchwork.h:278-504
+//   binning    SSC::makeApriVec + Utility polar math  src/ssc.cpp:155-195, include/utility.h:346-392
+//   descriptor SSC::makeHashCloud                     src/ssc.cpp:253-289
+//   cluster    findVoxelNeighbors / CVC adjacency / intensity-similarity edges  src/ssc.cpp:395-411,299-351,587-595
+//   diff       transformCloud + re-binning + next-frame lookup of SSC::tracking  include/utility.h:394-406, src/ssc.cpp:1275-1315
+//
+// Everything here is HBM/latency-bound integer and float work: no tensor-core path exists for it.
+// The file is compiled with -fmad=false; index- and threshold-determining float expressions also go
+// through explicit _rn intrinsics so that no FMA contraction can change a voxel index or a label.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "scvod_device_math.cuh"
+#include "scvod_internal.h"
+
+namespace scvod {
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one int per thread across the block; returns exclusive prefix, total in *total.
+template <int THREADS>
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* s_warp /* THREADS/32 + 1 ints */) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = warp_incl_scan(v);
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = (lane < THREADS / 32) ? s_warp[lane] : 0;
+    int xi = warp_incl_scan(x);
+    if (lane < THREADS / 32) s_warp[lane] = xi - x;
+    if (lane == THREADS / 32 - 1) s_warp[THREADS / 32] = xi;
+  }
+  __syncthreads();
+  int res = inc - v + s_warp[w];
+  *total = s_warp[THREADS / 32];
+  __syncthreads();
+  return res;
+}
+
+__device__ __forceinline__ uint32_t float_sort_key(float z) {
+  if (z == 0.f) z = 0.f;  // -0 and +0 compare equal in point_z_cmp (patchwork.h:33-35)
+  uint32_t u = __float_as_uint(z);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// PatchWork constants (patchwork.h:48-51,83-94,115-129)
+__constant__ int c_zone_sectors[4] = {16, 32, 54, 32};
+__constant__ int c_zone_rings[4] = {2, 4, 4, 4};
+__constant__ int c_zone_base[4] = {0, 32, 160, 376};
+__constant__ int c_zone_ring0[4] = {0, 2, 6, 10};  // concentric_idx of the zone's first ring
+__constant__ double c_elev_thr[4] = {-1.2, -0.9984, -0.851, -0.605};
+__constant__ double c_flat_thr[4] = {0.0, 0.000125, 0.000185, 0.000185};
+
+struct GroundConst {
+  double low_thr;   // -1.8 * sensor_height_  (patchwork.h:304)
+  double seed_thr;  // adaptive_seed_selection_margin_ * sensor_height_ (patchwork.h:247)
+  double min_range, max_range, z2, z3, z4;
+  double ring_size[4], sector_size[4], rmin[4];
+};
+
+// ------------------------------------------------------------------------------------------------
+// G1: per-point patch assignment (pc2czm, patchwork.h:431-459) + per-patch histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_patch_assign(const float4* __restrict__ pts, const int64_t* __restrict__ off,
+                                                      GroundConst gc, int16_t* __restrict__ patch_of,
+                                                      int32_t* __restrict__ patch_cnt, uint8_t* __restrict__ cls) {
+  __shared__ int s_hist[kNumPatches];
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int n = (int)(off[b + 1] - base);
+  for (int i = threadIdx.x; i < kNumPatches; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(&pts[base + i]);
+    int pid;
+    if ((double)p.z < gc.low_thr) {
+      pid = -1;
+    } else {
+      double x = (double)p.x, y = (double)p.y;
+      double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+      if ((r <= gc.max_range) && (r > gc.min_range)) {
+        double theta = (y >= 0) ? atan2(y, x) : __dadd_rn(2.0 * 3.14159265358979323846, atan2(y, x));
+        int k = (r < gc.z2) ? 0 : (r < gc.z3) ? 1 : (r < gc.z4) ? 2 : 3;
+        int ring = min((int)__ddiv_rn(__dsub_rn(r, gc.rmin[k]), gc.ring_size[k]), c_zone_rings[k] - 1);
+        int sector = min((int)__ddiv_rn(theta, gc.sector_size[k]), c_zone_sectors[k] - 1);
+        pid = c_zone_base[k] + ring * c_zone_sectors[k] + sector;
+      } else {
+        pid = -2;
+      }
+    }
+    patch_of[base + i] = (int16_t)pid;
+    if (pid >= 0)
+      atomicAdd(&s_hist[pid], 1);
+    else
+      cls[base + i] = (pid == -1) ? SCVOD_PT_DROPPED_LOW : SCVOD_PT_DROPPED_RANGE;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumPatches; i += blockDim.x) {
+    int c = s_hist[i];
+    if (c) atomicAdd(&patch_cnt[b * kNumPatches + i], c);
+  }
+}
+
+// G2: exclusive scan over the 504 patch counts of a scan
+__global__ void __launch_bounds__(512) k_patch_scan(const int32_t* __restrict__ patch_cnt, int32_t* __restrict__ patch_off,
+                                                    int32_t* __restrict__ patch_cur) {
+  __shared__ int s_w[17];
+  const int b = blockIdx.x;
+  int v = (threadIdx.x < kNumPatches) ? patch_cnt[b * kNumPatches + threadIdx.x] : 0;
+  int total;
+  int ex = block_excl_scan<512>(v, &total, s_w);
+  if (threadIdx.x < kNumPatches) {
+    patch_off[b * (kNumPatches + 1) + threadIdx.x] = ex;
+    patch_cur[b * kNumPatches + threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) patch_off[b * (kNumPatches + 1) + kNumPatches] = total;
+}
+
+// G3: scatter (z key, local index) into the patch buckets
+__global__ void __launch_bounds__(256) k_patch_scatter(const float4* __restrict__ pts, const int64_t* __restrict__ off,
+                                                       const int16_t* __restrict__ patch_of,
+                                                       const int32_t* __restrict__ patch_off, int32_t* __restrict__ patch_cur,
+                                                       uint64_t* __restrict__ bucket_kv) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int n = (int)(off[b + 1] - base);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int pid = patch_of[base + i];
+    if (pid < 0) continue;
+    float z = __ldg(&pts[base + i]).z;
+    int slot = patch_off[b * (kNumPatches + 1) + pid] + atomicAdd(&patch_cur[b * kNumPatches + pid], 1);
+    bucket_kv[base + slot] = ((uint64_t)float_sort_key(z) << 32) | (uint32_t)i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 one-sided... no: two-sided Jacobi SVD, float, in the evaluation order of Eigen 3.3.4's
+// JacobiSVD<MatrixXf> for a square input (called at patchwork.h:220).  U columns = left vectors.
+// ------------------------------------------------------------------------------------------------
+struct Rot2 {
+  float c, s;
+};
+
+__device__ __forceinline__ Rot2 dev_make_jacobi(float x, float y, float z) {
+  Rot2 r;
+  float deno = dm(2.f, fabsf(y));
+  if (deno < 1.17549435e-38f) {
+    r.c = 1.f;
+    r.s = 0.f;
+  } else {
+    float tau = dd(ds(x, z), deno);
+    float w = __fsqrt_rn(da(dm(tau, tau), 1.f));
+    float t = (tau > 0.f) ? dd(1.f, da(tau, w)) : dd(1.f, ds(tau, w));
+    float sign_t = t > 0.f ? 1.f : -1.f;
+    float n = dd(1.f, __fsqrt_rn(da(dm(t, t), 1.f)));
+    r.s = dm(dm(dm(-sign_t, dd(y, fabsf(y))), fabsf(t)), n);
+    r.c = n;
+  }
+  return r;
+}
+
+__device__ void dev_svd3(const float A[3][3], float U[3][3], float sv[3]) {
+  const float precision = dm(2.f, 1.1920929e-07f);
+  const float tinyf = 1.17549435e-38f;
+  float scale = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) scale = fmaxf(scale, fabsf(A[i][j]));
+  if (scale == 0.f) scale = 1.f;
+  float W[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      W[i][j] = dd(A[i][j], scale);
+      U[i][j] = (i == j) ? 1.f : 0.f;
+    }
+  float maxDiag = fmaxf(fabsf(W[0][0]), fmaxf(fabsf(W[1][1]), fabsf(W[2][2])));
+  bool finished = false;
+  int guard = 0;
+  while (!finished && guard++ < 64) {
+    finished = true;
+#pragma unroll
+    for (int p = 1; p < 3; ++p) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= p) continue;
+        float threshold = fmaxf(tinyf, dm(precision, maxDiag));
+        if (fabsf(W[p][q]) > threshold || fabsf(W[q][p]) > threshold) {
+          finished = false;
+          // real_2x2_jacobi_svd
+          float m00 = W[p][p], m01 = W[p][q], m10 = W[q][p], m11 = W[q][q];
+          Rot2 rot1;
+          float t = da(m00, m11);
+          float d = ds(m10, m01);
+          if (fabsf(d) < tinyf) {
+            rot1.s = 0.f;
+            rot1.c = 1.f;
+          } else {
+            float u = dd(t, d);
+            float tmp = __fsqrt_rn(da(1.f, dm(u, u)));
+            rot1.s = dd(1.f, tmp);
+            rot1.c = dd(u, tmp);
+          }
+          if (!(rot1.c == 1.f && rot1.s == 0.f)) {
+            float a00 = da(dm(rot1.c, m00), dm(rot1.s, m10)), a01 = da(dm(rot1.c, m01), dm(rot1.s, m11));
+            float a10 = da(dm(-rot1.s, m00), dm(rot1.c, m10)), a11 = da(dm(-rot1.s, m01), dm(rot1.c, m11));
+            m00 = a00;
+            m01 = a01;
+            m10 = a10;
+            m11 = a11;
+          }
+          Rot2 jr = dev_make_jacobi(m00, m01, m11);
+          Rot2 jl;
+          jl.c = ds(dm(rot1.c, jr.c), dm(rot1.s, -jr.s));
+          jl.s = da(dm(rot1.c, -jr.s), dm(rot1.s, jr.c));
+          if (!(jl.c == 1.f && jl.s == 0.f)) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float xi = W[p][k], yi = W[q][k];
+              W[p][k] = da(dm(jl.c, xi), dm(jl.s, yi));
+              W[q][k] = da(dm(-jl.s, xi), dm(jl.c, yi));
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float xi = U[k][p], yi = U[k][q];
+              U[k][p] = da(dm(jl.c, xi), dm(jl.s, yi));
+              U[k][q] = da(dm(-jl.s, xi), dm(jl.c, yi));
+            }
+          }
+          {
+            float c = jr.c, s = -jr.s;
+            if (!(c == 1.f && s == 0.f)) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                float xi = W[k][p], yi = W[k][q];
+                W[k][p] = da(dm(c, xi), dm(s, yi));
+                W[k][q] = da(dm(-s, xi), dm(c, yi));
+              }
+            }
+          }
+          maxDiag = fmaxf(maxDiag, fmaxf(fabsf(W[p][p]), fabsf(W[q][q])));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = W[i][i];
+    sv[i] = fabsf(a);
+    if (a < 0.f) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) U[k][i] = -U[k][i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sv[i] = dm(sv[i], scale);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    int pos = i;
+    float best = sv[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (k > i && sv[k] > best) {
+        best = sv[k];
+        pos = k;
+      }
+    if (best == 0.f) break;
+    if (pos != i) {
+      float t = sv[i];
+      sv[i] = sv[pos];
+      sv[pos] = t;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float u = U[k][i];
+        U[k][i] = U[k][pos];
+        U[k][pos] = u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G4: one CTA per (patch, scan): z-sort of the patch in shared memory, seed selection, three
+// sequential-order plane fits (R-GPF), gating, ordered ranks of ground / nonground / apri points and
+// the curved-voxel index of every surviving nonground point.
+//   patchwork.h:235-268 (seeds), :217-232 (plane), :463-504 (iterations), :331-384 (gating)
+//   ssc.cpp:158-172,185-188 (binning of the nonground points, fused here)
+// The covariance sums are accumulated strictly in z-sorted order, one lane per accumulator, because
+// PCL's single-pass float accumulation is order dependent (SURVEY.md hard part 3).
+// ------------------------------------------------------------------------------------------------
+struct FitArgs {
+  const float4* pts;
+  const int64_t* off;
+  const int32_t* patch_cnt;
+  const int32_t* patch_off;
+  const uint64_t* bucket_kv;
+  int32_t* sorted_idx;
+  int32_t* slot_pos;
+  int32_t* slot_apos;
+  int32_t* slot_vid;
+  int16_t* slot_patch;
+  int32_t* patch_out;
+  float* patch_dbg;
+  uint8_t* cls;
+  int32_t* err;
+  GroundConst gc;
+  BinParams bp;
+};
+
+constexpr uint32_t F_G = 1u;      // in the current ground set / final ground
+constexpr uint32_t F_PASS = 2u;   // survives the SSC gates
+constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md hard part 7)
+constexpr uint32_t F_BIN = 8u;    // binning was evaluated for this point
+
+template <int MAXN, int MINN, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* kv = reinterpret_cast<uint64_t*>(smem_raw);
+  float* sx = reinterpret_cast<float*>(kv + MAXN);
+  float* sy = sx + MAXN;
+  float* sz = sy + MAXN;
+  uint32_t* kv32 = reinterpret_cast<uint32_t*>(kv);  // [2*j] = low word, [2*j+1] = high word
+  __shared__ float s_plane[4];   // n0 n1 n2 th_dist_d
+  __shared__ float s_stat[8];    // mean z, sv0..2, d, mean x, mean y
+  __shared__ int s_int[8];       // decision, init_idx, ...
+  __shared__ double s_lpr;
+  __shared__ int s_scan[THREADS / 32 + 1];
+
+  const int p = blockIdx.x, b = blockIdx.y;
+  const int n = a.patch_cnt[b * kNumPatches + p];
+  if (n <= MINN || n > MAXN) {
+    if (MINN > 0 && n > kFitLarge && threadIdx.x == 0) atomicOr(a.err, 1);  // patch larger than the largest tile
+    return;
+  }
+  const int64_t base = a.off[b];
+  const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+  const int tid = threadIdx.x;
+  int32_t* pout = a.patch_out + (b * kNumPatches + p) * 4;
+
+  if (n <= kMinPatchPts) {  // patchwork.h:331: the patch vanishes from both outputs
+    for (int j = tid; j < n; j += THREADS) {
+      int idx = (int)(uint32_t)a.bucket_kv[base + slot0 + j];
+      a.cls[base + idx] = SCVOD_PT_DROPPED_SPARSE;
+      a.slot_pos[base + slot0 + j] = (3 << 30);
+      a.slot_patch[base + slot0 + j] = (int16_t)p;
+    }
+    if (tid == 0) {
+      pout[0] = 0;
+      pout[1] = 0;
+      pout[2] = 0;
+      pout[3] = 0;
+    }
+    return;
+  }
+
+  // ---- load + bitonic sort by (z key, original index) ---------------------------------------
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int j = tid; j < np2; j += THREADS) kv[j] = (j < n) ? a.bucket_kv[base + slot0 + j] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int s = k >> 1; s > 0; s >>= 1) {
+      for (int t = tid; t < (np2 >> 1); t += THREADS) {
+        int i = ((t & ~(s - 1)) << 1) | (t & (s - 1));
+        int l = i | s;
+        bool up = ((i & k) == 0);
+        uint64_t x = kv[i], y = kv[l];
+        if ((x > y) == up) {
+          kv[i] = y;
+          kv[l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- gather the points in sorted order ------------------------------------------------------
+  for (int j = tid; j < n; j += THREADS) {
+    int idx = (int)kv32[2 * j];
+    float4 q = __ldg(&a.pts[base + idx]);
+    sx[j] = q.x;
+    sy[j] = q.y;
+    sz[j] = q.z;
+    a.sorted_idx[base + slot0 + j] = idx;
+    a.slot_patch[base + slot0 + j] = (int16_t)p;
+  }
+  __syncthreads();
+
+  const int zone = (p < 32) ? 0 : (p < 160) ? 1 : (p < 376) ? 2 : 3;
+  // ---- seeds (patchwork.h:235-268) --------------------------------------------------------------
+  {
+    int c = 0;
+    if (zone == 0)
+      for (int j = tid; j < n; j += THREADS) c += ((double)sz[j] < a.gc.seed_thr) ? 1 : 0;
+    int total;
+    block_excl_scan<THREADS>(c, &total, s_scan);
+    if (tid == 0) {
+      int init_idx = total;  // sorted ascending => the points below the margin form a prefix
+      double sum = 0;
+      int cnt = 0;
+      for (int i = init_idx; i < n && cnt < 20; ++i) {
+        sum = __dadd_rn(sum, (double)sz[i]);
+        cnt++;
+      }
+      s_lpr = cnt != 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
+    }
+    __syncthreads();
+    double thr = __dadd_rn(s_lpr, 0.3);
+    for (int j = tid; j < n; j += THREADS) kv32[2 * j + 1] = ((double)sz[j] < thr) ? F_G : 0u;
+    __syncthreads();
+  }
+
+  // ---- three plane fits -------------------------------------------------------------------------
+  for (int it = 0; it < 3; ++it) {
+    if (tid < 32) {
+      const int lane = tid;
+      // lane L accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix: xx xy xz yy yz zz x y z
+      const int ia = (lane < 3 || lane == 6) ? 0 : (lane < 5 || lane == 7) ? 1 : 2;
+      const int ib = (lane == 0) ? 0 : (lane == 1 || lane == 3) ? 1 : (lane == 2 || lane == 4 || lane == 5) ? 2 : 3;
+      float acc = 0.f;
+      int cnt = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        if (kv32[2 * j + 1] & F_G) {
+          float xv = sx[j], yv = sy[j], zv = sz[j];
+          float av = (ia == 0) ? xv : (ia == 1) ? yv : zv;
+          float bv = (ib == 0) ? xv : (ib == 1) ? yv : (ib == 2) ? zv : 1.0f;
+          acc = da(acc, dm(av, bv));
+          ++cnt;
+        }
+      }
+      float accu[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) accu[k] = __shfl_sync(0xffffffffu, acc, k);
+      if (lane == 0) {
+        if (cnt == 0) {
+          atomicOr(a.err, 2);  // cannot happen for finite input; plane kept
+        } else {
+          float fn = (float)cnt;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) accu[k] = dd(accu[k], fn);
+          float C[3][3];
+          C[0][0] = ds(accu[0], dm(accu[6], accu[6]));
+          C[0][1] = ds(accu[1], dm(accu[6], accu[7]));
+          C[0][2] = ds(accu[2], dm(accu[6], accu[8]));
+          C[1][1] = ds(accu[3], dm(accu[7], accu[7]));
+          C[1][2] = ds(accu[4], dm(accu[7], accu[8]));
+          C[2][2] = ds(accu[5], dm(accu[8], accu[8]));
+          C[1][0] = C[0][1];
+          C[2][0] = C[0][2];
+          C[2][1] = C[1][2];
+          float U[3][3], sv[3];
+          dev_svd3(C, U, sv);
+          float n0 = U[0][2], n1 = U[1][2], n2 = U[2][2];
+          // d_ = -(normal^T * mean): Eigen 3-term unrolled redux a0 + (a1 + a2)
+          float dval = -da(dm(n0, accu[6]), da(dm(n1, accu[7]), dm(n2, accu[8])));
+          s_plane[0] = n0;
+          s_plane[1] = n1;
+          s_plane[2] = n2;
+          s_plane[3] = (float)__dsub_rn(0.1, (double)dval);  // th_dist_d_ = th_dist_ - d_
+          s_stat[0] = accu[8];
+          s_stat[1] = sv[0];
+          s_stat[2] = sv[1];
+          s_stat[3] = sv[2];
+          s_stat[4] = dval;
+          s_stat[5] = accu[6];
+          s_stat[6] = accu[7];
+        }
+      }
+    }
+    __syncthreads();
+    const float n0 = s_plane[0], n1 = s_plane[1], n2 = s_plane[2], th = s_plane[3];
+    for (int j = tid; j < n; j += THREADS) {
+      // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
+      float res = da(da(dm(sx[j], n0), dm(sy[j], n1)), dm(sz[j], n2));
+      kv32[2 * j + 1] = (res < th) ? F_G : 0u;
+    }
+    __syncthreads();
+  }
+
+  // ---- gating (patchwork.h:339-384) ---------------------------------------------------------------
+  if (tid == 0) {
+    const double ground_z_vec = (double)fabsf(s_plane[2]);
+    const double ground_z_elevation = (double)s_stat[0];
+    const float minsv = fminf(s_stat[1], fminf(s_stat[2], s_stat[3]));
+    const double surface_variable = (double)dd(minsv, da(da(s_stat[1], s_stat[2]), s_stat[3]));
+    const int ring = (p - c_zone_base[zone]) / c_zone_sectors[zone];
+    const int concentric_idx = c_zone_ring0[zone] + ring;
+    int decision = 0;
+    if (ground_z_vec < 0.707) {
+      decision = 1;
+    } else if (concentric_idx < 4) {
+      if (ground_z_elevation > c_elev_thr[ring + 2 * zone]) decision = (c_flat_thr[ring + 2 * zone] > surface_variable) ? 3 : 2;
+    }
+    s_int[0] = decision;
+    if (a.patch_dbg) {
+      float* dbg = a.patch_dbg + (size_t)(b * kNumPatches + p) * 12;
+      dbg[0] = s_plane[0];
+      dbg[1] = s_plane[1];
+      dbg[2] = s_plane[2];
+      dbg[3] = s_stat[5];
+      dbg[4] = s_stat[6];
+      dbg[5] = s_stat[0];
+      dbg[6] = s_stat[1];
+      dbg[7] = s_stat[2];
+      dbg[8] = s_stat[3];
+      dbg[9] = s_stat[4];
+      dbg[10] = (float)decision;
+      dbg[11] = (float)n;
+    }
+  }
+  __syncthreads();
+  const bool rejected = (s_int[0] == 1 || s_int[0] == 2);
+
+  // ---- curved-voxel binning of every point that ends up in cloud_nonground ------------------------
+  for (int j = tid; j < n; j += THREADS) {
+    uint32_t f = kv32[2 * j + 1] & F_G;
+    int vid = 0;
+    if (rejected || !(f & F_G)) {
+      BinResult r = dev_bin_point(sx[j], sy[j], sz[j], a.bp);
+      f |= F_BIN;
+      if (r.pass) {
+        f |= F_PASS;
+        if (r.ri < 0 || r.si < 0 || r.ei < 0) f |= F_QUIRK;
+      }
+      vid = r.vid;
+    }
+    kv32[2 * j + 1] = f;
+    kv32[2 * j] = (uint32_t)vid;
+  }
+  __syncthreads();
+
+  // ---- ordered ranks: ground list, nonground list ([G part][NG part] when rejected), apri list ------
+  const int chunk = (n + THREADS - 1) / THREADS;
+  const int j0 = min(n, tid * chunk), j1 = min(n, j0 + chunk);
+  int cG = 0, cGP = 0, cNP = 0, cQ = 0;
+  for (int j = j0; j < j1; ++j) {
+    uint32_t f = kv32[2 * j + 1];
+    bool g = f & F_G, ps = f & F_PASS;
+    cG += g;
+    cGP += (g && ps);
+    cNP += (!g && ps);
+    cQ += (f & F_QUIRK) ? 1 : 0;
+  }
+  int tG, tGP, tNP, tQ;
+  int eG = block_excl_scan<THREADS>(cG, &tG, s_scan);
+  int eGP = block_excl_scan<THREADS>(cGP, &tGP, s_scan);
+  int eNP = block_excl_scan<THREADS>(cNP, &tNP, s_scan);
+  block_excl_scan<THREADS>(cQ, &tQ, s_scan);
+  const int nG = tG, nN = n - tG;
+  int* spos = reinterpret_cast<int*>(sx);   // x,y no longer needed
+  int* sapos = reinterpret_cast<int*>(sy);
+  {
+    int rG = eG, rGP = eGP, rNP = eNP;
+    for (int j = j0; j < j1; ++j) {
+      uint32_t f = kv32[2 * j + 1];
+      bool g = f & F_G, ps = f & F_PASS;
+      int rN = j - rG;  // nonground points before j
+      int pos, apos = -1, role;
+      if (!rejected) {
+        if (g) {
+          role = 0;
+          pos = rG;
+        } else {
+          pos = rN;
+          role = ps ? 2 : 1;
+          if (ps) apos = rNP;
+        }
+      } else {
+        pos = g ? rG : nG + rN;
+        role = ps ? 2 : 1;
+        if (ps) apos = g ? rGP : tGP + rNP;
+      }
+      spos[j] = (role << 30) | pos;
+      sapos[j] = apos;
+      rG += g;
+      rGP += (g && ps);
+      rNP += (!g && ps);
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += THREADS) {
+    a.slot_pos[base + slot0 + j] = spos[j];
+    a.slot_apos[base + slot0 + j] = sapos[j];
+    a.slot_vid[base + slot0 + j] = (int)kv32[2 * j];
+  }
+  if (tid == 0) {
+    pout[0] = rejected ? 0 : nG;
+    pout[1] = rejected ? n : nN;
+    pout[2] = rejected ? (tGP + tNP) : tNP;
+    pout[3] = tQ;
+  }
+}
+
+// G5: per-scan exclusive scans of the per-patch output counts (patch-major output order, :327-391)
+__global__ void __launch_bounds__(512) k_patch_out_scan(const int32_t* __restrict__ patch_cnt, const int32_t* __restrict__ patch_out,
+                                                        int32_t* __restrict__ patch_out_off, int32_t* __restrict__ scan_counts) {
+  __shared__ int s_w[17];
+  const int b = blockIdx.x;
+  const int t = threadIdx.x;
+  const bool live = t < kNumPatches && patch_cnt[b * kNumPatches + t] > 0;
+  int v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = live ? patch_out[(b * kNumPatches + t) * 4 + k] : 0;
+  int tot[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int ex = block_excl_scan<512>(v[k], &tot[k], s_w);
+    if (k < 3 && t < kNumPatches) patch_out_off[(b * (kNumPatches + 1) + t) * 3 + k] = ex;
+  }
+  if (t == 0) {
+    scan_counts[b * 8 + 0] = tot[0];
+    scan_counts[b * 8 + 1] = tot[1];
+    scan_counts[b * 8 + 2] = tot[2];
+    scan_counts[b * 8 + 4] = tot[3];
+  }
+}
+
+// G6: emit cloud_out / cloud_nonground order and the apri arrays
+__global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ pts, const int64_t* __restrict__ off,
+                                              const int32_t* __restrict__ patch_off, const int32_t* __restrict__ patch_out_off,
+                                              const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ slot_pos,
+                                              const int32_t* __restrict__ slot_apos, const int32_t* __restrict__ slot_vid,
+                                              const int16_t* __restrict__ slot_patch, int32_t* __restrict__ ground_src,
+                                              int32_t* __restrict__ ng_src, int32_t* __restrict__ apri_src,
+                                              int32_t* __restrict__ apri_vid, float4* __restrict__ apri_xyzi,
+                                              uint8_t* __restrict__ cls) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int nslots = patch_off[b * (kNumPatches + 1) + kNumPatches];
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nslots; q += gridDim.x * blockDim.x) {
+    int sp = slot_pos[base + q];
+    int role = (sp >> 30) & 3;
+    if (role == 3) continue;
+    int pos = sp & 0x3fffffff;
+    int p = slot_patch[base + q];
+    int idx = sorted_idx[base + q];
+    const int32_t* o = patch_out_off + (b * (kNumPatches + 1) + p) * 3;
+    if (role == 0) {
+      ground_src[base + o[0] + pos] = idx;
+      cls[base + idx] = SCVOD_PT_GROUND;
+    } else {
+      ng_src[base + o[1] + pos] = idx;
+      if (role == 1) {
+        cls[base + idx] = SCVOD_PT_GATED_OUT;
+      } else {
+        int m = o[2] + slot_apos[base + q];
+        apri_src[base + m] = idx;
+        apri_vid[base + m] = slot_vid[base + q];
+        apri_xyzi[base + m] = __ldg(&pts[base + idx]);
+        cls[base + idx] = SCVOD_PT_UNCLUSTERED;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Descriptor stage (SSC::makeHashCloud, ssc.cpp:253-289).  The unordered_map<int,Voxel> becomes an
+// occupancy bitmap + popcount rank per scan (324 KB at the KITTI grid), which gives an O(1)
+// voxel_idx -> compact id lookup that the neighbour searches and the tracking diff reuse.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vox_mark(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                  const int32_t* __restrict__ apri_vid, GridSpec g, uint32_t* __restrict__ bitmap) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int m_total = scan_counts[b * 8 + 2];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < m_total; m += gridDim.x * blockDim.x) {
+    int key = apri_vid[base + m] + g.key_off;
+    if (key >= 0 && key < g.key_count) atomicOr(&bitmap[(size_t)b * g.words + (key >> 5)], 1u << (key & 31));
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_vox_rank(const int64_t* __restrict__ off, GridSpec g, const uint32_t* __restrict__ bitmap,
+                                                   int32_t* __restrict__ word_rank, int32_t* __restrict__ vox_vid,
+                                                   int32_t* __restrict__ vox_cnt, int32_t* __restrict__ scan_counts) {
+  __shared__ int s_w[33];
+  const int b = blockIdx.x;
+  const int64_t base = off[b];
+  const uint32_t* bm = bitmap + (size_t)b * g.words;
+  int32_t* wr = word_rank + (size_t)b * g.words;
+  const int chunk = (g.words + 1023) / 1024;
+  const int w0 = min(g.words, (int)threadIdx.x * chunk), w1 = min(g.words, w0 + chunk);
+  int c = 0;
+  for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
+  int total;
+  int ex = block_excl_scan<1024>(c, &total, s_w);
+  for (int w = w0; w < w1; ++w) {
+    uint32_t bits = bm[w];
+    wr[w] = ex;
+    while (bits) {
+      int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      vox_vid[base + ex] = (w << 5) + bit - g.key_off;
+      vox_cnt[base + ex] = 0;
+      ++ex;
+    }
+  }
+  if (threadIdx.x == 0) scan_counts[b * 8 + 3] = total;
+}
+
+__device__ __forceinline__ int vox_lookup(const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, const GridSpec& g, int vid) {
+  int key = vid + g.key_off;
+  if (key < 0 || key >= g.key_count) return -1;
+  uint32_t w = bm[key >> 5];
+  uint32_t bit = 1u << (key & 31);
+  if (!(w & bit)) return -1;
+  return wr[key >> 5] + __popc(w & (bit - 1));
+}
+
+__global__ void __launch_bounds__(256) k_vox_count(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                   const int32_t* __restrict__ apri_vid, GridSpec g, const uint32_t* __restrict__ bitmap,
+                                                   const int32_t* __restrict__ word_rank, int32_t* __restrict__ apri_cid,
+                                                   int32_t* __restrict__ vox_cnt) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int m_total = scan_counts[b * 8 + 2];
+  const uint32_t* bm = bitmap + (size_t)b * g.words;
+  const int32_t* wr = word_rank + (size_t)b * g.words;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < m_total; m += gridDim.x * blockDim.x) {
+    int cid = vox_lookup(bm, wr, g, apri_vid[base + m]);
+    apri_cid[base + m] = cid;
+    if (cid >= 0) atomicAdd(&vox_cnt[base + cid], 1);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_vox_offsets(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                      const int32_t* __restrict__ vox_cnt, int32_t* __restrict__ vox_off,
+                                                      int32_t* __restrict__ vox_cur) {
+  __shared__ int s_w[33];
+  const int b = blockIdx.x;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  int carry = 0;
+  for (int v0 = 0; v0 < V; v0 += 1024) {
+    int v = v0 + threadIdx.x;
+    int c = (v < V) ? vox_cnt[base + v] : 0;
+    int total;
+    int ex = block_excl_scan<1024>(c, &total, s_w);
+    if (v < V) {
+      vox_off[base + v] = carry + ex;
+      vox_cur[base + v] = 0;
+    }
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_vox_fill(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                  const int32_t* __restrict__ apri_cid, const int32_t* __restrict__ vox_off,
+                                                  int32_t* __restrict__ vox_cur, int32_t* __restrict__ vox_pts_tmp) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int m_total = scan_counts[b * 8 + 2];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < m_total; m += gridDim.x * blockDim.x) {
+    int cid = apri_cid[base + m];
+    if (cid < 0) continue;
+    int slot = vox_off[base + cid] + atomicAdd(&vox_cur[base + cid], 1);
+    vox_pts_tmp[base + slot] = m;
+  }
+}
+
+// One warp per voxel: order the voxel's points by m (rank by counting), then the strictly sequential
+// float intensity mean / population variance of ssc.cpp:261-287, voxel "centre" (:271-277), the index
+// triple of the first inserted point (:268-270) and the voxel's bounding box.
+__global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                   const int32_t* __restrict__ vox_cnt, const int32_t* __restrict__ vox_off,
+                                                   const int32_t* __restrict__ vox_pts_tmp, const float4* __restrict__ apri_xyzi,
+                                                   BinParams bp, scvod_params sp, int32_t* __restrict__ vox_pts,
+                                                   int32_t* __restrict__ apri_rank, float* __restrict__ vox_av,
+                                                   float* __restrict__ vox_cov, float* __restrict__ vox_center,
+                                                   int32_t* __restrict__ vox_tri, float* __restrict__ vox_bbox) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+    const int k = vox_cnt[base + v];
+    const int o = vox_off[base + v];
+    const int32_t* seg = vox_pts_tmp + base + o;
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int e = lane; e < k; e += 32) {
+      int me = seg[e];
+      int r = 0;
+      for (int t = 0; t < k; ++t) r += (seg[t] < me) ? 1 : 0;
+      vox_pts[base + o + r] = me;
+      apri_rank[base + me] = r;
+      float4 q = __ldg(&apri_xyzi[base + me]);
+      lo[0] = fminf(lo[0], q.x);
+      lo[1] = fminf(lo[1], q.y);
+      lo[2] = fminf(lo[2], q.z);
+      hi[0] = fmaxf(hi[0], q.x);
+      hi[1] = fmaxf(hi[1], q.y);
+      hi[2] = fmaxf(hi[2], q.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+      }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) {
+      const int32_t* srt = vox_pts + base + o;
+      float sum = 0.f;
+      for (int e = 0; e < k; ++e) sum = da(sum, apri_xyzi[base + srt[e]].w);
+      float av = dd(sum, (float)k);
+      float cov = 0.f;
+      for (int e = 0; e < k; ++e) {
+        float dlt = ds(apri_xyzi[base + srt[e]].w, av);
+        cov = (float)__dadd_rn((double)cov, __dmul_rn((double)dlt, (double)dlt));
+      }
+      cov = dd(cov, (float)k);
+      vox_av[base + v] = av;
+      vox_cov[base + v] = cov;
+      float4 q0 = apri_xyzi[base + srt[0]];
+      BinResult r = dev_bin_point(q0.x, q0.y, q0.z, bp);
+      vox_tri[3 * (base + v) + 0] = r.ri;
+      vox_tri[3 * (base + v) + 1] = r.si;
+      vox_tri[3 * (base + v) + 2] = r.ei;
+      float range_center = da(dm((float)((r.ri * 2 + 1) / 2), sp.range_res), sp.min_dis);
+      float sector_center = da(dev_deg2rad_f(dm((float)((r.si * 2 + 1) / 2), sp.sector_res)), sp.min_angle);
+      float azimuth_center = da(dev_deg2rad_f(dm((float)((r.ei * 2 + 1) / 2), sp.azimuth_res)), dev_deg2rad_f(sp.min_azimuth));
+      vox_center[3 * (base + v) + 0] = dm(range_center, cosf(sector_center));
+      vox_center[3 * (base + v) + 1] = dm(range_center, sinf(sector_center));
+      vox_center[3 * (base + v) + 2] = dm(range_center, tanf(azimuth_center));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        vox_bbox[6 * (base + v) + d] = lo[d];
+        vox_bbox[6 * (base + v) + 3 + d] = hi[d];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cluster preparation: 27-neighbour adjacency in findVoxelNeighbors order (ssc.cpp:395-411), GPU
+// connected components, intensity-similarity edges between components (ssc.cpp:587-595), and the
+// ordered list of "clustering events" the host needs to reproduce the sequential cluster names
+// (ssc.cpp:304-352; see host_cluster.cpp).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vox_nbr(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts, GridSpec g,
+                                                 const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
+                                                 const int32_t* __restrict__ vox_tri, int32_t* __restrict__ vox_nbr,
+                                                 int32_t* __restrict__ vox_root) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  const uint32_t* bm = bitmap + (size_t)b * g.words;
+  const int32_t* wr = word_rank + (size_t)b * g.words;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
+    int32_t* out = vox_nbr + 27 * (base + v);
+    int t = 0;
+    for (int x = ri - 1; x <= ri + 1; ++x)
+      for (int y = si - 1; y <= si + 1; ++y)
+        for (int z = ei - 1; z <= ei + 1; ++z) {
+          int cid = -1;
+          if (!(x > g.range_num - 1 || x < 0 || y > g.sector_num - 1 || y < 0 || z > g.azimuth_num - 1 || z < 0))
+            cid = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
+          out[t++] = cid;
+        }
+    vox_root[base + v] = v;
+  }
+}
+
+__device__ __forceinline__ int uf_find(int32_t* parent, int v) {
+  int r = v;
+  while (true) {
+    int pr = parent[r];
+    if (pr == r) break;
+    int gp = parent[pr];
+    if (gp != pr) parent[r] = gp;  // path halving (benign race: always points to an ancestor)
+    r = pr;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_ccl_union(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                   const int32_t* __restrict__ vox_nbr, int32_t* __restrict__ vox_root) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  int32_t* parent = vox_root + base;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    const int32_t* nb = vox_nbr + 27 * (base + v);
+    for (int t = 0; t < 27; ++t) {
+      int u = nb[t];
+      if (u < 0 || u >= v) continue;  // each undirected edge once
+      int ra = uf_find(parent, v), rb = uf_find(parent, u);
+      while (ra != rb) {
+        if (ra < rb) {
+          int tmp = ra;
+          ra = rb;
+          rb = tmp;
+        }
+        int old = atomicCAS(&parent[ra], ra, rb);  // hook the larger root under the smaller
+        if (old == ra) break;
+        ra = uf_find(parent, old);
+        rb = uf_find(parent, rb);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                     int32_t* __restrict__ vox_root) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    int r = v;
+    while (vox_root[base + r] != r) r = vox_root[base + r];
+    vox_root[base + v] = r;
+  }
+}
+
+// directed component edges (root(v) -> root(n)) for every voxel pair that satisfies the intensity
+// similarity test of refineClusterByIntensity (ssc.cpp:588-594); self pairs included.
+__global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts, GridSpec g,
+                                                       const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
+                                                       const int32_t* __restrict__ vox_tri, const float* __restrict__ vox_av,
+                                                       const float* __restrict__ vox_cov, const int32_t* __restrict__ vox_root,
+                                                       int search_c, float intensity_cov, float intensity_diff,
+                                                       unsigned long long* __restrict__ edge_hash, int hash_cap,
+                                                       int32_t* __restrict__ edge_buf, int edge_cap) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  const uint32_t* bm = bitmap + (size_t)b * g.words;
+  const int32_t* wr = word_rank + (size_t)b * g.words;
+  unsigned long long* table = edge_hash + (size_t)b * hash_cap;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
+    int size = ((double)ri > (double)g.range_num * 0.6) ? 1 : search_c;  // ssc.cpp:397-399
+    float avv = vox_av[base + v];
+    int rv = vox_root[base + v];
+    int last = -1;
+    for (int x = ri - size; x <= ri + size; ++x) {
+      if (x > g.range_num - 1 || x < 0) continue;
+      for (int y = si - size; y <= si + size; ++y) {
+        if (y > g.sector_num - 1 || y < 0) continue;
+        for (int z = ei - size; z <= ei + size; ++z) {
+          if (z > g.azimuth_num - 1 || z < 0) continue;
+          int u = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
+          if (u < 0) continue;
+          if (vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) {
+            int ru = vox_root[base + u];
+            if (ru == last) continue;
+            last = ru;
+            unsigned long long key = ((unsigned long long)(uint32_t)rv << 32) | (uint32_t)ru;
+            unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
+            int slot = (int)(h >> 40) % hash_cap;
+            bool inserted = false, done = false;
+            for (int probe = 0; probe < hash_cap && !done; ++probe) {
+              unsigned long long old = atomicCAS(&table[slot], ~0ull, key);
+              if (old == ~0ull) {
+                inserted = true;
+                done = true;
+              } else if (old == key) {
+                done = true;
+              } else {
+                slot = (slot + 1 == hash_cap) ? 0 : slot + 1;
+              }
+            }
+            if (!done) atomicExch(&scan_counts[b * 8 + 7], -1 << 20);  // table full
+            if (inserted) {
+              int e = atomicAdd(&scan_counts[b * 8 + 7], 1);
+              if (e >= 0 && e < edge_cap) {
+                edge_buf[((size_t)b * edge_cap + e) * 2] = rv;
+                edge_buf[((size_t)b * edge_cap + e) * 2 + 1] = ru;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ordered compaction of the apri points whose rank inside their voxel is < 3 ("clustering events")
+__global__ void __launch_bounds__(1024) k_events(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
+                                                 const int32_t* __restrict__ apri_cid, const int32_t* __restrict__ apri_rank,
+                                                 int32_t* __restrict__ ev_cid) {
+  __shared__ int s_w[33];
+  const int b = blockIdx.x;
+  const int64_t base = off[b];
+  const int M = scan_counts[b * 8 + 2];
+  int carry = 0;
+  for (int m0 = 0; m0 < M; m0 += 1024) {
+    int m = m0 + threadIdx.x;
+    int f = (m < M && apri_cid[base + m] >= 0 && apri_rank[base + m] < 3) ? 1 : 0;
+    int total;
+    int ex = block_excl_scan<1024>(f, &total, s_w);
+    if (f) ev_cid[base + carry + ex] = apri_cid[base + m];
+    carry += total;
+  }
+  if (threadIdx.x == 0) scan_counts[b * 8 + 5] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone binning of an arbitrary cloud (scvod_bin) and the tracking diff kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_only(const float4* __restrict__ pts, int n, BinParams bp, uint8_t* pass, int32_t* vid,
+                                                  int32_t* ri, int32_t* si, int32_t* ei, float* range, float* angle, float* azimuth) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(&pts[i]);
+    BinResult r = dev_bin_point(p.x, p.y, p.z, bp);
+    if (pass) pass[i] = r.pass ? 1 : 0;
+    if (vid) vid[i] = r.vid;
+    if (ri) ri[i] = r.ri;
+    if (si) si[i] = r.si;
+    if (ei) ei[i] = r.ei;
+    if (range) range[i] = r.dis;
+    if (angle) angle[i] = r.angle;
+    if (azimuth) azimuth[i] = r.azimuth;
+  }
+}
+
+// transformCloud (utility.h:394-406: left-to-right float, no FMA) + ungated re-binning
+// (ssc.cpp:1280-1286) + next.hash_cloud.find(voxel_idx) (ssc.cpp:1304) via the bitmap rank.
+__global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, const float4* __restrict__ carried,
+                                               const int32_t* __restrict__ sel, int k, const float* __restrict__ T, BinParams bp,
+                                               GridSpec g, const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr,
+                                               float4* __restrict__ out_xyzi, int32_t* __restrict__ out_hit) {
+  float t[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) t[i] = T[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+    int s = sel[i];
+    float4 p = (s >= 0) ? __ldg(&own[s]) : __ldg(&carried[-1 - s]);
+    float4 q;
+    q.x = da(da(da(dm(t[0], p.x), dm(t[1], p.y)), dm(t[2], p.z)), t[3]);
+    q.y = da(da(da(dm(t[4], p.x), dm(t[5], p.y)), dm(t[6], p.z)), t[7]);
+    q.z = da(da(da(dm(t[8], p.x), dm(t[9], p.y)), dm(t[10], p.z)), t[11]);
+    q.w = p.w;
+    out_xyzi[i] = q;
+    BinResult r = dev_bin_point(q.x, q.y, q.z, bp);
+    out_hit[i] = vox_lookup(bm, wr, g, r.vid);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_final_labels(const int32_t* __restrict__ apri_src, const int32_t* __restrict__ apri_cid,
+                                                      const uint8_t* __restrict__ vox_cls, int m_total, uint8_t* __restrict__ cls) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < m_total; m += gridDim.x * blockDim.x) {
+    int cid = apri_cid[m];
+    if (cid >= 0) cls[apri_src[m]] = vox_cls[cid];
+  }
+}
+
+// static submap: every non-dynamic point of a frame moved to the map frame (transformCloud arithmetic)
+__global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, const uint8_t* __restrict__ cls, int n,
+                                                const float* __restrict__ T, float4* __restrict__ out,
+                                                unsigned long long* __restrict__ counter, long long cap) {
+  float t[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) t[i] = T[i];
+  const int lane = threadIdx.x & 31;
+  for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += gridDim.x * blockDim.x) {
+    int i = i0 + lane;
+    bool keep = (i < n) && cls[i] != SCVOD_PT_DYNAMIC;
+    unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (!mask) continue;
+    unsigned long long basepos = 0;
+    if (lane == 0) basepos = atomicAdd(counter, (unsigned long long)__popc(mask));  // warp-aggregated append
+    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+    if (keep) {
+      long long pos = (long long)basepos + __popc(mask & ((1u << lane) - 1));
+      if (pos < cap) {
+        float4 p = __ldg(&pts[i]);
+        float4 q;
+        q.x = da(da(da(dm(t[0], p.x), dm(t[1], p.y)), dm(t[2], p.z)), t[3]);
+        q.y = da(da(da(dm(t[4], p.x), dm(t[5], p.y)), dm(t[6], p.z)), t[7]);
+        q.z = da(da(da(dm(t[8], p.x), dm(t[9], p.y)), dm(t[10], p.z)), t[11]);
+        q.w = p.w;
+        out[pos] = q;
+      }
+    }
+  }
+}
+
+__global__ void k_atan2f_probe(const float* y, const float* x, float* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = dev_atan2f(y[i], x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch wrappers
+// ------------------------------------------------------------------------------------------------
+static BinParams make_bin_params(const HostParams& hp) {
+  BinParams bp;
+  bp.min_dis = hp.p.min_dis;
+  bp.max_dis = hp.p.max_dis;
+  bp.min_angle = hp.p.min_angle;
+  bp.max_angle = hp.p.max_angle;
+  bp.min_azimuth = hp.p.min_azimuth;
+  bp.max_azimuth = hp.p.max_azimuth;
+  bp.range_res = hp.p.range_res;
+  bp.sector_res = hp.p.sector_res;
+  bp.azimuth_res = hp.p.azimuth_res;
+  bp.range_num = hp.g.range_num;
+  bp.sector_num = hp.g.sector_num;
+  return bp;
+}
+
+static GroundConst make_ground_const(const HostParams& hp) {
+  GroundConst gc;
+  const double h = (double)hp.p.sensor_height;  // set_sensor(const double&) receives the float param
+  const double min_range = 2.7, max_range = 80.0;
+  gc.low_thr = -1.8 * h;
+  gc.seed_thr = -1.1 * h;
+  gc.min_range = min_range;
+  gc.max_range = max_range;
+  gc.z2 = (7 * min_range + max_range) / 8.0;
+  gc.z3 = (3 * min_range + max_range) / 4.0;
+  gc.z4 = (min_range + max_range) / 2.0;
+  gc.rmin[0] = min_range;
+  gc.rmin[1] = gc.z2;
+  gc.rmin[2] = gc.z3;
+  gc.rmin[3] = gc.z4;
+  gc.ring_size[0] = (gc.z2 - min_range) / 2;
+  gc.ring_size[1] = (gc.z3 - gc.z2) / 4;
+  gc.ring_size[2] = (gc.z4 - gc.z3) / 4;
+  gc.ring_size[3] = (max_range - gc.z4) / 4;
+  const int sectors[4] = {16, 32, 54, 32};
+  for (int k = 0; k < 4; ++k) gc.sector_size[k] = 2 * M_PI / sectors[k];
+  return gc;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// grid.x for "per point of a scan" kernels: enough CTAs per scan that nscans * gx covers the GPU a
+// few times over, in multiples of the SM count.
+static int grid_x_for(int nscans, int per_scan_items, int threads) {
+  int want = (per_scan_items + threads - 1) / threads;
+  int cap = (num_sms() * 8 + nscans - 1) / nscans;
+  if (cap < 1) cap = 1;
+  return want < cap ? (want < 1 ? 1 : want) : cap;
+}
+
+int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_points, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  GroundConst gc = make_ground_const(hp);
+  BinParams bp = make_bin_params(hp);
+  int launches = 0;
+  cudaMemsetAsync(d.patch_cnt, 0, sizeof(int32_t) * (size_t)nscans * kNumPatches, st);
+  dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
+  k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, d.patch_cnt, d.cls);
+  k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur);
+  k_patch_scatter<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_of, d.patch_off, d.patch_cur, d.bucket_kv);
+  FitArgs fa;
+  fa.pts = d.pts;
+  fa.off = d.off;
+  fa.patch_cnt = d.patch_cnt;
+  fa.patch_off = d.patch_off;
+  fa.bucket_kv = d.bucket_kv;
+  fa.sorted_idx = d.sorted_idx;
+  fa.slot_pos = d.slot_pos;
+  fa.slot_apos = d.slot_apos;
+  fa.slot_vid = d.slot_vid;
+  fa.slot_patch = d.slot_patch;
+  fa.patch_out = d.patch_out;
+  fa.patch_dbg = d.patch_dbg;
+  fa.cls = d.cls;
+  fa.err = d.scan_counts + (size_t)d.cap_scans * 8;  // one extra int past the per-scan counters
+  fa.gc = gc;
+  fa.bp = bp;
+  static bool attr_set = false;
+  const int smem_small = kFitSmall * 20, smem_large = kFitLarge * 20;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_patch_fit<kFitSmall, 0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
+    cudaFuncSetAttribute(k_patch_fit<kFitLarge, kFitSmall, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large);
+    attr_set = true;
+  }
+  dim3 gfit(kNumPatches, nscans);
+  k_patch_fit<kFitSmall, 0, 128><<<gfit, 128, smem_small, st>>>(fa);
+  k_patch_fit<kFitLarge, kFitSmall, 256><<<gfit, 256, smem_large, st>>>(fa);
+  k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts);
+  k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
+                             d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls);
+  launches += 7;
+  return launches;
+}
+
+int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int max_scan_points, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  BinParams bp = make_bin_params(hp);
+  cudaMemsetAsync(d.bitmap, 0, sizeof(uint32_t) * (size_t)nscans * hp.g.words, st);
+  dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
+  k_vox_mark<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap);
+  k_vox_rank<<<nscans, 1024, 0, st>>>(d.off, hp.g, d.bitmap, d.word_rank, d.vox_vid, d.vox_cnt, d.scan_counts);
+  k_vox_count<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap, d.word_rank, d.apri_cid, d.vox_cnt);
+  k_vox_offsets<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_cur);
+  k_vox_fill<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.vox_off, d.vox_cur, d.vox_pts_tmp);
+  dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 8), nscans);  // one warp per voxel, 8 warps per CTA
+  k_vox_stats<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_pts_tmp, d.apri_xyzi, bp, hp.p, d.vox_pts,
+                                  d.apri_rank, d.vox_av, d.vox_cov, d.vox_center, d.vox_tri, d.vox_bbox);
+  return 6;
+}
+
+int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int max_scan_points, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  cudaMemsetAsync(d.edge_hash, 0xff, sizeof(unsigned long long) * (size_t)nscans * d.hash_cap, st);
+  dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 256), nscans);
+  k_vox_nbr<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_nbr, d.vox_root);
+  k_ccl_union<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_nbr, d.vox_root);
+  k_ccl_flatten<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_root);
+  k_similar_edges<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_av, d.vox_cov, d.vox_root,
+                                      hp.p.search_c, hp.p.intensity_cov, hp.p.intensity_diff,
+                                      reinterpret_cast<unsigned long long*>(d.edge_hash), d.hash_cap, d.edge_buf, d.edge_cap);
+  k_events<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.apri_rank, d.ev_cid);
+  return 5;
+}
+
+int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t* pass, int32_t* vid, int32_t* ri, int32_t* si,
+                    int32_t* ei, float* range, float* angle, float* azimuth, void* stream_) {
+  if (n <= 0) return 0;
+  int blocks = (n + 255) / 256;
+  int cap = num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_bin_only<<<blocks, 256, 0, (cudaStream_t)stream_>>>(pts_dev, n, make_bin_params(hp), pass, vid, ri, si, ei, range, angle, azimuth);
+  return 1;
+}
+
+int launch_track(const HostParams& hp, const float4* own_xyzi, const float4* carried, const int32_t* sel, int k, const float* T12_dev,
+                 const uint32_t* next_bitmap, const int32_t* next_word_rank, float4* out_xyzi, int32_t* out_hit, void* stream_) {
+  if (k <= 0) return 0;
+  int blocks = (k + 255) / 256;
+  int cap = num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_track<<<blocks, 256, 0, (cudaStream_t)stream_>>>(own_xyzi, carried, sel, k, T12_dev, make_bin_params(hp), hp.g, next_bitmap,
+                                                   next_word_rank, out_xyzi, out_hit);
+  return 1;
+}
+
+int launch_final_labels(const int32_t* apri_src, const int32_t* apri_cid, const uint8_t* vox_cls, int m, uint8_t* cls, void* stream_) {
+  if (m <= 0) return 0;
+  int blocks = (m + 255) / 256;
+  k_final_labels<<<blocks, 256, 0, (cudaStream_t)stream_>>>(apri_src, apri_cid, vox_cls, m, cls);
+  return 1;
+}
+
+int launch_submap(const float4* pts, const uint8_t* cls, int n, const float* T12_dev, float4* out, unsigned long long* counter,
+                  long long cap, void* stream_) {
+  if (n <= 0) return 0;
+  int blocks = (n + 255) / 256;
+  int capb = num_sms() * 8;
+  if (blocks > capb) blocks = capb;
+  k_submap<<<blocks, 256, 0, (cudaStream_t)stream_>>>(pts, cls, n, T12_dev, out, counter, cap);
+  return 1;
+}
+
+int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream_) {
+  k_atan2f_probe<<<num_sms() * 8, 256, 0, (cudaStream_t)stream_>>>(y, x, out, n);
+  return 1;
+}
+
+}  // namespace scvod

@@ -85,6 +85,9 @@ int scvod_create(const scvod_params* p, int device, int max_points, int max_batc
 int scvod_destroy(scvod_ctx* ctx);
 const char* scvod_last_error(void);
 int scvod_num_kernel_launches(const scvod_ctx* ctx, int64_t* out); /* kernels launched so far */
+/* options: "inspect" (keep per-stage cluster names for scvod_frame_point_cluster; default 1),
+ * "host_threads" (threads used for the per-scan cluster bookkeeping). */
+int scvod_set_option(scvod_ctx* ctx, const char* key, int value);
 
 /* ---- stage entry points (single scan, host buffers; replace the bodies named on each line) --- */
 
@@ -122,6 +125,9 @@ int scvod_reset_frames(scvod_ctx* ctx); /* SSC::reset + frame_set.clear() */
 /* Per-input-point outcome class (enum scvod_point_class) of frame f; cls holds n_in bytes. */
 int scvod_frame_labels(scvod_ctx* ctx, int frame, uint8_t* cls, int n);
 
+/* Labels of frames [f0,f1) concatenated in frame order into one host buffer of `cap` bytes. */
+int scvod_labels_range(scvod_ctx* ctx, int f0, int f1, uint8_t* cls, int64_t cap);
+
 /* frame inspection — sizes: counts[0]=n_in, [1]=n_ground, [2]=n_nonground, [3]=n_apri (cloud_use),
  * [4]=n_voxels (hash_cloud.size()), [5]=clusters after CVC, [6]=after intensity refine,
  * [7]=after bounding-box refine, [8]=clusters now (after tracking mutations). */
@@ -146,6 +152,12 @@ int scvod_frame_clusters(scvod_ctx* ctx, int frame, int cap, int32_t* name, int3
  * ssc.cpp:531-555).  Written to device memory for the NCCL all-gather; returns the point count. */
 int scvod_static_submap_dev(scvod_ctx* ctx, int f0, int f1, const float* poses6, void* out_xyzi_dev,
                             int64_t cap_points, int64_t* n_points);
+
+/* Per-patch plane fits of the most recent ground pass of batch slot `slot`: 504 rows of 12 floats
+ * {normal[3], mean[3], singular values[3], d, decision, npts}; rows of skipped patches are stale. */
+int scvod_last_patch_records(scvod_ctx* ctx, int slot, float* rec504x12);
+/* The device port of glibc's atan2f evaluated on the GPU (libm-parity test hook). */
+int scvod_atan2f_device(scvod_ctx* ctx, const float* y, const float* x, float* out, int64_t n);
 
 /* ---- helpers shared by tests and the bench ---------------------------------------------------- */
 /* trans_next.inverse() * trans_pre of SSC::tracking (ssc.cpp:1255-1257) as 12 floats row-major 3x4. */

@@ -1,0 +1,202 @@
+"""Shared fixtures: the product package (ctypes over libscvod_b200.so) and the CPU oracle.
+
+The oracle (oracle/_build/libscvod_oracle.so) is test infrastructure: it is only ever loaded here, in
+__graft_entry__.smoke() and in bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes
+import importlib.util
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "dr-using-scv-od_b200")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libscvod_oracle.so")
+SEED = 0x5C0D0000
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_package():
+    name = "scvod_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Oracle:
+    """ctypes wrapper of the CPU restatement (oracle/scvod_oracle.cpp)."""
+
+    def __init__(self, params):
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+        self.lib = ctypes.CDLL(ORACLE_SO)
+        self.lib.orc_create.restype = ctypes.c_void_p
+        self.lib.orc_run_sequence.restype = ctypes.c_double
+        self.lib.orc_atan2f.restype = ctypes.c_float
+        self.params = params
+        self.h = ctypes.c_void_p(self.lib.orc_create(ctypes.byref(params)))
+        self.sizes = []
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def grid_dims(self):
+        out = (ctypes.c_int * 4)()
+        self.lib.orc_grid_dims(self.h, out)
+        return list(out)
+
+    def push_scan(self, xyzi):
+        xyzi = np.ascontiguousarray(xyzi, np.float32)
+        self.sizes.append(len(xyzi))
+        return self.lib.orc_push_scan(self.h, _ptr(xyzi), len(xyzi))
+
+    def track(self, poses):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        self.lib.orc_track(self.h, _ptr(poses), len(poses))
+
+    def reset(self):
+        self.lib.orc_reset_frames(self.h)
+        self.sizes = []
+
+    def counts(self, f):
+        c = np.zeros(9, np.int32)
+        self.lib.orc_frame_counts(self.h, f, _ptr(c))
+        return c
+
+    def labels(self, f):
+        cls = np.zeros(max(self.sizes[f], 1), np.uint8)
+        self.lib.orc_frame_labels(self.h, f, _ptr(cls))
+        return cls[: self.sizes[f]]
+
+    def ground_order(self, f):
+        c = self.counts(f)
+        g = np.zeros(max(int(c[1]), 1), np.int32)
+        ng = np.zeros(max(int(c[2]), 1), np.int32)
+        self.lib.orc_frame_ground_order(self.h, f, _ptr(g), _ptr(ng))
+        return g[: c[1]], ng[: c[2]]
+
+    def apri(self, f):
+        m = int(self.counts(f)[3])
+        src = np.zeros(max(m, 1), np.int32)
+        vid = np.zeros(max(m, 1), np.int32)
+        self.lib.orc_frame_apri(self.h, f, _ptr(src), _ptr(vid))
+        return src[:m], vid[:m]
+
+    def voxels(self, f):
+        v = int(self.counts(f)[4])
+        cap = max(v, 1)
+        out = {"voxel_idx": np.zeros(cap, np.int32), "count": np.zeros(cap, np.int32), "av": np.zeros(cap, np.float32),
+               "cov": np.zeros(cap, np.float32), "center": np.zeros((cap, 3), np.float32), "tri": np.zeros((cap, 3), np.int32),
+               "label": np.zeros(cap, np.int32)}
+        self.lib.orc_frame_voxels(self.h, f, _ptr(out["voxel_idx"]), _ptr(out["count"]), _ptr(out["av"]), _ptr(out["cov"]),
+                                  _ptr(out["center"]), _ptr(out["tri"]), _ptr(out["label"]))
+        return {k: a[:v] for k, a in out.items()}
+
+    def point_cluster(self, f, stage):
+        m = int(self.counts(f)[3])
+        name = np.zeros(max(m, 1), np.int32)
+        self.lib.orc_frame_point_cluster(self.h, f, stage, _ptr(name))
+        return name[:m]
+
+    def clusters(self, f):
+        cap = max(int(self.counts(f)[8]), 1)
+        out = {"name": np.zeros(cap, np.int32), "type": np.zeros(cap, np.int32), "state": np.zeros(cap, np.int32),
+               "npts": np.zeros(cap, np.int32), "nvox": np.zeros(cap, np.int32), "bbox": np.zeros((cap, 6), np.float32)}
+        n = self.lib.orc_frame_clusters(self.h, f, cap, _ptr(out["name"]), _ptr(out["type"]), _ptr(out["state"]), _ptr(out["npts"]),
+                                        _ptr(out["nvox"]), _ptr(out["bbox"]))
+        return {k: a[:n] for k, a in out.items()}
+
+    # stage-level helpers
+    def bin(self, xyzi):
+        xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = len(xyzi)
+        out = {"pass": np.zeros(n, np.uint8), "voxel_idx": np.zeros(n, np.int32), "range_idx": np.zeros(n, np.int32),
+               "sector_idx": np.zeros(n, np.int32), "azimuth_idx": np.zeros(n, np.int32), "range": np.zeros(n, np.float32),
+               "angle": np.zeros(n, np.float32), "azimuth": np.zeros(n, np.float32)}
+        self.lib.orc_bin(ctypes.byref(self.params), _ptr(xyzi), n, _ptr(out["pass"]), _ptr(out["voxel_idx"]), _ptr(out["range_idx"]),
+                         _ptr(out["sector_idx"]), _ptr(out["azimuth_idx"]), _ptr(out["range"]), _ptr(out["angle"]), _ptr(out["azimuth"]))
+        return out
+
+    def ground(self, xyzi, sensor_height=None):
+        xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = len(xyzi)
+        g = np.zeros(max(n, 1), np.int32)
+        ng = np.zeros(max(n, 1), np.int32)
+        cls = np.zeros(max(n, 1), np.uint8)
+        rec = np.zeros((504, 15), np.float32)
+        cg, cng = ctypes.c_int32(), ctypes.c_int32()
+        h = float(np.float32(self.params.sensor_height)) if sensor_height is None else sensor_height
+        npatch = self.lib.orc_ground(_ptr(xyzi), n, ctypes.c_double(h), _ptr(g), ctypes.byref(cg), _ptr(ng), ctypes.byref(cng),
+                                     _ptr(cls), _ptr(rec), 504)
+        return g[: cg.value].copy(), ng[: cng.value].copy(), cls[:n], rec[:npatch]
+
+    def atan2f_many(self, y, x):
+        y = np.ascontiguousarray(y, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty_like(y)
+        self.lib.orc_atan2f_many(_ptr(y), _ptr(x), _ptr(out), ctypes.c_int64(y.size))
+        return out
+
+    def relative_pose(self, pose_next, pose_pre):
+        T = np.zeros(12, np.float32)
+        a = np.ascontiguousarray(pose_next, np.float32)
+        b = np.ascontiguousarray(pose_pre, np.float32)
+        self.lib.orc_relative_pose(_ptr(a), _ptr(b), _ptr(T))
+        return T.reshape(3, 4)
+
+    def svd3(self, A):
+        A = np.ascontiguousarray(A, np.float32).reshape(9)
+        U = np.zeros(9, np.float32)
+        sv = np.zeros(3, np.float32)
+        self.lib.orc_svd3(_ptr(A), _ptr(U), _ptr(sv))
+        return U.reshape(3, 3), sv
+
+    def run_sequence(self, scans, poses, nthreads=1, want_labels=True):
+        off = np.zeros(len(scans) + 1, np.int64)
+        off[1:] = np.cumsum([len(s) for s in scans])
+        flat = np.ascontiguousarray(np.concatenate(scans, axis=0), np.float32)
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        labels = np.zeros(max(int(off[-1]), 1), np.uint8) if want_labels else None
+        secs = self.lib.orc_run_sequence(ctypes.byref(self.params), _ptr(flat), _ptr(off), len(scans), _ptr(poses), int(nthreads), _ptr(labels))
+        return secs, (labels[: off[-1]] if want_labels else None), off
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return load_package()
+
+
+@pytest.fixture(scope="session")
+def kitti_params(pkg):
+    return pkg.semantickitti_params()
+
+
+@pytest.fixture()
+def oracle(kitti_params):
+    o = Oracle(kitti_params)
+    yield o
+    o.close()
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
