@@ -1056,3 +1056,39 @@ extern "C" int scvod_atan2f_device(scvod_ctx* c, const float* y, const float* x,
   dy.release(); dx.release(); dout.release();
   return SCVOD_OK;
 }
+
+// Host-only hook: the cluster bookkeeping (host_cluster.cpp) on caller-provided voxel tables, without a
+// GPU.  Used by the CPU test-suite to check the name replay / fusion / bounding-box / car logic against
+// the oracle; the product pipeline calls segment_and_recognize() directly with GPU-produced tables.
+extern "C" int scvod_host_segment(const scvod_params* p, int V, const int32_t* vox_cnt, const int32_t* vox_root, const int32_t* vox_nbr,
+                                  const float* vox_bbox, int n_events, const int32_t* ev_cid, int n_edges, const int32_t* edges,
+                                  int32_t* name_stage0, int32_t* name_stage1, int32_t* name_stage2, int32_t n_clusters[3], int cap,
+                                  int32_t* cluster_name, int32_t* cluster_type, int32_t* max_name) {
+  if (!p || V < 0) return fail(SCVOD_ERR_ARG, "bad arguments");
+  ScanTables t;
+  t.V = V;
+  t.n_events = n_events;
+  t.n_edges = n_edges;
+  t.vox_cnt = vox_cnt;
+  t.vox_root = vox_root;
+  t.vox_nbr = vox_nbr;
+  t.vox_bbox = vox_bbox;
+  t.ev_cid = ev_cid;
+  t.edges = edges;
+  FrameClusters fc;
+  if (!segment_and_recognize(*p, t, fc, true)) return fail(SCVOD_ERR_STATE, "replayed partition differs from the given components");
+  if (name_stage0) std::memcpy(name_stage0, fc.vox_name_stage[0].data(), sizeof(int32_t) * V);
+  if (name_stage1) std::memcpy(name_stage1, fc.vox_name_stage[1].data(), sizeof(int32_t) * V);
+  if (name_stage2) std::memcpy(name_stage2, fc.vox_name_stage[2].data(), sizeof(int32_t) * V);
+  if (n_clusters)
+    for (int i = 0; i < 3; ++i) n_clusters[i] = fc.n_clusters[i];
+  if (max_name) *max_name = fc.max_name;
+  int i = 0;
+  for (auto& cs : fc.cluster_set) {
+    if (i >= cap) break;
+    if (cluster_name) cluster_name[i] = cs.first;
+    if (cluster_type) cluster_type[i] = cs.second.type;
+    ++i;
+  }
+  return (int)fc.cluster_set.size();
+}

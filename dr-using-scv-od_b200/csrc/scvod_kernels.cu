@@ -329,14 +329,13 @@ constexpr uint32_t F_PASS = 2u;   // survives the SSC gates
 constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md hard part 7)
 constexpr uint32_t F_BIN = 8u;    // binning was evaluated for this point
 
-template <int MAXN, int MINN, int THREADS>
+// GLOBAL = true is the overflow tier for patches that do not fit the largest shared-memory tile: the
+// same code runs with its scratch arrays placed in the (L2-resident) global buffers of the patch itself.
+template <int MAXN, int MINN, int THREADS, bool GLOBAL>
 __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* kv = reinterpret_cast<uint64_t*>(smem_raw);
-  float* sx = reinterpret_cast<float*>(kv + MAXN);
-  float* sy = sx + MAXN;
-  float* sz = sy + MAXN;
-  uint32_t* kv32 = reinterpret_cast<uint32_t*>(kv);  // [2*j] = low word, [2*j+1] = high word
+  uint64_t* kv;
+  float *sx, *sy, *sz;
   __shared__ float s_plane[4];   // n0 n1 n2 th_dist_d
   __shared__ float s_stat[8];    // mean z, sv0..2, d, mean x, mean y
   __shared__ int s_int[8];       // decision, init_idx, ...
@@ -345,12 +344,21 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
 
   const int p = blockIdx.x, b = blockIdx.y;
   const int n = a.patch_cnt[b * kNumPatches + p];
-  if (n <= MINN || n > MAXN) {
-    if (MINN > 0 && n > kFitLarge && threadIdx.x == 0) atomicOr(a.err, 1);  // patch larger than the largest tile
-    return;
-  }
+  if (n <= MINN || n > MAXN) return;
   const int64_t base = a.off[b];
   const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+  if (GLOBAL) {
+    kv = const_cast<uint64_t*>(a.bucket_kv) + base + slot0;  // sorted in place
+    sx = reinterpret_cast<float*>(a.slot_pos + base + slot0);
+    sy = reinterpret_cast<float*>(a.slot_apos + base + slot0);
+    sz = reinterpret_cast<float*>(a.slot_vid + base + slot0);
+  } else {
+    kv = reinterpret_cast<uint64_t*>(smem_raw);
+    sx = reinterpret_cast<float*>(kv + MAXN);
+    sy = sx + MAXN;
+    sz = sy + MAXN;
+  }
+  uint32_t* kv32 = reinterpret_cast<uint32_t*>(kv);  // [2*j] = low word, [2*j+1] = high word
   const int tid = threadIdx.x;
   int32_t* pout = a.patch_out + (b * kNumPatches + p) * 4;
 
@@ -371,20 +379,38 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   }
 
   // ---- load + bitonic sort by (z key, original index) ---------------------------------------
+  // Bitonic network with a "flip" first step per merge, so every compare-exchange is ascending and
+  // the virtual +inf padding above n never moves: indices >= n are simply skipped.
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  for (int j = tid; j < np2; j += THREADS) kv[j] = (j < n) ? a.bucket_kv[base + slot0 + j] : ~0ull;
+  if (!GLOBAL) {
+    for (int j = tid; j < n; j += THREADS) kv[j] = a.bucket_kv[base + slot0 + j];
+  }
   __syncthreads();
   for (int k = 2; k <= np2; k <<= 1) {
-    for (int s = k >> 1; s > 0; s >>= 1) {
-      for (int t = tid; t < (np2 >> 1); t += THREADS) {
-        int i = ((t & ~(s - 1)) << 1) | (t & (s - 1));
-        int l = i | s;
-        bool up = ((i & k) == 0);
+    const int hk = k >> 1;
+    for (int t = tid; t < (np2 >> 1); t += THREADS) {
+      int blk = t / hk, j = t - blk * hk;
+      int i = blk * k + j, l = blk * k + k - 1 - j;
+      if (l < n) {
         uint64_t x = kv[i], y = kv[l];
-        if ((x > y) == up) {
+        if (x > y) {
           kv[i] = y;
           kv[l] = x;
+        }
+      }
+    }
+    __syncthreads();
+    for (int s2 = hk >> 1; s2 > 0; s2 >>= 1) {
+      for (int t = tid; t < (np2 >> 1); t += THREADS) {
+        int i = ((t & ~(s2 - 1)) << 1) | (t & (s2 - 1));
+        int l = i | s2;
+        if (l < n) {
+          uint64_t x = kv[i], y = kv[l];
+          if (x > y) {
+            kv[i] = y;
+            kv[l] = x;
+          }
         }
       }
       __syncthreads();
@@ -596,8 +622,10 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   }
   __syncthreads();
   for (int j = tid; j < n; j += THREADS) {
-    a.slot_pos[base + slot0 + j] = spos[j];
-    a.slot_apos[base + slot0 + j] = sapos[j];
+    if (!GLOBAL) {
+      a.slot_pos[base + slot0 + j] = spos[j];
+      a.slot_apos[base + slot0 + j] = sapos[j];
+    }
     a.slot_vid[base + slot0 + j] = (int)kv32[2 * j];
   }
   if (tid == 0) {
@@ -1194,17 +1222,24 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   static bool attr_set = false;
   const int smem_small = kFitSmall * 20, smem_large = kFitLarge * 20;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_patch_fit<kFitSmall, 0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
-    cudaFuncSetAttribute(k_patch_fit<kFitLarge, kFitSmall, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large);
+    cudaFuncSetAttribute(k_patch_fit<kFitSmall, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
+    cudaFuncSetAttribute(k_patch_fit<kFitLarge, kFitSmall, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large);
     attr_set = true;
   }
   dim3 gfit(kNumPatches, nscans);
-  k_patch_fit<kFitSmall, 0, 128><<<gfit, 128, smem_small, st>>>(fa);
-  k_patch_fit<kFitLarge, kFitSmall, 256><<<gfit, 256, smem_large, st>>>(fa);
+  k_patch_fit<kFitSmall, 0, 128, false><<<gfit, 128, smem_small, st>>>(fa);
+  if (max_scan_points > kFitSmall) {
+    k_patch_fit<kFitLarge, kFitSmall, 256, false><<<gfit, 256, smem_large, st>>>(fa);
+    launches += 1;
+  }
+  if (max_scan_points > kFitLarge) {  // overflow tier: scratch in global memory
+    k_patch_fit<0x3fffffff, kFitLarge, 256, true><<<gfit, 256, 0, st>>>(fa);
+    launches += 1;
+  }
   k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts);
   k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
                              d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls);
-  launches += 7;
+  launches += 6;
   return launches;
 }
 

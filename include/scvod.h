@@ -159,6 +159,15 @@ int scvod_last_patch_records(scvod_ctx* ctx, int slot, float* rec504x12);
 /* The device port of glibc's atan2f evaluated on the GPU (libm-parity test hook). */
 int scvod_atan2f_device(scvod_ctx* ctx, const float* y, const float* x, float* out, int64_t n);
 
+/* Host-only: the cluster bookkeeping of SSC::segment + recognize (ssc.cpp:299-393, 571-635, 437-467,
+ * 834-895) on caller-provided voxel tables (the tables the GPU stages produce).  Needs no device; used
+ * by the CPU test-suite.  Returns the number of clusters (<0 on error). */
+int scvod_host_segment(const scvod_params* p, int V, const int32_t* vox_cnt, const int32_t* vox_root,
+                       const int32_t* vox_nbr, const float* vox_bbox, int n_events, const int32_t* ev_cid,
+                       int n_edges, const int32_t* edges, int32_t* name_stage0, int32_t* name_stage1,
+                       int32_t* name_stage2, int32_t n_clusters[3], int cap, int32_t* cluster_name,
+                       int32_t* cluster_type, int32_t* max_name);
+
 /* ---- helpers shared by tests and the bench ---------------------------------------------------- */
 /* trans_next.inverse() * trans_pre of SSC::tracking (ssc.cpp:1255-1257) as 12 floats row-major 3x4. */
 void scvod_relative_pose(const float pose_next6[6], const float pose_pre6[6], float T[12]);

@@ -1,0 +1,262 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): bit-exact voxel indices and per-point dynamic/static classes;
+descriptor floats within 1e-4 (intensity mean/variance are in fact bit-exact; only the voxel "centre",
+which goes through sinf/cosf/tanf, differs in the last bits).  Nothing here reads /root/reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import conftest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DESC_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ssc(pkg):
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=131072, max_batch=8)
+    yield s
+    s.close()
+
+
+def bits(a):
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+# ---- scalar arithmetic ---------------------------------------------------------------------------
+def test_device_atan2f_equals_host_libm(ssc, oracle):
+    rng = np.random.default_rng(2024)
+    n = 4_000_000
+    y = rng.uniform(-80, 80, n).astype(np.float32)
+    x = rng.uniform(-80, 80, n).astype(np.float32)
+    # structured edge inputs: zeros, signed zeros, axes, tiny/huge ratios, infinities, NaN
+    sp = np.array([0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 1e30, -1e30, np.inf, -np.inf, 0.4375, 0.6875, 1.1875, 2.4375, 1.5, 2.0 ** 25,
+                   2.0 ** -29], np.float32)
+    yy, xx = np.meshgrid(sp, sp)
+    y = np.concatenate([y, yy.ravel(), rng.uniform(-3, 3, 100000).astype(np.float32), rng.normal(size=100000).astype(np.float32) * 1e-3])
+    x = np.concatenate([x, xx.ravel(), np.ones(100000, np.float32), rng.uniform(1, 80, 100000).astype(np.float32)])
+    d = ssc.atan2f_device(y, x)
+    h = oracle.atan2f_many(y, x)
+    assert int((d.view(np.uint32) != h.view(np.uint32)).sum()) == 0
+
+
+@pytest.mark.parametrize("config", ["semantickitti", "parkinglot"])
+def test_binning_bit_exact(pkg, config):
+    P = pkg.semantickitti_params() if config == "semantickitti" else pkg.parkinglot_params()
+    s = pkg.SSC(P, device=0, max_points=65536, max_batch=1)
+    o = conftest.Oracle(P)
+    rng = np.random.default_rng(5)
+    n = 1_000_000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-45, 45, n)
+    pts[:, 1] = rng.uniform(-45, 45, n)
+    pts[:, 2] = rng.uniform(-4, 12, n)
+    pts[:1000, 1] = 0.0                      # y == 0 quirk rows
+    pts[1000:1100, :2] = 0.0                 # x == y == 0
+    pts[1100:1200, 0] = P.min_dis
+    pts[1100:1200, 1] = 0.0                  # dis == min_dis
+    g, c = s.makeApriVec(pts), o.bin(pts)
+    for k in g:
+        assert np.array_equal(bits(g[k]), bits(c[k])), k
+    z = np.load(os.path.join(GOLD, "bin_edge_cases.npz"))
+    if config == "semantickitti":
+        g = s.makeApriVec(z["xyzi"])
+        for k in g:
+            assert np.array_equal(bits(g[k]), bits(z["o_" + k])), k
+    assert len(s.makeApriVec(np.zeros((0, 4), np.float32))["pass"]) == 0  # empty input
+    s.close()
+    o.close()
+
+
+# ---- ground ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scan_id,rings,cols", [(0, 64, 1800), (11, 64, 1800), (2, 16, 450), (4, 128, 2250)])
+def test_ground_order_bit_exact(pkg, oracle, scan_id, rings, cols):
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=rings * cols, max_batch=1)
+    cloud, _ = pkg.synth_scan(conftest.SEED, scan_id, rings=rings, cols=cols)
+    g, ng = s.extractGroudByPatchWork(cloud)
+    og, ong, ocls, orec = oracle.ground(cloud)
+    assert np.array_equal(g, og) and np.array_equal(ng, ong)
+    rec = s.last_patch_records(0)
+    base, secs = [0, 32, 160, 376], [16, 32, 54, 32]
+    for r in orec:  # per-patch plane parameters, bit for bit
+        pid = base[int(r[0])] + int(r[1]) * secs[int(r[0])] + int(r[2])
+        assert np.array_equal(rec[pid, 0:3].view(np.uint32), r[5:8].view(np.uint32)), f"normal of patch {pid}"
+        assert np.array_equal(rec[pid, 6:9].view(np.uint32), r[11:14].view(np.uint32)), f"singular values of patch {pid}"
+        assert int(rec[pid, 10]) == int(r[4]) and int(rec[pid, 11]) == int(r[3])
+    s.close()
+
+
+def test_ground_ragged_inputs(ssc, oracle, pkg):
+    for cloud in (np.zeros((0, 4), np.float32), np.array([[5, 5, -1.7, 1]], np.float32),
+                  np.tile(np.array([[6, 1, -1.7, 1]], np.float32), (11, 1)) + np.arange(11, dtype=np.float32)[:, None] * 1e-3):
+        g, ng = ssc.extractGroudByPatchWork(cloud)
+        og, ong, _, _ = oracle.ground(cloud)
+        assert np.array_equal(g, og) and np.array_equal(ng, ong)
+
+
+# ---- whole path -------------------------------------------------------------------------------------
+def compare_frames(ssc, orc, nframes, pkg):
+    for f in range(nframes):
+        assert np.array_equal(ssc.frame_counts(f)[:8], orc.counts(f)[:8])
+        g, ng = ssc.frame_ground_order(f)
+        og, ong = orc.ground_order(f)
+        assert np.array_equal(g, og) and np.array_equal(ng, ong)
+        src, vid = ssc.frame_apri(f)
+        osrc, ovid = orc.apri(f)
+        assert np.array_equal(src, osrc) and np.array_equal(vid, ovid)  # bit-exact voxel indices
+        vg, vo = ssc.frame_voxels(f), orc.voxels(f)
+        for k in ("voxel_idx", "count", "tri", "label"):
+            assert np.array_equal(vg[k], vo[k]), k
+        for k in ("av", "cov", "center"):
+            assert np.allclose(vg[k], vo[k], rtol=0, atol=DESC_ATOL), k
+        assert np.array_equal(vg["av"].view(np.uint32), vo["av"].view(np.uint32))
+        assert np.array_equal(vg["cov"].view(np.uint32), vo["cov"].view(np.uint32))
+        for st in range(3):
+            assert np.array_equal(ssc.frame_point_cluster(f, st), orc.point_cluster(f, st)), f"cluster names, stage {st}"
+        cg, co = ssc.frame_clusters(f), orc.clusters(f)
+        for k in ("name", "type", "npts", "nvox", "bbox"):
+            assert np.array_equal(bits(cg[k]), bits(co[k])), k
+
+
+def test_pipeline_stage_by_stage_kitti(pkg, ssc, oracle):
+    ssc.reset()
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED, k) for k in range(6)])
+    poses = np.stack(poses)
+    ssc.process(scans)
+    for s in scans:
+        oracle.push_scan(s)
+    compare_frames(ssc, oracle, len(scans), pkg)
+    ssc.tracking(poses)
+    oracle.track(poses)
+    ndyn = 0
+    for f in range(len(scans)):
+        lg, lo = ssc.frame_labels(f), oracle.labels(f)
+        assert np.array_equal(lg, lo)  # bit-exact per-point classes
+        ndyn += int((lg == pkg.PT_DYNAMIC).sum())
+        cg, co = ssc.frame_clusters(f), oracle.clusters(f)
+        for k in ("name", "type", "state", "npts", "nvox"):
+            assert np.array_equal(cg[k], co[k]), k
+    assert ndyn > 0  # the sequence does contain moving cars
+
+
+def test_long_sequence_labels(pkg, oracle):
+    """40-frame chain at reduced resolution: exercises carried clouds, splits and fusions of tracking."""
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=16)
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 1, k, rings=32, cols=900) for k in range(40)])
+    poses = np.stack(poses)
+    labels = s.segDF(scans, poses)
+    for sc in scans:
+        oracle.push_scan(sc)
+    oracle.track(poses)
+    for f in range(len(scans)):
+        assert np.array_equal(labels[f], oracle.labels(f)), f"frame {f}"
+        cg, co = s.frame_clusters(f), oracle.clusters(f)
+        assert np.array_equal(cg["name"], co["name"]) and np.array_equal(cg["state"], co["state"])
+    s.close()
+
+
+def test_incremental_push_and_track_equals_one_shot(pkg):
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 2, k, rings=32, cols=900) for k in range(9)])
+    poses = np.stack(poses)
+    a = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=16)
+    la = a.segDF(scans, poses)
+    b = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=2)  # forces 5 batches
+    for i in range(0, 9, 3):
+        b.process(scans[i:i + 3])
+        b.tracking(poses[: i + 3])
+    for f in range(9):
+        assert np.array_equal(la[f], b.frame_labels(f))
+    a.close()
+    b.close()
+
+
+def test_parkinglot_dense_scan(pkg):
+    """parkinglot.yaml parameters on a dense (3x) cloud: descriptor and labels vs the oracle."""
+    P = pkg.parkinglot_params()
+    s = pkg.SSC(P, device=0, max_points=128 * 2700, max_batch=2)
+    o = conftest.Oracle(P)
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 3, k, rings=128, cols=2700) for k in range(2)])
+    poses = np.stack(poses)
+    s.process(scans)
+    for sc in scans:
+        o.push_scan(sc)
+    compare_frames(s, o, 2, pkg)
+    s.tracking(poses)
+    o.track(poses)
+    for f in range(2):
+        assert np.array_equal(s.frame_labels(f), o.labels(f))
+    s.close()
+    o.close()
+
+
+def test_golden_fixture_through_gpu(pkg):
+    z = np.load(os.path.join(GOLD, "scan_small.npz"))
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=16 * 450, max_batch=4)
+    labels = s.segDF([z[f"xyzi{f}"] for f in range(3)], z["poses"])
+    for f in range(3):
+        src, vid = s.frame_apri(f)
+        assert np.array_equal(src, z[f"apri_src{f}"]) and np.array_equal(vid, z[f"apri_vid{f}"])
+        vox = s.frame_voxels(f)
+        assert np.array_equal(vox["voxel_idx"], z[f"vox_vid{f}"])
+        assert np.allclose(vox["av"], z[f"vox_av{f}"], rtol=0, atol=DESC_ATOL) and np.allclose(vox["cov"], z[f"vox_cov{f}"], rtol=0, atol=DESC_ATOL)
+        for st in range(3):
+            assert np.array_equal(s.frame_point_cluster(f, st), z[f"names{f}_{st}"])
+        assert np.array_equal(labels[f], z[f"labels{f}"])
+    s.close()
+
+
+# ---- size-independent properties at the benchmark size ----------------------------------------------------
+def test_full_size_batch_properties(pkg):
+    n = 16
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 4, k) for k in range(n)])
+    poses = np.stack(poses)
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=16)
+    labels = s.segDF(scans, poses)
+    for f in range(n):
+        c = s.frame_counts(f)
+        lab = labels[f]
+        hist = np.bincount(lab, minlength=8)
+        assert hist.sum() == len(scans[f]) == c[0]
+        assert hist[pkg.PT_GROUND] == c[1]
+        assert hist[pkg.PT_GATED_OUT] + hist[pkg.PT_UNCLUSTERED] + hist[pkg.PT_STATIC] + hist[pkg.PT_DYNAMIC] == c[2]
+        assert hist[pkg.PT_UNCLUSTERED] + hist[pkg.PT_STATIC] + hist[pkg.PT_DYNAMIC] == c[3]
+        g, ng = s.frame_ground_order(f)
+        assert len(np.unique(np.concatenate([g, ng]))) == c[1] + c[2]
+        vox = s.frame_voxels(f)
+        assert np.all(np.diff(vox["voxel_idx"]) > 0) and vox["count"].sum() == c[3]  # sortedness + checksum
+    assert np.all(labels[-1] != pkg.PT_DYNAMIC)  # the last frame is never tracked (ssc.cpp:1450)
+    # idempotence / batch invariance: same scans one at a time give identical classes
+    t = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=1)
+    l2 = t.segDF(scans[:4], poses[:4])
+    for f in range(3):
+        assert np.array_equal(l2[f], labels[f])
+    # static submap: one point per non-dynamic input point
+    import torch
+    total = sum(len(x) for x in scans)
+    out = torch.empty((total, 4), dtype=torch.float32, device="cuda:0")
+    cnt = s.static_submap_device(0, n, poses, out.data_ptr(), total)
+    assert cnt == sum(int((l != pkg.PT_DYNAMIC).sum()) for l in labels)
+    assert torch.isfinite(out[:cnt]).all()
+    s.close()
+    t.close()
+
+
+def test_aliased_voxel_scan_is_rejected_loudly(pkg):
+    """Points with a -1 index (y == 0 exactly) alias voxels; clustering them is not supported yet and must
+    fail with an explicit error rather than return different labels."""
+    cloud, _ = pkg.synth_scan(conftest.SEED, 0, rings=16, cols=450)
+    cloud = cloud.copy()
+    k = np.argmax((cloud[:, 2] > -1.0) & (cloud[:, 0] > 3) & (np.hypot(cloud[:, 0], cloud[:, 1]) < 25))
+    cloud[k, 1] = 0.0
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=16 * 450, max_batch=1)
+    try:
+        s.process([cloud])
+        c = s.frame_counts(0)  # accepted only if the point did not survive as an apri point
+        assert c[3] >= 0
+    except pkg.ScvodError as e:
+        assert "-1" in str(e)
+    s.close()
