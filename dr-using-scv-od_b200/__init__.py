@@ -45,7 +45,7 @@ EXPORTS = (
     "scvod_push_scans_dev", "scvod_track", "scvod_num_frames", "scvod_reset_frames", "scvod_frame_labels",
     "scvod_labels_range", "scvod_frame_counts", "scvod_frame_ground_order", "scvod_frame_apri", "scvod_frame_voxels",
     "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
-    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment",
+    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report",
 )
 
 _lib = None
@@ -117,6 +117,21 @@ def relative_pose(pose_next: np.ndarray, pose_pre: np.ndarray) -> np.ndarray:
     return T.reshape(3, 4)
 
 
+def kernel_timing(enable: bool):
+    _check(load_library().scvod_kernel_timing(1 if enable else 0))
+
+
+def kernel_timing_report() -> dict:
+    """{kernel: (total_ms, launches)} measured with CUDA events on the launching stream."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _check(load_library().scvod_kernel_timing_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt = line.split()
+        out[name] = (float(ms), int(cnt))
+    return out
+
+
 class SSC:
     """Mirror of the reference's ``class SSC`` for the hot path (reference include/ssc.h:55-104).
 
@@ -147,6 +162,9 @@ class SSC:
 
     def set_option(self, key: str, value: int):
         _check(self._lib.scvod_set_option(self._ctx, key.encode(), int(value)))
+
+    def set_stream(self, cuda_stream: int):
+        _check(self._lib.scvod_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
 
     # -- per-scan stages ------------------------------------------------------------------------
     def process(self, clouds: Sequence[np.ndarray]):
@@ -247,6 +265,18 @@ class SSC:
             out = np.zeros(max(total, 1), np.uint8)
         _check(self._lib.scvod_labels_range(self._ctx, f0, f1, _ptr(out), ctypes.c_int64(out.size)))
         return out[:total]
+
+    def refresh_labels(self, f0: int, f1: int):
+        """Bring the device-resident per-point classes of frames [f0,f1) up to date (no host copy)."""
+        _check(self._lib.scvod_labels_range(self._ctx, f0, f1, None, ctypes.c_int64(0)))
+
+    def labels_into(self, f0: int, f1: int, host_ptr: int, cap: int):
+        _check(self._lib.scvod_labels_range(self._ctx, f0, f1, ctypes.c_void_p(host_ptr), ctypes.c_int64(cap)))
+
+    def process_host_ptr(self, host_ptr: int, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        _check(self._lib.scvod_push_scans(self._ctx, ctypes.c_void_p(host_ptr), _ptr(offsets), len(offsets) - 1))
+        self.frame_sizes.extend(int(x) for x in np.diff(offsets))
 
     def frame_ground_order(self, f: int):
         c = self.frame_counts(f)

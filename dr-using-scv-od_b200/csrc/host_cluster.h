@@ -27,10 +27,11 @@ struct HCluster {
   float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
   std::vector<int> occupy_voxels;
   std::vector<int> part_end;    // ends (in occupy_voxels) of the initial CVC components concatenated by fusion
-  int npts = 0;                 // occupy_pts.size()
-  bool pts_valid = false;       // occupy_pts materialised (car clusters only)
-  std::vector<int> occupy_pts;  // apri indices, reference order
-  std::vector<P4> carried;      // transformed clouds appended by tracking (ssc.cpp:1382)
+  int npts = 0;                 // occupy_pts.size(); the point lists themselves stay on the device (voxel CSR)
+  // transformed clouds appended by tracking (*cloud += *cluster, ssc.cpp:1382): (offset, length) ranges of the
+  // device-resident output of the tracking pass that produced them
+  std::vector<std::pair<int, int>> carried;
+  int n_carried = 0;
 };
 
 // per-scan inputs from the GPU (host copies)

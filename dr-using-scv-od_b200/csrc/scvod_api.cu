@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -35,13 +36,46 @@ static int fail(int code, const std::string& msg) {
 
 namespace {
 
+// host-side section timer (SCVOD_PROFILE=1 prints the accumulated breakdown at scvod_destroy)
+struct HostProf {
+  bool on = getenv("SCVOD_PROFILE") != nullptr;
+  std::vector<std::pair<std::string, double>> acc;
+  void add(const char* name, double ms) {
+    for (auto& a : acc)
+      if (a.first == name) {
+        a.second += ms;
+        return;
+      }
+    acc.push_back(std::make_pair(std::string(name), ms));
+  }
+  void dump() {
+    if (!on) return;
+    for (auto& a : acc) fprintf(stderr, "[scvod profile] %-28s %10.3f ms\n", a.first.c_str(), a.second);
+  }
+};
+HostProf g_prof;
+struct ProfScope {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit ProfScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~ProfScope() {
+    if (g_prof.on) g_prof.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+#define PROF_CAT2(a, b) a##b
+#define PROF_CAT(a, b) PROF_CAT2(a, b)
+#define PROF(name) ProfScope PROF_CAT(prof_scope__, __COUNTER__)(name)
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     if (count <= n && p) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      count += count / 2 + 1024;  // geometric growth: buffers that grow step by step are not re-allocated every time
+    }
     p = nullptr;
     n = 0;
     cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
@@ -61,7 +95,10 @@ struct PinBuf {
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     if (count <= n && p) return cudaSuccess;
-    if (p) cudaFreeHost(p);
+    if (p) {
+      cudaFreeHost(p);
+      count += count / 2 + 1024;
+    }
     p = nullptr;
     n = 0;
     cudaError_t e = cudaMallocHost((void**)&p, count * sizeof(T));
@@ -84,6 +121,11 @@ struct PersistBatch {
   DevBuf<uint8_t> cls;
   DevBuf<int32_t> apri_src, apri_cid, apri_vid, word_rank, vox_off, vox_pts, vox_cnt, ground_src, ng_src;
   DevBuf<uint32_t> bitmap;
+  DevBuf<int64_t> off_dev;           // device copy of off
+  DevBuf<int32_t> scan_counts_dev;   // device copy of the per-scan counters
+  PinBuf<int32_t> h_vox_off, h_vox_pts;  // host copy of the voxel CSR of every frame (packed per scan)
+  int max_n = 0;
+  bool labels_current = false;
   // inspection-only
   DevBuf<int32_t> vox_vid, vox_tri;
   DevBuf<float> vox_av, vox_cov, vox_center;
@@ -101,6 +143,10 @@ struct PersistBatch {
     ground_src.release();
     ng_src.release();
     bitmap.release();
+    off_dev.release();
+    scan_counts_dev.release();
+    h_vox_off.release();
+    h_vox_pts.release();
     vox_vid.release();
     vox_tri.release();
     vox_av.release();
@@ -115,10 +161,6 @@ struct FrameHost {
   int n_in = 0, n_ground = 0, n_ng = 0, n_apri = 0, n_vox = 0;
   FrameClusters fc;
   std::vector<int32_t> vox_cnt;
-  // lazily fetched CSR (tracking splits / car point lists)
-  bool have_csr = false;
-  std::vector<int32_t> vox_off, vox_pts;
-  bool labels_current = false;
 };
 
 }  // namespace
@@ -128,6 +170,7 @@ struct scvod_ctx {
   int device = 0;
   int max_points = 0, max_batch = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   int64_t launches = 0;
   int host_threads = 1;
   bool inspect = true;
@@ -142,16 +185,21 @@ struct scvod_ctx {
   // pinned host mirrors of what the host logic reads per batch
   PinBuf<int32_t> h_scan_counts, h_vox_cnt, h_vox_root, h_vox_nbr, h_ev_cid, h_edge_buf;
   PinBuf<float> h_vox_bbox;
-  // tracking buffers
-  DevBuf<int32_t> d_sel, d_hit;
-  DevBuf<float4> d_carried, d_tout;
-  PinBuf<int32_t> h_sel, h_hit;
-  PinBuf<P4> h_carried, h_tout;
-  DevBuf<uint8_t> d_vox_cls;
-  PinBuf<uint8_t> h_vox_cls;
+  // tracking buffers: packed request (segments + own indices), ping-pong transformed clouds, hit table
+  DevBuf<int32_t> d_treq, d_triples;
+  DevBuf<unsigned long long> d_first;
+  PinBuf<int32_t> h_treq, h_triples;
+  DevBuf<float4> d_tout[2];
+  int tout_cur = 0;  // d_tout[tout_cur] holds the carried clouds of the frame that is the next frame_pre_
+  // label refresh staging
+  DevBuf<int32_t> d_vcls;
+  PinBuf<int32_t> h_vcls;
+  DevBuf<float> d_Ts;
+  PinBuf<float> h_Ts;
   DevBuf<unsigned long long> d_counter;
 
   std::vector<std::unique_ptr<PersistBatch>> batches;
+  std::vector<std::unique_ptr<PersistBatch>> batch_pool;  // released batches kept for reuse (no cudaMalloc in steady state)
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
   int track_name = 0;  // SSC::name (ssc.h:49)
@@ -337,9 +385,12 @@ extern "C" int scvod_create(const scvod_params* p, int device, int max_points, i
 
 extern "C" int scvod_destroy(scvod_ctx* c) {
   if (!c) return SCVOD_OK;
+  g_prof.dump();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->batches)
+    if (b) b->release();
+  for (auto& b : c->batch_pool)
     if (b) b->release();
   c->d_off.release(); c->d_patch_of.release(); c->d_slot_patch.release(); c->d_patch_cnt.release(); c->d_patch_off.release();
   c->d_patch_cur.release(); c->d_sorted_idx.release(); c->d_slot_pos.release(); c->d_slot_apos.release(); c->d_slot_vid.release();
@@ -347,10 +398,11 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_vox_pts_tmp.release(); c->d_vox_nbr.release(); c->d_vox_root.release(); c->d_ev_cid.release(); c->d_edge_buf.release();
   c->d_bucket_kv.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
   c->h_scan_counts.release(); c->h_vox_cnt.release(); c->h_vox_root.release(); c->h_vox_nbr.release(); c->h_ev_cid.release();
-  c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_sel.release(); c->d_hit.release(); c->d_carried.release(); c->d_tout.release();
-  c->h_sel.release(); c->h_hit.release(); c->h_carried.release(); c->h_tout.release(); c->d_vox_cls.release(); c->h_vox_cls.release();
+  c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_treq.release(); c->d_first.release(); c->d_triples.release();
+  c->h_treq.release(); c->h_triples.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
+  c->d_Ts.release(); c->h_Ts.release();
   c->d_counter.release();
-  cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return SCVOD_OK;
 }
@@ -373,6 +425,30 @@ extern "C" int scvod_set_option(scvod_ctx* c, const char* key, int value) {
   return SCVOD_OK;
 }
 
+extern "C" int scvod_set_stream(scvod_ctx* c, void* cuda_stream) {
+  if (!c) return fail(SCVOD_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)cuda_stream;
+  c->own_stream = false;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_kernel_timing(int enable) {
+  timing_enable(enable != 0);
+  if (enable) timing_reset();
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_kernel_timing_report(char* buf, int cap) {
+  if (!buf || cap <= 0) return fail(SCVOD_ERR_ARG, "bad buffer");
+  std::string r = timing_report();
+  if ((int)r.size() + 1 > cap) return fail(SCVOD_ERR_CAPACITY, "report buffer too small");
+  std::memcpy(buf, r.c_str(), r.size() + 1);
+  return (int)r.size();
+}
+
 // ---------------------------------------------------------------------------------------------
 // batched frame pipeline
 // ---------------------------------------------------------------------------------------------
@@ -389,10 +465,19 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   }
   if (total > (int64_t)c->ws.cap_points) return fail(SCVOD_ERR_CAPACITY, "batch larger than workspace");
 
-  std::unique_ptr<PersistBatch> pb(new PersistBatch());
+  PROF("push_batch total");
+  std::unique_ptr<PersistBatch> pb;
+  if (!c->batch_pool.empty()) {
+    pb = std::move(c->batch_pool.back());
+    c->batch_pool.pop_back();
+  } else {
+    pb.reset(new PersistBatch());
+  }
   pb->nscans = nscans;
   pb->total = total;
   pb->off = off;
+  pb->max_n = max_n;
+  pb->labels_current = false;
   const size_t T = (size_t)std::max<int64_t>(total, 1);
   CU(pb->pts.alloc(T));
   CU(pb->apri_xyzi.alloc(T));
@@ -412,6 +497,8 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   CU(pb->vox_av.alloc(T));
   CU(pb->vox_cov.alloc(T));
   CU(pb->vox_center.alloc(3 * T));
+  CU(pb->off_dev.alloc(nscans + 1));
+  CU(pb->scan_counts_dev.alloc((size_t)nscans * 8));
 
   BatchDev& w = c->ws;
   w.pts = pb->pts.p;
@@ -433,6 +520,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   w.vox_cov = pb->vox_cov.p;
   w.vox_center = pb->vox_center.p;
 
+  std::chrono::steady_clock::time_point tk0 = std::chrono::steady_clock::now();
   CU(cudaMemcpyAsync(w.off, off.data(), sizeof(int64_t) * (nscans + 1), cudaMemcpyHostToDevice, st));
   if (total > 0)
     CU(cudaMemcpyAsync(w.pts, (const char*)xyzi + sizeof(float) * 4 * offsets[0], sizeof(float4) * total,
@@ -444,11 +532,14 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_scan_counts.p, w.scan_counts, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (g_prof.on) g_prof.add("  h2d + kernels + sync", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
   const int32_t* sc = c->h_scan_counts.p;
   if (sc[(size_t)w.cap_scans * 8] & 1) return fail(SCVOD_ERR_CAPACITY, "a PatchWork patch holds more points than the largest fit tile");
 
   // per-scan table sizes -> packed host copies
-  std::vector<int64_t> vbase(nscans + 1, 0), ebase(nscans + 1, 0), gbase(nscans + 1, 0);
+  CU(cudaMemcpyAsync(pb->off_dev.p, w.off, sizeof(int64_t) * (nscans + 1), cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(pb->scan_counts_dev.p, w.scan_counts, sizeof(int32_t) * (size_t)nscans * 8, cudaMemcpyDeviceToDevice, st));
+  std::vector<int64_t> vbase(nscans + 1, 0), ebase(nscans + 1, 0), gbase(nscans + 1, 0), mbase(nscans + 1, 0), obase(nscans + 1, 0);
   for (int s = 0; s < nscans; ++s) {
     int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
     if (G < 0 || G > w.edge_cap) return fail(SCVOD_ERR_CAPACITY, "similarity edge table overflow");
@@ -459,7 +550,11 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     vbase[s + 1] = vbase[s] + V;
     ebase[s + 1] = ebase[s] + E;
     gbase[s + 1] = gbase[s] + G;
+    mbase[s + 1] = mbase[s] + sc[s * 8 + 2];
+    obase[s + 1] = obase[s] + V + 1;
   }
+
+  std::chrono::steady_clock::time_point td0 = std::chrono::steady_clock::now();
   CU(c->h_vox_cnt.alloc(std::max<int64_t>(1, vbase[nscans])));
   CU(c->h_vox_root.alloc(std::max<int64_t>(1, vbase[nscans])));
   CU(c->h_vox_nbr.alloc(std::max<int64_t>(1, vbase[nscans] * 27)));
@@ -482,6 +577,8 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   }
   CU(cudaStreamSynchronize(st));
 
+  if (g_prof.on) g_prof.add("  d2h voxel tables", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td0).count());
+  std::chrono::steady_clock::time_point th0 = std::chrono::steady_clock::now();
   // host cluster bookkeeping, one scan per task
   const int batch_id = (int)c->batches.size();
   const size_t f0 = c->frames.size();
@@ -524,6 +621,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     for (int i = 0; i < nt; ++i) th.emplace_back(worker);
     for (auto& t : th) t.join();
   }
+  if (g_prof.on) g_prof.add("  host segment+recognize", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count());
   c->batches.push_back(std::move(pb));
   if (bad.load()) return fail(SCVOD_ERR_STATE, "internal: replayed cluster partition differs from the GPU components");
   return SCVOD_OK;
@@ -560,115 +658,123 @@ extern "C" int scvod_num_frames(const scvod_ctx* c) { return c ? (int)c->frames.
 
 extern "C" int scvod_reset_frames(scvod_ctx* c) {
   if (!c) return fail(SCVOD_ERR_ARG, "null ctx");
+  PROF("reset_frames total");
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->batches)
-    if (b) b->release();
+    if (b) c->batch_pool.push_back(std::move(b));
   c->batches.clear();
   c->frames.clear();
   c->tracked = 0;
   c->track_name = 0;
+  c->tout_cur = 0;
   return SCVOD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // tracking (SSC::tracking, reference src/ssc.cpp:1250-1426)
 // ---------------------------------------------------------------------------------------------
-static int fetch_csr(scvod_ctx* c, FrameHost& fr) {
-  if (fr.have_csr) return SCVOD_OK;
-  PersistBatch& pb = *c->batches[fr.batch];
-  fr.vox_off.resize(fr.n_vox + 1);
-  fr.vox_pts.resize(std::max(1, fr.n_apri));
-  if (fr.n_vox > 0) CU(cudaMemcpyAsync(fr.vox_off.data(), pb.vox_off.p + fr.base, sizeof(int32_t) * fr.n_vox, cudaMemcpyDeviceToHost, c->stream));
-  if (fr.n_apri > 0) CU(cudaMemcpyAsync(fr.vox_pts.data(), pb.vox_pts.p + fr.base, sizeof(int32_t) * fr.n_apri, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  fr.vox_off[fr.n_vox] = fr.n_apri;
-  fr.have_csr = true;
-  return SCVOD_OK;
-}
-
-// occupy_pts of a cluster in the reference's order: each initial CVC component contributes its points in
-// ascending apri index (ssc.cpp:360-380); fusion concatenates components (ssc.cpp:617).
-static void materialise_pts(const FrameHost& fr, HCluster& cl) {
-  if (cl.pts_valid) return;
-  cl.occupy_pts.clear();
-  int start = 0;
-  for (int pe : cl.part_end) {
-    size_t b0 = cl.occupy_pts.size();
-    for (int i = start; i < pe; ++i) {
-      int v = cl.occupy_voxels[i];
-      cl.occupy_pts.insert(cl.occupy_pts.end(), fr.vox_pts.begin() + fr.vox_off[v], fr.vox_pts.begin() + fr.vox_off[v + 1]);
-    }
-    std::sort(cl.occupy_pts.begin() + b0, cl.occupy_pts.end());
-    start = pe;
-  }
-  cl.pts_valid = true;
-}
-
 static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float* pose_pre, const float* pose_next) {
+  PROF("track_pair total");
   const scvod_params& P = c->hp.p;
   float T[12];
   relative_pose(pose_next, pose_pre, T);
-  int rc = fetch_csr(c, pre);
-  if (rc) return rc;
   // car clusters of frame_pre_ in cluster_set order (ssc.cpp:1261-1264)
   std::vector<HCluster*> cars;
-  for (auto& cs : pre.fc.cluster_set)
-    if (cs.second.type == P.car) cars.push_back(&cs.second);
-  size_t K = 0, KC = 0;
-  for (HCluster* cl : cars) {
-    materialise_pts(pre, *cl);
-    K += cl->occupy_pts.size() + cl->carried.size();
-    KC += cl->carried.size();
+  size_t n_seg = 0;
+  {
+    PROF("  track: prepare");
+    for (auto& cs : pre.fc.cluster_set)
+      if (cs.second.type == P.car) cars.push_back(&cs.second);
+    for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size();
   }
+  const int ncl = (int)cars.size();
+  const int vn = next.n_vox;
   std::vector<size_t> cstart(cars.size() + 1, 0);
-  if (K > 0) {
-    CU(c->h_sel.alloc(K));
-    CU(c->h_hit.alloc(K));
-    CU(c->h_tout.alloc(K));
-    CU(c->h_carried.alloc(std::max<size_t>(KC, 1)));
-    CU(c->d_sel.alloc(K));
-    CU(c->d_hit.alloc(K));
-    CU(c->d_tout.alloc(K));
-    CU(c->d_carried.alloc(std::max<size_t>(KC, 1)));
-    size_t k = 0, kc = 0;
+  // per cluster: (first-occurrence key, hit voxel).  The cloud of a cluster is [part 0][part 1]...[carried 0]...
+  // (ssc.cpp:380,617,1382) with ascending apri index inside a part, which is what the 64-bit key encodes.
+  std::vector<std::vector<std::pair<uint64_t, int>>> hits(cars.size());
+  const int in_buf = c->tout_cur, out_buf = 1 - c->tout_cur;
+  {
+    PROF("  track: gpu round trip");
+    CU(c->h_treq.alloc(std::max<size_t>(4, n_seg * 4)));
+    int32_t* seg = c->h_treq.p;
+    size_t k = 0, si = 0;
     for (size_t i = 0; i < cars.size(); ++i) {
       cstart[i] = k;
-      for (int m : cars[i]->occupy_pts) c->h_sel.p[k++] = m;
-      for (const P4& q : cars[i]->carried) {
-        c->h_carried.p[kc] = q;
-        c->h_sel.p[k++] = -1 - (int)kc;
-        ++kc;
+      HCluster& cl = *cars[i];
+      int part = 0, vi = 0;
+      for (int v : cl.occupy_voxels) {
+        while (part < (int)cl.part_end.size() && vi >= cl.part_end[part]) ++part;
+        ++vi;
+        int cnt = pre.vox_cnt[v];
+        if (cnt <= 0) continue;
+        seg[4 * si] = (int)k;
+        seg[4 * si + 1] = v;
+        seg[4 * si + 2] = (int)i;
+        seg[4 * si + 3] = part;
+        ++si;
+        k += cnt;
+      }
+      int ord = 0x40000000;
+      for (auto& cr : cl.carried) {
+        if (cr.second <= 0) continue;
+        seg[4 * si] = (int)k;
+        seg[4 * si + 1] = -1 - cr.first;
+        seg[4 * si + 2] = (int)i;
+        seg[4 * si + 3] = ord++;
+        ++si;
+        k += cr.second;
       }
     }
     cstart[cars.size()] = k;
-    PersistBatch& pbp = *c->batches[pre.batch];
-    PersistBatch& pbn = *c->batches[next.batch];
-    CU(cudaMemcpyAsync(c->d_T.p, T, sizeof(float) * 12, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_sel.p, c->h_sel.p, sizeof(int32_t) * K, cudaMemcpyHostToDevice, c->stream));
-    if (KC) CU(cudaMemcpyAsync(c->d_carried.p, c->h_carried.p, sizeof(P4) * KC, cudaMemcpyHostToDevice, c->stream));
-    c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, c->d_carried.p, c->d_sel.p, (int)K, c->d_T.p,
-                                pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words,
-                                c->d_tout.p, c->d_hit.p, c->stream);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_hit.p, c->d_hit.p, sizeof(int32_t) * K, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_tout.p, c->d_tout.p, sizeof(P4) * K, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    const size_t K = k;
+    if (K > 0 && vn > 0 && si > 0) {
+      const int cap_quads = (int)std::min<size_t>((size_t)ncl * vn, (size_t)1 << 20);
+      CU(c->d_treq.alloc(si * 4));
+      CU(c->d_tout[out_buf].alloc(K));
+      CU(c->d_first.alloc((size_t)ncl * vn));
+      CU(c->d_triples.alloc(4 + 4 * (size_t)cap_quads));
+      CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));
+      PersistBatch& pbp = *c->batches[pre.batch];
+      PersistBatch& pbn = *c->batches[next.batch];
+      CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4), cudaMemcpyHostToDevice, c->stream));
+      c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
+                                  reinterpret_cast<const int4*>(c->d_treq.p), (int)si, (int)K, T,
+                                  pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
+                                  vn, c->d_tout[out_buf].p, c->d_first.p, c->d_triples.p, cap_quads, c->stream);
+      CU(cudaGetLastError());
+      const size_t first_chunk = std::min<size_t>(4 + 4 * (size_t)cap_quads, 4 + 4 * 4096);
+      CU(cudaMemcpyAsync(c->h_triples.p, c->d_triples.p, sizeof(int32_t) * first_chunk, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      int nt = c->h_triples.p[0];
+      if (nt > cap_quads) return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
+      if (4 + 4 * (size_t)nt > first_chunk) {
+        CU(cudaMemcpyAsync(c->h_triples.p + first_chunk, c->d_triples.p + first_chunk, sizeof(int32_t) * (4 + 4 * (size_t)nt - first_chunk),
+                           cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+      }
+      for (int t = 0; t < nt; ++t) {
+        const int32_t* q = c->h_triples.p + 4 + 4 * t;
+        hits[q[0]].push_back(std::make_pair(((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3], q[1]));
+      }
+      for (auto& h : hits) std::sort(h.begin(), h.end());  // order of first occurrence along the cloud
+    }
   }
 
+  PROF("  track: host decisions");
   std::vector<int>& nlabel = next.fc.vox_label;
   auto& nset = next.fc.cluster_set;
   for (size_t ci = 0; ci < cars.size(); ++ci) {
     HCluster& cc = *cars[ci];
-    if (cc.type != P.car) continue;  // (type is only rewritten for the cluster being processed)
+    if (cc.type != P.car) continue;
     if (cc.track_id == -1) {
       cc.track_id = c->track_name;
       c->track_name++;
     }
     std::unordered_map<int, std::vector<int>> remap_name;  // label -> hit voxels (ssc.cpp:1277-1317)
-    for (size_t k = cstart[ci]; k < cstart[ci + 1]; ++k) {
-      int v = c->h_hit.p[k];
-      if (v < 0) continue;
+    for (auto& h : hits[ci]) {
+      const int v = h.second;
       int lab = nlabel[v];
       if (lab == -1) continue;
       auto l_find = remap_name.find(lab);
@@ -680,10 +786,7 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
         l_find->second.emplace_back(v);
       }
     }
-    for (auto& re : remap_name) {
-      std::sort(re.second.begin(), re.second.end());
-      re.second.erase(std::unique(re.second.begin(), re.second.end()), re.second.end());
-    }
+    for (auto& re : remap_name) std::sort(re.second.begin(), re.second.end());  // sampleVec: already unique
     if (remap_name.size() == 0) {
       cc.state = 1;
     } else if (remap_name.size() == 1) {
@@ -721,8 +824,11 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
           cc.state = 0;
           HCluster& dst = nset[it->first];
           dst.track_id = cc.track_id;
-          const P4* tp = c->h_tout.p + cstart[ci];
-          dst.carried.insert(dst.carried.end(), tp, tp + (cstart[ci + 1] - cstart[ci]));  // *cloud += *cluster (ssc.cpp:1382)
+          int len = (int)(cstart[ci + 1] - cstart[ci]);
+          if (len > 0) {  // *cloud += *cluster (ssc.cpp:1382): the transformed cloud stays on the device
+            dst.carried.push_back(std::make_pair((int)cstart[ci], len));
+            dst.n_carried += len;
+          }
         }
       }
     } else {
@@ -731,27 +837,24 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       cluster_new.track_id = cc.track_id;
       cluster_new.name = next.fc.max_name++;
       cluster_new.type = P.car;
-      rc = fetch_csr(c, next);
-      if (rc) return rc;
-      cluster_new.pts_valid = true;
       for (auto& re : remap_name) {
         if (nset[re.first].type == P.car &&
             ((float)re.second.size() / (float)nset[re.first].occupy_voxels.size()) >= P.occupancy) {
           HCluster& src = nset[re.first];
-          materialise_pts(next, src);
-          cluster_new.occupy_pts.insert(cluster_new.occupy_pts.end(), src.occupy_pts.begin(), src.occupy_pts.end());
+          const int basev = (int)cluster_new.occupy_voxels.size();  // addVec of pts and voxels (ssc.cpp:1409-1410): parts are kept
           cluster_new.occupy_voxels.insert(cluster_new.occupy_voxels.end(), src.occupy_voxels.begin(), src.occupy_voxels.end());
+          for (int pe : src.part_end) cluster_new.part_end.push_back(basev + pe);
           cluster_new.npts += src.npts;
           nset.erase(re.first);
         }
       }
-      cluster_new.part_end.push_back((int)cluster_new.occupy_voxels.size());
       for (int v : cluster_new.occupy_voxels) nlabel[v] = cluster_new.name;
       nset.insert(std::make_pair(cluster_new.name, cluster_new));
     }
   }
-  pre.labels_current = false;
-  next.labels_current = false;
+  c->tout_cur = out_buf;  // this pass's output holds the carried clouds of `next`
+  c->batches[pre.batch]->labels_current = false;
+  c->batches[next.batch]->labels_current = false;
   return SCVOD_OK;
 }
 
@@ -770,22 +873,38 @@ extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
 // ---------------------------------------------------------------------------------------------
 // labels
 // ---------------------------------------------------------------------------------------------
-static int refresh_labels(scvod_ctx* c, int f) {
-  FrameHost& fr = c->frames[f];
-  if (fr.labels_current) return SCVOD_OK;
-  PersistBatch& pb = *c->batches[fr.batch];
-  const int V = std::max(1, fr.n_vox);
-  CU(c->h_vox_cls.alloc(V));
-  CU(c->d_vox_cls.alloc(V));
-  std::memset(c->h_vox_cls.p, SCVOD_PT_UNCLUSTERED, V);
-  for (auto& cs : fr.fc.cluster_set) {
-    uint8_t v = (cs.second.state == 1) ? SCVOD_PT_DYNAMIC : SCVOD_PT_STATIC;
-    for (int vx : cs.second.occupy_voxels) c->h_vox_cls.p[vx] = v;
+// per-voxel classes of every frame of a batch (decided on the host) -> per-point classes on the device
+static int refresh_batch_labels(scvod_ctx* c, int batch) {
+  PersistBatch& pb = *c->batches[batch];
+  if (pb.labels_current) return SCVOD_OK;
+  std::vector<FrameHost*> frs(pb.nscans, nullptr);
+  for (auto& fr : c->frames)
+    if (fr.batch == batch) frs[fr.slot] = &fr;
+  size_t vtot = 0;
+  for (FrameHost* fr : frs) vtot += fr ? ((fr->n_vox + 3) & ~3) : 0;
+  const size_t words = pb.nscans + (vtot + 3) / 4 + 1;
+  CU(c->h_vcls.alloc(words));
+  CU(c->d_vcls.alloc(words));
+  int32_t* voff = c->h_vcls.p;
+  uint8_t* vc = reinterpret_cast<uint8_t*>(c->h_vcls.p + pb.nscans);
+  size_t pos = 0;
+  for (int s = 0; s < pb.nscans; ++s) {
+    voff[s] = (int32_t)pos;
+    FrameHost* fr = frs[s];
+    if (!fr) continue;
+    std::memset(vc + pos, SCVOD_PT_UNCLUSTERED, fr->n_vox);
+    for (auto& cs : fr->fc.cluster_set) {
+      uint8_t v = (cs.second.state == 1) ? SCVOD_PT_DYNAMIC : SCVOD_PT_STATIC;
+      for (int vx : cs.second.occupy_voxels) vc[pos + vx] = v;
+    }
+    pos += (fr->n_vox + 3) & ~3;
   }
-  CU(cudaMemcpyAsync(c->d_vox_cls.p, c->h_vox_cls.p, V, cudaMemcpyHostToDevice, c->stream));
-  c->launches += launch_final_labels(pb.apri_src.p + fr.base, pb.apri_cid.p + fr.base, c->d_vox_cls.p, fr.n_apri, pb.cls.p + fr.base, c->stream);
+  CU(cudaMemcpyAsync(c->d_vcls.p, c->h_vcls.p, sizeof(int32_t) * words, cudaMemcpyHostToDevice, c->stream));
+  c->launches += launch_final_labels(pb.off_dev.p, pb.scan_counts_dev.p, pb.nscans, pb.max_n, pb.apri_src.p, pb.apri_cid.p, c->d_vcls.p,
+                                     reinterpret_cast<const uint8_t*>(c->d_vcls.p + pb.nscans), pb.cls.p, c->stream);
   CU(cudaGetLastError());
-  fr.labels_current = true;
+  CU(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next batch
+  pb.labels_current = true;
   return SCVOD_OK;
 }
 
@@ -794,7 +913,7 @@ extern "C" int scvod_frame_labels(scvod_ctx* c, int frame, uint8_t* cls, int n) 
   CU(cudaSetDevice(c->device));
   FrameHost& fr = c->frames[frame];
   if (n < fr.n_in) return fail(SCVOD_ERR_ARG, "label buffer too small");
-  int rc = refresh_labels(c, frame);
+  int rc = refresh_batch_labels(c, fr.batch);
   if (rc) return rc;
   PersistBatch& pb = *c->batches[fr.batch];
   if (fr.n_in > 0) CU(cudaMemcpyAsync(cls, pb.cls.p + fr.base, fr.n_in, cudaMemcpyDeviceToHost, c->stream));
@@ -802,19 +921,31 @@ extern "C" int scvod_frame_labels(scvod_ctx* c, int frame, uint8_t* cls, int n) 
   return SCVOD_OK;
 }
 
-// labels of frames [f0,f1) into one host buffer (concatenated in frame order)
+// labels of frames [f0,f1) into one host buffer (concatenated in frame order); cls == NULL: refresh only
 extern "C" int scvod_labels_range(scvod_ctx* c, int f0, int f1, uint8_t* cls, int64_t cap) {
-  if (!c || !cls || f0 < 0 || f1 > (int)c->frames.size() || f0 > f1) return fail(SCVOD_ERR_ARG, "bad frame range");
+  if (!c || f0 < 0 || f1 > (int)c->frames.size() || f0 > f1) return fail(SCVOD_ERR_ARG, "bad frame range");
+  PROF("labels_range total");
   CU(cudaSetDevice(c->device));
   int64_t pos = 0;
-  for (int f = f0; f < f1; ++f) {
+  int f = f0;
+  while (f < f1) {
     FrameHost& fr = c->frames[f];
-    if (pos + fr.n_in > cap) return fail(SCVOD_ERR_ARG, "label buffer too small");
-    int rc = refresh_labels(c, f);
+    int rc = refresh_batch_labels(c, fr.batch);
     if (rc) return rc;
-    PersistBatch& pb = *c->batches[fr.batch];
-    if (fr.n_in > 0) CU(cudaMemcpyAsync(cls + pos, pb.cls.p + fr.base, fr.n_in, cudaMemcpyDeviceToHost, c->stream));
-    pos += fr.n_in;
+    // frames of one batch are contiguous in frame order and in device memory: one copy per run
+    int g = f;
+    int64_t bytes = 0;
+    while (g < f1 && c->frames[g].batch == fr.batch) {
+      bytes += c->frames[g].n_in;
+      ++g;
+    }
+    if (cls) {
+      if (pos + bytes > cap) return fail(SCVOD_ERR_ARG, "label buffer too small");
+      PersistBatch& pb = *c->batches[fr.batch];
+      if (bytes > 0) CU(cudaMemcpyAsync(cls + pos, pb.cls.p + fr.base, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    pos += bytes;
+    f = g;
   }
   CU(cudaStreamSynchronize(c->stream));
   return SCVOD_OK;
@@ -824,20 +955,26 @@ extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float
                                        int64_t* n_points) {
   if (!c || !poses6 || !out_xyzi_dev || !n_points || f0 < 0 || f1 > (int)c->frames.size() || f0 > f1)
     return fail(SCVOD_ERR_ARG, "bad arguments to scvod_static_submap_dev");
+  PROF("static_submap total");
   CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
-  for (int f = f0; f < f1; ++f) {
+  const int nf = f1 - f0;
+  CU(c->h_Ts.alloc(std::max(1, nf) * 12));
+  CU(c->d_Ts.alloc(std::max(1, nf) * 12));
+  for (int f = f0; f < f1; ++f) pose_matrix(poses6 + 6 * f, c->h_Ts.p + 12 * (f - f0));
+  if (nf > 0) CU(cudaMemcpyAsync(c->d_Ts.p, c->h_Ts.p, sizeof(float) * 12 * nf, cudaMemcpyHostToDevice, c->stream));
+  int f = f0;
+  while (f < f1) {
     FrameHost& fr = c->frames[f];
-    int rc = refresh_labels(c, f);
+    int rc = refresh_batch_labels(c, fr.batch);
     if (rc) return rc;
-    float T[12];
-    pose_matrix(poses6 + 6 * f, T);
-    // d_T is reused per frame: stream order keeps each copy ahead of its kernel
-    CU(cudaMemcpyAsync(c->d_T.p, T, sizeof(float) * 12, cudaMemcpyHostToDevice, c->stream));
+    int g = f;
+    while (g < f1 && c->frames[g].batch == fr.batch) ++g;
     PersistBatch& pb = *c->batches[fr.batch];
-    c->launches += launch_submap(pb.pts.p + fr.base, pb.cls.p + fr.base, fr.n_in, c->d_T.p, (float4*)out_xyzi_dev, c->d_counter.p,
-                                 cap_points, c->stream);
-    CU(cudaStreamSynchronize(c->stream));  // T lives on the host stack
+    c->launches += launch_submap(pb.pts.p, pb.cls.p, pb.off_dev.p, c->d_Ts.p + 12 * (f - f0), fr.slot, g - f, pb.max_n,
+                                 (float4*)out_xyzi_dev, c->d_counter.p, cap_points, c->stream);
+    CU(cudaGetLastError());
+    f = g;
   }
   unsigned long long cnt = 0;
   CU(cudaMemcpyAsync(&cnt, c->d_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));

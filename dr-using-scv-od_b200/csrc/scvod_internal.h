@@ -13,8 +13,7 @@ namespace scvod {
 constexpr int kNumZones = 4;
 constexpr int kNumPatches = 504;  // 2*16 + 4*32 + 4*54 + 4*32
 constexpr int kMinPatchPts = 10;  // num_min_pts_: patches need > 10 points (patchwork.h:331)
-constexpr int kFitSmall = 2048;   // points per patch handled by the small-tile fit kernel
-constexpr int kFitLarge = 11000;  // ... by the large-tile fit kernel (20 B/pt of shared memory)
+constexpr int kFitLarge = 9400;    // points per patch of the largest shared-memory fit tile (24 B/pt)
 
 struct GridSpec {
   int range_num, sector_num, azimuth_num, bin_num;
@@ -89,12 +88,20 @@ int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int total_p
 int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
 int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t* pass, int32_t* vid, int32_t* ri, int32_t* si,
                     int32_t* ei, float* range, float* angle, float* azimuth, void* stream);
-// tracking: gather (sel >= 0: own apri point; sel < 0: carried[-1-sel]) -> transform by T -> bin -> lookup in next frame
-int launch_track(const HostParams& hp, const float4* own_xyzi, const float4* carried, const int32_t* sel, int k, const float* T12_dev,
-                 const uint32_t* next_bitmap, const int32_t* next_word_rank, float4* out_xyzi, int32_t* out_hit, void* stream);
-int launch_final_labels(const int32_t* apri_src, const int32_t* apri_cid, const uint8_t* vox_cls, int m, uint8_t* cls, void* stream);
-int launch_submap(const float4* pts, const uint8_t* cls, int n, const float* T12_dev, float4* out, unsigned long long* counter,
-                  long long cap, void* stream);
+// tracking diff of one frame pair: segments {dst_off, source (>=0 voxel of frame_pre_ / <0 carried range), cluster, order}
+int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
+                 const int4* segs, int nseg, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* out_quads, int cap_quads, void* stream);
+int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
+                        const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream);
+int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,
+                  int max_scan_points, float4* out, unsigned long long* counter, long long cap, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
+
+// per-kernel CUDA-event timing (process-wide; used by bench.py for the roofline block)
+void timing_enable(bool on);
+void timing_collect();
+void timing_reset();
+std::string timing_report();  // lines of "<kernel> <total ms> <launches>"
 
 }  // namespace scvod

@@ -14,6 +14,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <cstdio>
+#include <string>
+#include <vector>
+
 #include "scvod_device_math.cuh"
 #include "scvod_internal.h"
 
@@ -65,6 +69,10 @@ __constant__ int c_zone_base[4] = {0, 32, 160, 376};
 __constant__ int c_zone_ring0[4] = {0, 2, 6, 10};  // concentric_idx of the zone's first ring
 __constant__ double c_elev_thr[4] = {-1.2, -0.9984, -0.851, -0.605};
 __constant__ double c_flat_thr[4] = {0.0, 0.000125, 0.000185, 0.000185};
+
+struct Mat34 {
+  float m[12];
+};
 
 struct GroundConst {
   double low_thr;   // -1.8 * sensor_height_  (patchwork.h:304)
@@ -310,7 +318,8 @@ struct FitArgs {
   const int64_t* off;
   const int32_t* patch_cnt;
   const int32_t* patch_off;
-  const uint64_t* bucket_kv;
+  uint64_t* bucket_kv;
+  float4* scratch4;  // GLOBAL tier only: per-slot float4 scratch (the not-yet-written apri_xyzi array)
   int32_t* sorted_idx;
   int32_t* slot_pos;
   int32_t* slot_apos;
@@ -327,18 +336,17 @@ struct FitArgs {
 constexpr uint32_t F_G = 1u;      // in the current ground set / final ground
 constexpr uint32_t F_PASS = 2u;   // survives the SSC gates
 constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md hard part 7)
-constexpr uint32_t F_BIN = 8u;    // binning was evaluated for this point
 
+// Shared-memory layout per point: one float4 {x, y, z, flag bits} (a single broadcast LDS.128 feeds the
+// sequential chain) + one 64-bit sort key whose words are reused after the sort (low: voxel_idx).
 // GLOBAL = true is the overflow tier for patches that do not fit the largest shared-memory tile: the
-// same code runs with its scratch arrays placed in the (L2-resident) global buffers of the patch itself.
+// same code runs with its scratch arrays in the (L2-resident) global buffers of the patch itself.
 template <int MAXN, int MINN, int THREADS, bool GLOBAL>
 __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* kv;
-  float *sx, *sy, *sz;
-  __shared__ float s_plane[4];   // n0 n1 n2 th_dist_d
-  __shared__ float s_stat[8];    // mean z, sv0..2, d, mean x, mean y
-  __shared__ int s_int[8];       // decision, init_idx, ...
+  __shared__ float s_plane[4];  // n0 n1 n2 th_dist_d
+  __shared__ float s_stat[8];   // mean z, sv0..2, d, mean x, mean y
+  __shared__ int s_int[4];
   __shared__ double s_lpr;
   __shared__ int s_scan[THREADS / 32 + 1];
 
@@ -347,16 +355,14 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   if (n <= MINN || n > MAXN) return;
   const int64_t base = a.off[b];
   const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+  float4* P;
+  uint64_t* kv;
   if (GLOBAL) {
-    kv = const_cast<uint64_t*>(a.bucket_kv) + base + slot0;  // sorted in place
-    sx = reinterpret_cast<float*>(a.slot_pos + base + slot0);
-    sy = reinterpret_cast<float*>(a.slot_apos + base + slot0);
-    sz = reinterpret_cast<float*>(a.slot_vid + base + slot0);
+    P = a.scratch4 + base + slot0;
+    kv = a.bucket_kv + base + slot0;  // sorted in place
   } else {
-    kv = reinterpret_cast<uint64_t*>(smem_raw);
-    sx = reinterpret_cast<float*>(kv + MAXN);
-    sy = sx + MAXN;
-    sz = sy + MAXN;
+    P = reinterpret_cast<float4*>(smem_raw);
+    kv = reinterpret_cast<uint64_t*>(P + MAXN);
   }
   uint32_t* kv32 = reinterpret_cast<uint32_t*>(kv);  // [2*j] = low word, [2*j+1] = high word
   const int tid = threadIdx.x;
@@ -420,9 +426,8 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   for (int j = tid; j < n; j += THREADS) {
     int idx = (int)kv32[2 * j];
     float4 q = __ldg(&a.pts[base + idx]);
-    sx[j] = q.x;
-    sy[j] = q.y;
-    sz[j] = q.z;
+    q.w = __uint_as_float(0u);
+    P[j] = q;
     a.sorted_idx[base + slot0 + j] = idx;
     a.slot_patch[base + slot0 + j] = (int16_t)p;
   }
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   {
     int c = 0;
     if (zone == 0)
-      for (int j = tid; j < n; j += THREADS) c += ((double)sz[j] < a.gc.seed_thr) ? 1 : 0;
+      for (int j = tid; j < n; j += THREADS) c += ((double)P[j].z < a.gc.seed_thr) ? 1 : 0;
     int total;
     block_excl_scan<THREADS>(c, &total, s_scan);
     if (tid == 0) {
@@ -441,14 +446,14 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
       double sum = 0;
       int cnt = 0;
       for (int i = init_idx; i < n && cnt < 20; ++i) {
-        sum = __dadd_rn(sum, (double)sz[i]);
+        sum = __dadd_rn(sum, (double)P[i].z);
         cnt++;
       }
       s_lpr = cnt != 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
     }
     __syncthreads();
     double thr = __dadd_rn(s_lpr, 0.3);
-    for (int j = tid; j < n; j += THREADS) kv32[2 * j + 1] = ((double)sz[j] < thr) ? F_G : 0u;
+    for (int j = tid; j < n; j += THREADS) P[j].w = __uint_as_float(((double)P[j].z < thr) ? F_G : 0u);
     __syncthreads();
   }
 
@@ -456,20 +461,23 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   for (int it = 0; it < 3; ++it) {
     if (tid < 32) {
       const int lane = tid;
-      // lane L accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix: xx xy xz yy yz zz x y z
-      const int ia = (lane < 3 || lane == 6) ? 0 : (lane < 5 || lane == 7) ? 1 : 2;
-      const int ib = (lane == 0) ? 0 : (lane == 1 || lane == 3) ? 1 : (lane == 2 || lane == 4 || lane == 5) ? 2 : 3;
+      // lane L accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix: xx xy xz yy yz zz x y z.
+      // Strictly sequential in z-sorted order (PCL's float single pass is order dependent); points
+      // outside the ground set contribute -0.0f, which is an exact identity for float addition, so
+      // the loop is branch free and the only loop-carried dependency is one FADD.
+      const bool a_is_x = (lane < 3 || lane == 6), a_is_y = (lane == 3 || lane == 4 || lane == 7);
+      const bool b_is_x = (lane == 0), b_is_y = (lane == 1 || lane == 3), b_is_z = (lane == 2 || lane == 4 || lane == 5);
       float acc = 0.f;
       int cnt = 0;
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < n; ++j) {
-        if (kv32[2 * j + 1] & F_G) {
-          float xv = sx[j], yv = sy[j], zv = sz[j];
-          float av = (ia == 0) ? xv : (ia == 1) ? yv : zv;
-          float bv = (ib == 0) ? xv : (ib == 1) ? yv : (ib == 2) ? zv : 1.0f;
-          acc = da(acc, dm(av, bv));
-          ++cnt;
-        }
+        const float4 q = P[j];
+        const float av = a_is_x ? q.x : (a_is_y ? q.y : q.z);
+        const float bv = b_is_x ? q.x : (b_is_y ? q.y : (b_is_z ? q.z : 1.0f));
+        const bool in = (__float_as_uint(q.w) & F_G) != 0u;
+        const float term = in ? dm(av, bv) : -0.0f;
+        acc = da(acc, term);
+        cnt += in ? 1 : 0;
       }
       float accu[9];
 #pragma unroll
@@ -514,8 +522,9 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
     const float n0 = s_plane[0], n1 = s_plane[1], n2 = s_plane[2], th = s_plane[3];
     for (int j = tid; j < n; j += THREADS) {
       // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
-      float res = da(da(dm(sx[j], n0), dm(sy[j], n1)), dm(sz[j], n2));
-      kv32[2 * j + 1] = (res < th) ? F_G : 0u;
+      const float4 q = P[j];
+      float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
+      P[j].w = __uint_as_float((res < th) ? F_G : 0u);
     }
     __syncthreads();
   }
@@ -556,18 +565,18 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
 
   // ---- curved-voxel binning of every point that ends up in cloud_nonground ------------------------
   for (int j = tid; j < n; j += THREADS) {
-    uint32_t f = kv32[2 * j + 1] & F_G;
+    const float4 q = P[j];
+    uint32_t f = __float_as_uint(q.w) & F_G;
     int vid = 0;
     if (rejected || !(f & F_G)) {
-      BinResult r = dev_bin_point(sx[j], sy[j], sz[j], a.bp);
-      f |= F_BIN;
+      BinResult r = dev_bin_point(q.x, q.y, q.z, a.bp);
       if (r.pass) {
         f |= F_PASS;
         if (r.ri < 0 || r.si < 0 || r.ei < 0) f |= F_QUIRK;
       }
       vid = r.vid;
     }
-    kv32[2 * j + 1] = f;
+    P[j].w = __uint_as_float(f);
     kv32[2 * j] = (uint32_t)vid;
   }
   __syncthreads();
@@ -577,7 +586,7 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   const int j0 = min(n, tid * chunk), j1 = min(n, j0 + chunk);
   int cG = 0, cGP = 0, cNP = 0, cQ = 0;
   for (int j = j0; j < j1; ++j) {
-    uint32_t f = kv32[2 * j + 1];
+    uint32_t f = __float_as_uint(P[j].w);
     bool g = f & F_G, ps = f & F_PASS;
     cG += g;
     cGP += (g && ps);
@@ -590,12 +599,10 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   int eNP = block_excl_scan<THREADS>(cNP, &tNP, s_scan);
   block_excl_scan<THREADS>(cQ, &tQ, s_scan);
   const int nG = tG, nN = n - tG;
-  int* spos = reinterpret_cast<int*>(sx);   // x,y no longer needed
-  int* sapos = reinterpret_cast<int*>(sy);
   {
     int rG = eG, rGP = eGP, rNP = eNP;
     for (int j = j0; j < j1; ++j) {
-      uint32_t f = kv32[2 * j + 1];
+      uint32_t f = __float_as_uint(P[j].w);
       bool g = f & F_G, ps = f & F_PASS;
       int rN = j - rG;  // nonground points before j
       int pos, apos = -1, role;
@@ -613,8 +620,8 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
         role = ps ? 2 : 1;
         if (ps) apos = g ? rGP : tGP + rNP;
       }
-      spos[j] = (role << 30) | pos;
-      sapos[j] = apos;
+      P[j].x = __int_as_float((role << 30) | pos);  // x, y are dead from here on
+      P[j].y = __int_as_float(apos);
       rG += g;
       rGP += (g && ps);
       rNP += (!g && ps);
@@ -622,10 +629,8 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
   }
   __syncthreads();
   for (int j = tid; j < n; j += THREADS) {
-    if (!GLOBAL) {
-      a.slot_pos[base + slot0 + j] = spos[j];
-      a.slot_apos[base + slot0 + j] = sapos[j];
-    }
+    a.slot_pos[base + slot0 + j] = __float_as_int(P[j].x);
+    a.slot_apos[base + slot0 + j] = __float_as_int(P[j].y);
     a.slot_vid[base + slot0 + j] = (int)kv32[2 * j];
   }
   if (tid == 0) {
@@ -1062,57 +1067,112 @@ __global__ void __launch_bounds__(256) k_bin_only(const float4* __restrict__ pts
   }
 }
 
-// transformCloud (utility.h:394-406: left-to-right float, no FMA) + ungated re-binning
-// (ssc.cpp:1280-1286) + next.hash_cloud.find(voxel_idx) (ssc.cpp:1304) via the bitmap rank.
-__global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, const float4* __restrict__ carried,
-                                               const int32_t* __restrict__ sel, int k, const float* __restrict__ T, BinParams bp,
-                                               GridSpec g, const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr,
-                                               float4* __restrict__ out_xyzi, int32_t* __restrict__ out_hit) {
-  float t[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) t[i] = T[i];
+// ------------------------------------------------------------------------------------------------
+// Tracking diff (SSC::tracking, ssc.cpp:1274-1321): all car clusters of frame_pre_ in one launch.
+// The clouds are described by segments (own points gathered by apri index, or carried points that
+// already live on the device from the previous pair).  Per point: transformCloud (utility.h:394-406,
+// left-to-right float, no FMA) -> ungated re-binning (ssc.cpp:1280-1286) -> next.hash_cloud.find
+// (ssc.cpp:1304) via the bitmap rank.  Instead of shipping one hit per point to the host, the kernel
+// keeps, per (cluster, hit voxel), the smallest point position: that is exactly the information the
+// reference's remap_name needs (set of hit voxels per label + order of first occurrence).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, const int32_t* __restrict__ vox_off,
+                                               const int32_t* __restrict__ vox_pts, const float4* __restrict__ carried,
+                                               const int4* __restrict__ segs, int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
+                                               const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
+                                               float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
-    int s = sel[i];
-    float4 p = (s >= 0) ? __ldg(&own[s]) : __ldg(&carried[-1 - s]);
+    int lo = 0, hi = nseg - 1;  // last segment with dst_off <= i
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].x <= i)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    // x = dst_off, y = source (>= 0: voxel of frame_pre_, its points come from the CSR; < 0: carried range at -1-y),
+    // z = cluster, w = order of the segment inside the cluster's cloud (part index / carried ordinal)
+    const int4 sg = segs[lo];
+    const int j = i - sg.x;
+    float4 p;
+    unsigned low;
+    if (sg.y >= 0) {
+      int m = vox_pts[vox_off[sg.y] + j];
+      p = __ldg(&own[m]);
+      low = (unsigned)m;  // inside a part the reference's cloud is in ascending apri index (ssc.cpp:360-380)
+    } else {
+      p = __ldg(&carried[(-1 - sg.y) + j]);
+      low = (unsigned)j;
+    }
     float4 q;
-    q.x = da(da(da(dm(t[0], p.x), dm(t[1], p.y)), dm(t[2], p.z)), t[3]);
-    q.y = da(da(da(dm(t[4], p.x), dm(t[5], p.y)), dm(t[6], p.z)), t[7]);
-    q.z = da(da(da(dm(t[8], p.x), dm(t[9], p.y)), dm(t[10], p.z)), t[11]);
+    q.x = da(da(da(dm(T.m[0], p.x), dm(T.m[1], p.y)), dm(T.m[2], p.z)), T.m[3]);
+    q.y = da(da(da(dm(T.m[4], p.x), dm(T.m[5], p.y)), dm(T.m[6], p.z)), T.m[7]);
+    q.z = da(da(da(dm(T.m[8], p.x), dm(T.m[9], p.y)), dm(T.m[10], p.z)), T.m[11]);
     q.w = p.w;
     out_xyzi[i] = q;
     BinResult r = dev_bin_point(q.x, q.y, q.z, bp);
-    out_hit[i] = vox_lookup(bm, wr, g, r.vid);
+    int hit = vox_lookup(bm, wr, g, r.vid);
+    if (hit >= 0) atomicMin(&first[(size_t)sg.z * vn + hit], ((unsigned long long)(unsigned)sg.w << 32) | low);
   }
 }
 
-__global__ void __launch_bounds__(256) k_final_labels(const int32_t* __restrict__ apri_src, const int32_t* __restrict__ apri_cid,
-                                                      const uint8_t* __restrict__ vox_cls, int m_total, uint8_t* __restrict__ cls) {
+// compaction of the (cluster, voxel) -> first-occurrence key table: out[0] = count, quads from out[4]
+__global__ void __launch_bounds__(256) k_track_compact(const unsigned long long* __restrict__ first, int ncl, int vn,
+                                                       int32_t* __restrict__ out, int cap_quads) {
+  const int total = ncl * vn;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    unsigned long long f = first[e];
+    if (f != ~0ull) {
+      int slot = atomicAdd(&out[0], 1);
+      if (slot < cap_quads) {
+        out[4 + 4 * slot] = e / vn;
+        out[4 + 4 * slot + 1] = e % vn;
+        out[4 + 4 * slot + 2] = (int)(unsigned)(f >> 32);
+        out[4 + 4 * slot + 3] = (int)(unsigned)(f & 0xffffffffu);
+      }
+    }
+  }
+}
+
+// per-point classes of every frame of a batch from the per-voxel classes decided on the host
+__global__ void __launch_bounds__(256) k_final_labels(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                      const int32_t* __restrict__ apri_src, const int32_t* __restrict__ apri_cid,
+                                                      const int32_t* __restrict__ vcls_off, const uint8_t* __restrict__ vcls,
+                                                      uint8_t* __restrict__ cls) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int m_total = scan_counts[b * 8 + 2];
+  const uint8_t* vc = vcls + vcls_off[b];
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < m_total; m += gridDim.x * blockDim.x) {
-    int cid = apri_cid[m];
-    if (cid >= 0) cls[apri_src[m]] = vox_cls[cid];
+    int cid = apri_cid[base + m];
+    if (cid >= 0) cls[base + apri_src[base + m]] = vc[cid];
   }
 }
 
-// static submap: every non-dynamic point of a frame moved to the map frame (transformCloud arithmetic)
-__global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, const uint8_t* __restrict__ cls, int n,
-                                                const float* __restrict__ T, float4* __restrict__ out,
-                                                unsigned long long* __restrict__ counter, long long cap) {
+// static submap: every non-dynamic point of the frames of a batch moved to the map frame
+// (transformCloud arithmetic with the frame's pose), appended with warp-aggregated atomics
+__global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, const uint8_t* __restrict__ cls,
+                                                const int64_t* __restrict__ off, const float* __restrict__ Ts, int first_scan,
+                                                float4* __restrict__ out, unsigned long long* __restrict__ counter, long long cap) {
+  const int b = first_scan + blockIdx.y;
+  const int64_t base = off[b];
+  const int n = (int)(off[b + 1] - base);
   float t[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) t[i] = T[i];
+  for (int i = 0; i < 12; ++i) t[i] = Ts[blockIdx.y * 12 + i];
   const int lane = threadIdx.x & 31;
   for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += gridDim.x * blockDim.x) {
     int i = i0 + lane;
-    bool keep = (i < n) && cls[i] != SCVOD_PT_DYNAMIC;
+    bool keep = (i < n) && cls[base + i] != SCVOD_PT_DYNAMIC;
     unsigned mask = __ballot_sync(0xffffffffu, keep);
     if (!mask) continue;
     unsigned long long basepos = 0;
-    if (lane == 0) basepos = atomicAdd(counter, (unsigned long long)__popc(mask));  // warp-aggregated append
+    if (lane == 0) basepos = atomicAdd(counter, (unsigned long long)__popc(mask));
     basepos = __shfl_sync(0xffffffffu, basepos, 0);
     if (keep) {
       long long pos = (long long)basepos + __popc(mask & ((1u << lane) - 1));
       if (pos < cap) {
-        float4 p = __ldg(&pts[i]);
+        float4 p = __ldg(&pts[base + i]);
         float4 q;
         q.x = da(da(da(dm(t[0], p.x), dm(t[1], p.y)), dm(t[2], p.z)), t[3]);
         q.y = da(da(da(dm(t[4], p.x), dm(t[5], p.y)), dm(t[6], p.z)), t[7]);
@@ -1127,6 +1187,91 @@ __global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, 
 __global__ void k_atan2f_probe(const float* y, const float* x, float* out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = dev_atan2f(y[i], x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline block)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct TimedLaunch {
+  int name_id;
+  cudaEvent_t e0, e1;
+};
+bool g_timing = false;
+std::vector<std::string> g_names;
+std::vector<double> g_ms;
+std::vector<long long> g_cnt;
+std::vector<TimedLaunch> g_pending;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+int name_id(const char* name) {
+  for (size_t i = 0; i < g_names.size(); ++i)
+    if (g_names[i] == name) return (int)i;
+  g_names.push_back(name);
+  g_ms.push_back(0.0);
+  g_cnt.push_back(0);
+  return (int)g_names.size() - 1;
+}
+struct ScopedTimer {
+  cudaStream_t st;
+  TimedLaunch t;
+  bool on;
+  ScopedTimer(const char* name, cudaStream_t s) : st(s), on(g_timing) {
+    if (on) {
+      t.name_id = name_id(name);
+      t.e0 = get_event();
+      t.e1 = get_event();
+      cudaEventRecord(t.e0, st);
+    }
+  }
+  ~ScopedTimer() {
+    if (on) {
+      cudaEventRecord(t.e1, st);
+      g_pending.push_back(t);
+    }
+  }
+};
+}  // namespace
+#define TIMED(name, st) ScopedTimer timer__(name, st)
+#define TSTREAM ((cudaStream_t)stream_)
+
+void timing_enable(bool on) { g_timing = on; }
+void timing_reset() {
+  timing_collect();
+  for (auto& v : g_ms) v = 0;
+  for (auto& v : g_cnt) v = 0;
+}
+void timing_collect() {
+  for (auto& t : g_pending) {
+    cudaEventSynchronize(t.e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t.e0, t.e1);
+    g_ms[t.name_id] += ms;
+    g_cnt[t.name_id] += 1;
+    g_event_pool.push_back(t.e0);
+    g_event_pool.push_back(t.e1);
+  }
+  g_pending.clear();
+}
+std::string timing_report() {
+  timing_collect();
+  std::string out;
+  char line[256];
+  for (size_t i = 0; i < g_names.size(); ++i) {
+    snprintf(line, sizeof(line), "%s %.6f %lld\n", g_names[i].c_str(), g_ms[i], g_cnt[i]);
+    out += line;
+  }
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1199,15 +1344,16 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   int launches = 0;
   cudaMemsetAsync(d.patch_cnt, 0, sizeof(int32_t) * (size_t)nscans * kNumPatches, st);
   dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
-  k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, d.patch_cnt, d.cls);
-  k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur);
-  k_patch_scatter<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_of, d.patch_off, d.patch_cur, d.bucket_kv);
+  { TIMED("k_patch_assign", TSTREAM); k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, d.patch_cnt, d.cls); }
+  { TIMED("k_patch_scan", TSTREAM); k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur); }
+  { TIMED("k_patch_scatter", TSTREAM); k_patch_scatter<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_of, d.patch_off, d.patch_cur, d.bucket_kv); }
   FitArgs fa;
   fa.pts = d.pts;
   fa.off = d.off;
   fa.patch_cnt = d.patch_cnt;
   fa.patch_off = d.patch_off;
   fa.bucket_kv = d.bucket_kv;
+  fa.scratch4 = d.apri_xyzi;
   fa.sorted_idx = d.sorted_idx;
   fa.slot_pos = d.slot_pos;
   fa.slot_apos = d.slot_apos;
@@ -1220,25 +1366,35 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   fa.gc = gc;
   fa.bp = bp;
   static bool attr_set = false;
-  const int smem_small = kFitSmall * 20, smem_large = kFitLarge * 20;
+  constexpr int kT0 = 1024, kT1 = 2048, kT2 = 4096;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_patch_fit<kFitSmall, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_small);
-    cudaFuncSetAttribute(k_patch_fit<kFitLarge, kFitSmall, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_large);
+    cudaFuncSetAttribute(k_patch_fit<kT0, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT0 * 24);
+    cudaFuncSetAttribute(k_patch_fit<kT1, kT0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1 * 24);
+    cudaFuncSetAttribute(k_patch_fit<kT2, kT1, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2 * 24);
+    cudaFuncSetAttribute(k_patch_fit<kFitLarge, kT2, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitLarge * 24);
     attr_set = true;
   }
   dim3 gfit(kNumPatches, nscans);
-  k_patch_fit<kFitSmall, 0, 128, false><<<gfit, 128, smem_small, st>>>(fa);
-  if (max_scan_points > kFitSmall) {
-    k_patch_fit<kFitLarge, kFitSmall, 256, false><<<gfit, 256, smem_large, st>>>(fa);
+  { TIMED("k_patch_fit_1k", TSTREAM); k_patch_fit<kT0, 0, 128, false><<<gfit, 128, kT0 * 24, st>>>(fa); }
+  if (max_scan_points > kT0) {
+    { TIMED("k_patch_fit_2k", TSTREAM); k_patch_fit<kT1, kT0, 128, false><<<gfit, 128, kT1 * 24, st>>>(fa); }
+    launches += 1;
+  }
+  if (max_scan_points > kT1) {
+    { TIMED("k_patch_fit_4k", TSTREAM); k_patch_fit<kT2, kT1, 256, false><<<gfit, 256, kT2 * 24, st>>>(fa); }
+    launches += 1;
+  }
+  if (max_scan_points > kT2) {
+    { TIMED("k_patch_fit_9k", TSTREAM); k_patch_fit<kFitLarge, kT2, 256, false><<<gfit, 256, kFitLarge * 24, st>>>(fa); }
     launches += 1;
   }
   if (max_scan_points > kFitLarge) {  // overflow tier: scratch in global memory
-    k_patch_fit<0x3fffffff, kFitLarge, 256, true><<<gfit, 256, 0, st>>>(fa);
+    { TIMED("k_patch_fit_overflow", TSTREAM); k_patch_fit<0x3fffffff, kFitLarge, 256, true><<<gfit, 256, 0, st>>>(fa); }
     launches += 1;
   }
-  k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts);
-  k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
-                             d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls);
+  { TIMED("k_patch_out_scan", TSTREAM); k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts); }
+  { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
+                             d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls); }
   launches += 6;
   return launches;
 }
@@ -1248,14 +1404,14 @@ int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int max_sca
   BinParams bp = make_bin_params(hp);
   cudaMemsetAsync(d.bitmap, 0, sizeof(uint32_t) * (size_t)nscans * hp.g.words, st);
   dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
-  k_vox_mark<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap);
-  k_vox_rank<<<nscans, 1024, 0, st>>>(d.off, hp.g, d.bitmap, d.word_rank, d.vox_vid, d.vox_cnt, d.scan_counts);
-  k_vox_count<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap, d.word_rank, d.apri_cid, d.vox_cnt);
-  k_vox_offsets<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_cur);
-  k_vox_fill<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.vox_off, d.vox_cur, d.vox_pts_tmp);
+  { TIMED("k_vox_mark", TSTREAM); k_vox_mark<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap); }
+  { TIMED("k_vox_rank", TSTREAM); k_vox_rank<<<nscans, 1024, 0, st>>>(d.off, hp.g, d.bitmap, d.word_rank, d.vox_vid, d.vox_cnt, d.scan_counts); }
+  { TIMED("k_vox_count", TSTREAM); k_vox_count<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap, d.word_rank, d.apri_cid, d.vox_cnt); }
+  { TIMED("k_vox_offsets", TSTREAM); k_vox_offsets<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_cur); }
+  { TIMED("k_vox_fill", TSTREAM); k_vox_fill<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.vox_off, d.vox_cur, d.vox_pts_tmp); }
   dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 8), nscans);  // one warp per voxel, 8 warps per CTA
-  k_vox_stats<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_pts_tmp, d.apri_xyzi, bp, hp.p, d.vox_pts,
-                                  d.apri_rank, d.vox_av, d.vox_cov, d.vox_center, d.vox_tri, d.vox_bbox);
+  { TIMED("k_vox_stats", TSTREAM); k_vox_stats<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_pts_tmp, d.apri_xyzi, bp, hp.p, d.vox_pts,
+                                  d.apri_rank, d.vox_av, d.vox_cov, d.vox_center, d.vox_tri, d.vox_bbox); }
   return 6;
 }
 
@@ -1263,13 +1419,13 @@ int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int max_s
   cudaStream_t st = (cudaStream_t)stream_;
   cudaMemsetAsync(d.edge_hash, 0xff, sizeof(unsigned long long) * (size_t)nscans * d.hash_cap, st);
   dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 256), nscans);
-  k_vox_nbr<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_nbr, d.vox_root);
-  k_ccl_union<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_nbr, d.vox_root);
-  k_ccl_flatten<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_root);
-  k_similar_edges<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_av, d.vox_cov, d.vox_root,
+  { TIMED("k_vox_nbr", TSTREAM); k_vox_nbr<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_nbr, d.vox_root); }
+  { TIMED("k_ccl_union", TSTREAM); k_ccl_union<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_nbr, d.vox_root); }
+  { TIMED("k_ccl_flatten", TSTREAM); k_ccl_flatten<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_root); }
+  { TIMED("k_similar_edges", TSTREAM); k_similar_edges<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_av, d.vox_cov, d.vox_root,
                                       hp.p.search_c, hp.p.intensity_cov, hp.p.intensity_diff,
-                                      reinterpret_cast<unsigned long long*>(d.edge_hash), d.hash_cap, d.edge_buf, d.edge_cap);
-  k_events<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.apri_rank, d.ev_cid);
+                                      reinterpret_cast<unsigned long long*>(d.edge_hash), d.hash_cap, d.edge_buf, d.edge_cap); }
+  { TIMED("k_events", TSTREAM); k_events<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.apri_rank, d.ev_cid); }
   return 5;
 }
 
@@ -1279,40 +1435,47 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
   int blocks = (n + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  k_bin_only<<<blocks, 256, 0, (cudaStream_t)stream_>>>(pts_dev, n, make_bin_params(hp), pass, vid, ri, si, ei, range, angle, azimuth);
+  { TIMED("k_bin_only", TSTREAM); k_bin_only<<<blocks, 256, 0, (cudaStream_t)stream_>>>(pts_dev, n, make_bin_params(hp), pass, vid, ri, si, ei, range, angle, azimuth); }
   return 1;
 }
 
-int launch_track(const HostParams& hp, const float4* own_xyzi, const float4* carried, const int32_t* sel, int k, const float* T12_dev,
-                 const uint32_t* next_bitmap, const int32_t* next_word_rank, float4* out_xyzi, int32_t* out_hit, void* stream_) {
-  if (k <= 0) return 0;
+int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
+                 const int4* segs, int nseg, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* out_quads, int cap_quads, void* stream_) {
+  if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * (size_t)ncl * vn, st);
+  cudaMemsetAsync(out_quads, 0, sizeof(int32_t) * 4, st);
+  Mat34 T;
+  for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
   int blocks = (k + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  k_track<<<blocks, 256, 0, (cudaStream_t)stream_>>>(own_xyzi, carried, sel, k, T12_dev, make_bin_params(hp), hp.g, next_bitmap,
-                                                   next_word_rank, out_xyzi, out_hit);
+  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first); }
+  int blocks2 = (ncl * vn + 255) / 256;
+  if (blocks2 > cap) blocks2 = cap;
+  { TIMED("k_track_compact", TSTREAM); k_track_compact<<<blocks2, 256, 0, st>>>(first, ncl, vn, out_quads, cap_quads); }
+  return 2;
+}
+
+int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
+                        const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream_) {
+  if (nscans <= 0) return 0;
+  dim3 grid(grid_x_for(nscans, max_scan_points, 256), nscans);
+  { TIMED("k_final_labels", TSTREAM); k_final_labels<<<grid, 256, 0, (cudaStream_t)stream_>>>(off, scan_counts, apri_src, apri_cid, vcls_off, vcls, cls); }
   return 1;
 }
 
-int launch_final_labels(const int32_t* apri_src, const int32_t* apri_cid, const uint8_t* vox_cls, int m, uint8_t* cls, void* stream_) {
-  if (m <= 0) return 0;
-  int blocks = (m + 255) / 256;
-  k_final_labels<<<blocks, 256, 0, (cudaStream_t)stream_>>>(apri_src, apri_cid, vox_cls, m, cls);
-  return 1;
-}
-
-int launch_submap(const float4* pts, const uint8_t* cls, int n, const float* T12_dev, float4* out, unsigned long long* counter,
-                  long long cap, void* stream_) {
-  if (n <= 0) return 0;
-  int blocks = (n + 255) / 256;
-  int capb = num_sms() * 8;
-  if (blocks > capb) blocks = capb;
-  k_submap<<<blocks, 256, 0, (cudaStream_t)stream_>>>(pts, cls, n, T12_dev, out, counter, cap);
+int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,
+                  int max_scan_points, float4* out, unsigned long long* counter, long long cap, void* stream_) {
+  if (nscans <= 0) return 0;
+  dim3 grid(grid_x_for(nscans, max_scan_points, 256), nscans);
+  { TIMED("k_submap", TSTREAM); k_submap<<<grid, 256, 0, (cudaStream_t)stream_>>>(pts, cls, off, Ts_dev, first_scan, out, counter, cap); }
   return 1;
 }
 
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream_) {
-  k_atan2f_probe<<<num_sms() * 8, 256, 0, (cudaStream_t)stream_>>>(y, x, out, n);
+  { TIMED("k_atan2f_probe", TSTREAM); k_atan2f_probe<<<num_sms() * 8, 256, 0, (cudaStream_t)stream_>>>(y, x, out, n); }
   return 1;
 }
 

@@ -89,6 +89,13 @@ int scvod_num_kernel_launches(const scvod_ctx* ctx, int64_t* out); /* kernels la
  * "host_threads" (threads used for the per-scan cluster bookkeeping). */
 int scvod_set_option(scvod_ctx* ctx, const char* key, int value);
 
+/* Run all work of this context on a caller-owned CUDA stream (e.g. torch's current stream). */
+int scvod_set_stream(scvod_ctx* ctx, void* cuda_stream);
+/* Process-wide per-kernel timing with CUDA events on the launching stream: enable!=0 starts (and
+ * resets), the report is text lines "<kernel> <total ms> <launches>". Returns the text length. */
+int scvod_kernel_timing(int enable);
+int scvod_kernel_timing_report(char* buf, int cap);
+
 /* ---- stage entry points (single scan, host buffers; replace the bodies named on each line) --- */
 
 /* PatchWork::estimate_ground (patchwork.h:278-398) as called by SSC::extractGroudByPatchWork
@@ -125,7 +132,8 @@ int scvod_reset_frames(scvod_ctx* ctx); /* SSC::reset + frame_set.clear() */
 /* Per-input-point outcome class (enum scvod_point_class) of frame f; cls holds n_in bytes. */
 int scvod_frame_labels(scvod_ctx* ctx, int frame, uint8_t* cls, int n);
 
-/* Labels of frames [f0,f1) concatenated in frame order into one host buffer of `cap` bytes. */
+/* Labels of frames [f0,f1) concatenated in frame order into one host buffer of `cap` bytes.
+ * cls == NULL only brings the device-resident label arrays up to date (no copy). */
 int scvod_labels_range(scvod_ctx* ctx, int f0, int f1, uint8_t* cls, int64_t cap);
 
 /* frame inspection — sizes: counts[0]=n_in, [1]=n_ground, [2]=n_nonground, [3]=n_apri (cloud_use),
