@@ -453,7 +453,15 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
     }
     __syncthreads();
     double thr = __dadd_rn(s_lpr, 0.3);
-    for (int j = tid; j < n; j += THREADS) P[j].w = __uint_as_float(((double)P[j].z < thr) ? F_G : 0u);
+    if (tid == 0) s_int[1] = 0;
+    __syncthreads();
+    int local = 0;
+    for (int j = tid; j < n; j += THREADS) {
+      bool in = (double)P[j].z < thr;
+      P[j].w = __uint_as_float(in ? F_G : 0u);
+      local += in ? 1 : 0;
+    }
+    if (local) atomicAdd(&s_int[1], local);
     __syncthreads();
   }
 
@@ -465,20 +473,26 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
       // Strictly sequential in z-sorted order (PCL's float single pass is order dependent); points
       // outside the ground set contribute -0.0f, which is an exact identity for float addition, so
       // the loop is branch free and the only loop-carried dependency is one FADD.
-      const bool a_is_x = (lane < 3 || lane == 6), a_is_y = (lane == 3 || lane == 4 || lane == 7);
-      const bool b_is_x = (lane == 0), b_is_y = (lane == 1 || lane == 3), b_is_z = (lane == 2 || lane == 4 || lane == 5);
+      // Each lane reads its two factors straight from shared memory with a lane-specific word offset
+      // inside the point's float4 (no selects, no divergence); lanes 6..8 multiply by 1.
+      const int ia = (lane < 3 || lane == 6) ? 0 : ((lane == 3 || lane == 4 || lane == 7) ? 1 : 2);
+      const int ib = (lane == 0) ? 0 : ((lane == 1 || lane == 3) ? 1 : 2);
+      const bool plain_sum = lane >= 6;
+      const float* pa = reinterpret_cast<const float*>(P) + ia;
+      const float* pb = reinterpret_cast<const float*>(P) + ib;
+      const uint32_t* pf = reinterpret_cast<const uint32_t*>(P) + 3;
       float acc = 0.f;
-      int cnt = 0;
 #pragma unroll 8
       for (int j = 0; j < n; ++j) {
-        const float4 q = P[j];
-        const float av = a_is_x ? q.x : (a_is_y ? q.y : q.z);
-        const float bv = b_is_x ? q.x : (b_is_y ? q.y : (b_is_z ? q.z : 1.0f));
-        const bool in = (__float_as_uint(q.w) & F_G) != 0u;
-        const float term = in ? dm(av, bv) : -0.0f;
+        const float av = pa[4 * j];
+        float bv = pb[4 * j];
+        const uint32_t fl = pf[4 * j];
+        bv = plain_sum ? 1.0f : bv;
+        float term = dm(av, bv);
+        term = (fl & F_G) ? term : -0.0f;
         acc = da(acc, term);
-        cnt += in ? 1 : 0;
       }
+      const int cnt = s_int[1];
       float accu[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) accu[k] = __shfl_sync(0xffffffffu, acc, k);
@@ -520,12 +534,18 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
     }
     __syncthreads();
     const float n0 = s_plane[0], n1 = s_plane[1], n2 = s_plane[2], th = s_plane[3];
+    if (tid == 0) s_int[1] = 0;
+    __syncthreads();
+    int local = 0;
     for (int j = tid; j < n; j += THREADS) {
       // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
       const float4 q = P[j];
       float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
-      P[j].w = __uint_as_float((res < th) ? F_G : 0u);
+      bool in = res < th;
+      P[j].w = __uint_as_float(in ? F_G : 0u);
+      local += in ? 1 : 0;
     }
+    if (local) atomicAdd(&s_int[1], local);
     __syncthreads();
   }
 
