@@ -35,11 +35,12 @@ RINGS, COLS = 64, 1800
 SEED = 0x5C0D0000
 # algorithmic (compulsory) bytes per unit for the stage each kernel dominates
 ALGO_BYTES = {
-    "k_patch_fit": ("ground stage, 32 B per input point (16N read + 16N written in reference order)", 32.0, "points"),
-    "k_patch_assign": ("ground stage, 32 B per input point", 32.0, "points"),
-    "k_patch_scatter": ("ground stage, 32 B per input point", 32.0, "points"),
-    "k_emit": ("ground stage, 32 B per input point", 32.0, "points"),
-    "k_vox_stats": ("descriptor stage, 12 B per apri point + 32 B per voxel", 12.0, "apri"),
+    "k_patch_fit": ("ground stage (P1-P6): 32 B per input point (16N read + 16N written in reference order)", 32.0, "points"),
+    "k_patch_assign": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
+    "k_patch_scatter": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
+    "k_emit": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
+    "k_vox_stats": ("descriptor stage (B3): 12 B per apri point", 12.0, "apri"),
+    "k_track": ("diff stage (D1-D2): 16 B read + 16 B written (carried cloud) + 4 B hit per re-binned cluster point", 36.0, "track_points"),
 }
 
 
@@ -168,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--scans-per-step", type=int, default=64)
     ap.add_argument("--pool", type=int, default=3, help="distinct input batches rotated through (pool > L2)")
+    ap.add_argument("--workers", type=int, default=0, help="independent sequence chunks processed side by side per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans for the cpu_baseline leg (0 = auto)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -190,6 +192,8 @@ def main():
     pkg = entry._load_package()
     params = pkg.semantickitti_params()
     S = args.scans_per_step
+    local_world = env_int("LOCAL_WORLD_SIZE", world)
+    W = args.workers if args.workers > 0 else max(1, min(8, (os.cpu_count() or 8) // (2 * max(1, local_world))))
     # each rank owns its own sequence chunks (scan-sharding, no data-path collective before the submap merge)
     batches = []
     for b in range(args.pool):
@@ -200,16 +204,30 @@ def main():
         flat = torch.from_numpy(np.concatenate(scans, axis=0)).pin_memory()
         batches.append({"scans": scans, "poses": poses, "off": off, "host": flat, "dev": flat.to(dev), "npts": int(off[-1])})
     max_pts = max(b["npts"] for b in batches)
-    ssc = pkg.SSC(params, device=local_rank, max_points=RINGS * COLS, max_batch=S)
-    ssc.set_option("inspect", 0)
-    ssc.set_stream(torch.cuda.current_stream().cuda_stream)
-    labels_host = torch.empty(max_pts, dtype=torch.uint8).pin_memory()
-    submap = torch.empty((max_pts, 4), dtype=torch.float32, device=dev)
+
+    # W independent workers per GPU: each owns a context, a CUDA stream and its sequence chunks.  The tracking
+    # chain of a chunk is a latency-bound host<->device ping-pong; running several chunks side by side keeps
+    # the GPU busy (the same sharding that spreads chunks over GPUs, applied inside one GPU).
+    class Worker:
+        def __init__(self, wid):
+            self.wid = wid
+            self.stream = torch.cuda.Stream(device=dev)
+            self.ssc = pkg.SSC(params, device=local_rank, max_points=RINGS * COLS, max_batch=S)
+            self.ssc.set_option("inspect", 0)
+            self.ssc.set_option("host_threads", max(2, (os.cpu_count() or 8) // W))
+            self.ssc.set_stream(self.stream.cuda_stream)
+            self.labels_host = torch.empty(max_pts, dtype=torch.uint8).pin_memory()
+            self.submap = torch.empty((max_pts, 4), dtype=torch.float32, device=dev)
+            self.submap_free = threading.Event()
+            self.submap_free.set()
+
+    workers = [Worker(w) for w in range(W)]
     gathered = torch.empty((world * max_pts, 4), dtype=torch.float32, device=dev) if world > 1 else None
     counts_all = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
 
-    def step(i, host_io):
+    def step(wk, i, host_io):
         b = batches[i % len(batches)]
+        ssc = wk.ssc
         ssc.reset()
         if host_io:
             ssc.process_host_ptr(b["host"].data_ptr(), b["off"])
@@ -217,36 +235,78 @@ def main():
             ssc.process_device(b["dev"].data_ptr(), b["off"])
         ssc.tracking(b["poses"])
         if host_io:
-            ssc.labels_into(0, S, labels_host.data_ptr(), labels_host.numel())
+            ssc.labels_into(0, S, wk.labels_host.data_ptr(), wk.labels_host.numel())
         else:
             ssc.refresh_labels(0, S)
-        n_static = ssc.static_submap_device(0, S, b["poses"], submap.data_ptr(), max_pts)
-        if world > 1:  # the one collective of the path: merge per-GPU static submaps (NCCL all-gather over NVLink)
-            mine = torch.tensor([n_static], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(counts_all, mine)
-            dist.all_gather_into_tensor(gathered, submap)
-        return n_static
+        if world > 1:
+            wk.submap_free.wait()  # the comm thread may still be gathering this worker's previous submap
+            wk.submap_free.clear()
+        return ssc.static_submap_device(0, S, b["poses"], wk.submap.data_ptr(), max_pts)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(first_step, nsteps, host_io):
+        """nsteps steps spread over the workers; the per-GPU static submaps are merged by ONE NCCL all-gather
+        per step, issued in step order by a single communication thread (same order on every rank)."""
+        done = {}
+        cv = threading.Condition()
+        errors = []
+
+        def work(wk):
+            try:
+                with torch.cuda.stream(wk.stream):
+                    for i in range(first_step + wk.wid, first_step + nsteps, W):
+                        n_static = step(wk, i, host_io)
+                        with cv:
+                            done[i] = (wk, n_static)
+                            cv.notify_all()
+            except Exception as e:  # noqa: BLE001
+                with cv:
+                    errors.append(e)
+                    cv.notify_all()
+
+        def comm():
+            for i in range(first_step, first_step + nsteps):
+                with cv:
+                    while i not in done and not errors:
+                        cv.wait()
+                    if errors:
+                        return
+                    wk, n_static = done.pop(i)
+                mine = torch.tensor([n_static], dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(counts_all, mine)
+                dist.all_gather_into_tensor(gathered, wk.submap)
+                torch.cuda.current_stream().synchronize()
+                wk.submap_free.set()
+
+        threads = [threading.Thread(target=work, args=(wk,)) for wk in workers]
+        if world > 1:
+            threads.append(threading.Thread(target=comm))
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
     def timed(host_io, with_kernel_timing):
-        for i in range(args.warmup):
-            step(i, host_io)
+        run_steps(0, max(args.warmup, W * len(batches)), host_io)  # every worker sees every pool batch once: buffers reach steady state
         barrier()
         if with_kernel_timing:
             pkg.kernel_timing(True)
-        l0 = ssc.kernel_launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = sum(wk.ssc.kernel_launches for wk in workers)
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            step(args.warmup + i, host_io)
+        run_steps(1000, args.steps, host_io)
+        for wk in workers:
+            torch.cuda.current_stream().wait_stream(wk.stream)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -255,14 +315,29 @@ def main():
         rep = pkg.kernel_timing_report() if with_kernel_timing else None
         if with_kernel_timing:
             pkg.kernel_timing(False)
-        secs = max(ev, wall)  # the step ends with host-side bookkeeping, so wall >= device time
+        secs = max(ev, wall)  # every step ends with host-side bookkeeping, so wall >= device time
         t = torch.tensor([secs], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), ssc.kernel_launches - l0, clocks, rep
+        return float(t.item()), sum(wk.ssc.kernel_launches for wk in workers) - l0, clocks, rep
 
-    secs_dev, launches, clocks, rep = timed(False, True)
+    secs_dev, launches, clocks, _ = timed(False, False)
     secs_e2e, _, clocks_e2e, _ = timed(True, False)
+    # roofline block: per-kernel CUDA-event durations need launches that do not overlap with other streams, so
+    # they are measured in a dedicated pass of the same steps on ONE worker (events on that worker's stream)
+    rep = None
+    if rank == 0:
+        pkg.kernel_timing(True)
+        with torch.cuda.stream(workers[0].stream):
+            for i in range(args.steps):
+                step(workers[0], 2000 + i, False)
+                if world > 1:
+                    workers[0].submap_free.set()
+        torch.cuda.synchronize()
+        rep = pkg.kernel_timing_report()
+        pkg.kernel_timing(False)
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         value = world * S * args.steps / secs_dev
@@ -274,12 +349,16 @@ def main():
         dom_name, (dom_ms, dom_cnt) = dom
         key = "k_patch_fit" if dom_name.startswith("k_patch_fit") else dom_name
         desc, bytes_per_unit, unit_kind = ALGO_BYTES.get(key, ("ground stage, 32 B per input point", 32.0, "points"))
-        units_per_launch = avg_pts * S
+        w0 = workers[0].ssc
+        per_kind = {"points": w0.stat("points"), "apri": w0.stat("apri_points"), "track_points": w0.stat("track_points")}
+        steps_seen = max(1, w0.stat("scans") // S)
+        units_per_launch = per_kind[unit_kind] / steps_seen * (args.steps / dom_cnt)  # units handled by one launch, on average
         achieved = bytes_per_unit * units_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e9
         total_kernel_ms = sum(v[0] for v in rep.values())
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes": desc, "avg_launch_ms": dom_ms / dom_cnt,
                     "kernel_share_of_gpu_time": dom_ms / total_kernel_ms,
+                    "measured": f"CUDA events on the launching stream, dedicated single-worker pass of {args.steps} steps inside bench.py",
                     "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0])}}
         ncores = os.cpu_count() or 1
         b0 = batches[0]
@@ -293,7 +372,9 @@ def main():
                        "scans_per_step": S, "points_per_scan": avg_pts, "rings": RINGS, "cols": COLS,
                        "l2": f"inputs rotate over a pool of {args.pool} batches ({args.pool * b0['npts'] * 16 / 1e6:.0f} MB) larger than the 126 MB L2; "
                              "per-step workspace (>1 GB) is rewritten every step",
-                       "sharding": "scan-sharded, one independent sequence chunk per rank; one NCCL all-gather of static submaps per step" if world > 1 else "single GPU"},
+                       "workers_per_gpu": W,
+                       "sharding": ("scan-sharded: independent sequence chunks per rank and per worker; one NCCL all-gather of static submaps per step"
+                                    if world > 1 else "single GPU; independent sequence chunks per worker")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b0["npts"] * 16 + (S + 1) * 8), "d2h_bytes_per_step": int(b0["npts"]),
                     "ms_per_step": 1000.0 * secs_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -308,7 +389,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ssc.close()
+    for wk in workers:
+        wk.ssc.close()
     return 0
 
 

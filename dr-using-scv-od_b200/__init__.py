@@ -45,7 +45,7 @@ EXPORTS = (
     "scvod_push_scans_dev", "scvod_track", "scvod_num_frames", "scvod_reset_frames", "scvod_frame_labels",
     "scvod_labels_range", "scvod_frame_counts", "scvod_frame_ground_order", "scvod_frame_apri", "scvod_frame_voxels",
     "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
-    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report",
+    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
 )
 
 _lib = None
@@ -162,6 +162,11 @@ class SSC:
 
     def set_option(self, key: str, value: int):
         _check(self._lib.scvod_set_option(self._ctx, key.encode(), int(value)))
+
+    def stat(self, key: str) -> int:
+        v = ctypes.c_int64()
+        _check(self._lib.scvod_get_stat(self._ctx, key.encode(), ctypes.byref(v)))
+        return v.value
 
     def set_stream(self, cuda_stream: int):
         _check(self._lib.scvod_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))

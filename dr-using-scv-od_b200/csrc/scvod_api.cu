@@ -40,7 +40,9 @@ namespace {
 struct HostProf {
   bool on = getenv("SCVOD_PROFILE") != nullptr;
   std::vector<std::pair<std::string, double>> acc;
+  std::mutex mu;
   void add(const char* name, double ms) {
+    std::lock_guard<std::mutex> lk(mu);
     for (auto& a : acc)
       if (a.first == name) {
         a.second += ms;
@@ -185,6 +187,10 @@ struct scvod_ctx {
   // pinned host mirrors of what the host logic reads per batch
   PinBuf<int32_t> h_scan_counts, h_vox_cnt, h_vox_root, h_vox_nbr, h_ev_cid, h_edge_buf;
   PinBuf<float> h_vox_bbox;
+  PinBuf<int32_t> h_pack;
+  DevBuf<int32_t> d_pack;
+  PinBuf<PackDesc> h_desc;
+  DevBuf<PackDesc> d_desc;
   // tracking buffers: packed request (segments + own indices), ping-pong transformed clouds, hit table
   DevBuf<int32_t> d_treq, d_triples;
   DevBuf<unsigned long long> d_first;
@@ -203,6 +209,7 @@ struct scvod_ctx {
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
   int track_name = 0;  // SSC::name (ssc.h:49)
+  int64_t stat_track_points = 0, stat_track_pairs = 0, stat_scans = 0, stat_points = 0, stat_apri = 0, stat_voxels = 0;
 };
 
 static void params_common(scvod_params* p) {
@@ -402,6 +409,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->h_treq.release(); c->h_triples.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
   c->d_Ts.release(); c->h_Ts.release();
   c->d_counter.release();
+  c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return SCVOD_OK;
@@ -410,6 +418,19 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
 extern "C" int scvod_num_kernel_launches(const scvod_ctx* c, int64_t* out) {
   if (!c || !out) return fail(SCVOD_ERR_ARG, "null argument");
   *out = c->launches;
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_get_stat(scvod_ctx* c, const char* key, int64_t* out) {
+  if (!c || !key || !out) return fail(SCVOD_ERR_ARG, "null argument");
+  std::string k(key);
+  if (k == "track_points") *out = c->stat_track_points;
+  else if (k == "track_pairs") *out = c->stat_track_pairs;
+  else if (k == "scans") *out = c->stat_scans;
+  else if (k == "points") *out = c->stat_points;
+  else if (k == "apri_points") *out = c->stat_apri;
+  else if (k == "voxels") *out = c->stat_voxels;
+  else return fail(SCVOD_ERR_ARG, "unknown stat " + k);
   return SCVOD_OK;
 }
 
@@ -555,28 +576,48 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   }
 
   std::chrono::steady_clock::time_point td0 = std::chrono::steady_clock::now();
-  CU(c->h_vox_cnt.alloc(std::max<int64_t>(1, vbase[nscans])));
-  CU(c->h_vox_root.alloc(std::max<int64_t>(1, vbase[nscans])));
-  CU(c->h_vox_nbr.alloc(std::max<int64_t>(1, vbase[nscans] * 27)));
-  CU(c->h_vox_bbox.alloc(std::max<int64_t>(1, vbase[nscans] * 6)));
-  CU(c->h_ev_cid.alloc(std::max<int64_t>(1, ebase[nscans])));
-  CU(c->h_edge_buf.alloc(std::max<int64_t>(1, gbase[nscans] * 2)));
+  // one packed gather + one D2H for all per-scan tables: [cnt Vt][root Vt][nbr 27Vt][bbox 6Vt][events Et][edges 2Gt]
+  const int64_t Vt = vbase[nscans], Et = ebase[nscans], Gt = gbase[nscans];
+  const int64_t o_cnt = 0, o_root = Vt, o_nbr = 2 * Vt, o_bbox = 29 * Vt, o_ev = 35 * Vt, o_edge = 35 * Vt + Et;
+  const int64_t pack_ints = std::max<int64_t>(1, 35 * Vt + Et + 2 * Gt);
+  CU(c->h_pack.alloc(pack_ints));
+  CU(c->d_pack.alloc(pack_ints));
+  CU(c->h_desc.alloc((size_t)nscans * 6));
+  CU(c->d_desc.alloc((size_t)nscans * 6));
+  int nd = 0, max_desc_n = 1;
   for (int s = 0; s < nscans; ++s) {
     int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
     int64_t b = off[s];
-    if (V > 0) {
-      CU(cudaMemcpyAsync(c->h_vox_cnt.p + vbase[s], w.vox_cnt + b, sizeof(int32_t) * V, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(c->h_vox_root.p + vbase[s], w.vox_root + b, sizeof(int32_t) * V, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(c->h_vox_nbr.p + vbase[s] * 27, w.vox_nbr + b * 27, sizeof(int32_t) * V * 27, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(c->h_vox_bbox.p + vbase[s] * 6, w.vox_bbox + b * 6, sizeof(float) * V * 6, cudaMemcpyDeviceToHost, st));
-    }
-    if (E > 0) CU(cudaMemcpyAsync(c->h_ev_cid.p + ebase[s], w.ev_cid + b, sizeof(int32_t) * E, cudaMemcpyDeviceToHost, st));
-    if (G > 0)
-      CU(cudaMemcpyAsync(c->h_edge_buf.p + gbase[s] * 2, w.edge_buf + (size_t)s * w.edge_cap * 2, sizeof(int32_t) * G * 2,
-                         cudaMemcpyDeviceToHost, st));
+    auto add = [&](const void* src, int64_t dst, int n) {
+      if (n <= 0) return;
+      PackDesc d;
+      d.src = reinterpret_cast<const int32_t*>(src);
+      d.dst = dst;
+      d.n = n;
+      d.pad = 0;
+      c->h_desc.p[nd++] = d;
+      max_desc_n = std::max(max_desc_n, n);
+    };
+    add(w.vox_cnt + b, o_cnt + vbase[s], V);
+    add(w.vox_root + b, o_root + vbase[s], V);
+    add(w.vox_nbr + b * 27, o_nbr + vbase[s] * 27, V * 27);
+    add(w.vox_bbox + b * 6, o_bbox + vbase[s] * 6, V * 6);
+    add(w.ev_cid + b, o_ev + ebase[s], E);
+    add(w.edge_buf + (size_t)s * w.edge_cap * 2, o_edge + gbase[s] * 2, G * 2);
+  }
+  if (nd > 0) {
+    CU(cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, sizeof(PackDesc) * nd, cudaMemcpyHostToDevice, st));
+    c->launches += launch_pack(c->d_desc.p, nd, max_desc_n, c->d_pack.p, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_pack.p, c->d_pack.p, sizeof(int32_t) * pack_ints, cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
-
+  const int32_t* hp_cnt = c->h_pack.p + o_cnt;
+  const int32_t* hp_root = c->h_pack.p + o_root;
+  const int32_t* hp_nbr = c->h_pack.p + o_nbr;
+  const float* hp_bbox = reinterpret_cast<const float*>(c->h_pack.p + o_bbox);
+  const int32_t* hp_ev = c->h_pack.p + o_ev;
+  const int32_t* hp_edge = c->h_pack.p + o_edge;
   if (g_prof.on) g_prof.add("  d2h voxel tables", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td0).count());
   std::chrono::steady_clock::time_point th0 = std::chrono::steady_clock::now();
   // host cluster bookkeeping, one scan per task
@@ -603,12 +644,12 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
       t.V = fr.n_vox;
       t.n_events = sc[s * 8 + 5];
       t.n_edges = sc[s * 8 + 7];
-      t.vox_cnt = c->h_vox_cnt.p + vbase[s];
-      t.vox_root = c->h_vox_root.p + vbase[s];
-      t.vox_nbr = c->h_vox_nbr.p + vbase[s] * 27;
-      t.vox_bbox = c->h_vox_bbox.p + vbase[s] * 6;
-      t.ev_cid = c->h_ev_cid.p + ebase[s];
-      t.edges = c->h_edge_buf.p + gbase[s] * 2;
+      t.vox_cnt = hp_cnt + vbase[s];
+      t.vox_root = hp_root + vbase[s];
+      t.vox_nbr = hp_nbr + vbase[s] * 27;
+      t.vox_bbox = hp_bbox + vbase[s] * 6;
+      t.ev_cid = hp_ev + ebase[s];
+      t.edges = hp_edge + gbase[s] * 2;
       fr.vox_cnt.assign(t.vox_cnt, t.vox_cnt + t.V);
       if (!segment_and_recognize(c->hp.p, t, fr.fc, c->inspect)) bad.store(1);
     }
@@ -622,6 +663,10 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     for (auto& t : th) t.join();
   }
   if (g_prof.on) g_prof.add("  host segment+recognize", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count());
+  c->stat_scans += nscans;
+  c->stat_points += total;
+  c->stat_apri += mbase[nscans];
+  c->stat_voxels += vbase[nscans];
   c->batches.push_back(std::move(pb));
   if (bad.load()) return fail(SCVOD_ERR_STATE, "internal: replayed cluster partition differs from the GPU components");
   return SCVOD_OK;
@@ -729,31 +774,32 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
     }
     cstart[cars.size()] = k;
     const size_t K = k;
+    c->stat_track_pairs += 1;
     if (K > 0 && vn > 0 && si > 0) {
+      c->stat_track_points += (int64_t)K;
       const int cap_quads = (int)std::min<size_t>((size_t)ncl * vn, (size_t)1 << 20);
       CU(c->d_treq.alloc(si * 4));
       CU(c->d_tout[out_buf].alloc(K));
-      CU(c->d_first.alloc((size_t)ncl * vn));
-      CU(c->d_triples.alloc(4 + 4 * (size_t)cap_quads));
-      CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));
+      {
+        const size_t need = (size_t)ncl * vn;
+        if (need > c->d_first.n) {  // (re)allocation: the table must start out "empty"; afterwards k_track_compact keeps it so
+          CU(c->d_first.alloc(need));
+          CU(cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream));
+        }
+      }
+      CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));  // pinned + device-accessible (UVA): the kernel writes the hits straight to the host
       PersistBatch& pbp = *c->batches[pre.batch];
       PersistBatch& pbn = *c->batches[next.batch];
       CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4), cudaMemcpyHostToDevice, c->stream));
       c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                   reinterpret_cast<const int4*>(c->d_treq.p), (int)si, (int)K, T,
                                   pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
-                                  vn, c->d_tout[out_buf].p, c->d_first.p, c->d_triples.p, cap_quads, c->stream);
+                                  vn, c->d_tout[out_buf].p, c->d_first.p, reinterpret_cast<int32_t*>(c->d_counter.p), c->h_triples.p, cap_quads,
+                                  c->stream);
       CU(cudaGetLastError());
-      const size_t first_chunk = std::min<size_t>(4 + 4 * (size_t)cap_quads, 4 + 4 * 4096);
-      CU(cudaMemcpyAsync(c->h_triples.p, c->d_triples.p, sizeof(int32_t) * first_chunk, cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       int nt = c->h_triples.p[0];
       if (nt > cap_quads) return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
-      if (4 + 4 * (size_t)nt > first_chunk) {
-        CU(cudaMemcpyAsync(c->h_triples.p + first_chunk, c->d_triples.p + first_chunk, sizeof(int32_t) * (4 + 4 * (size_t)nt - first_chunk),
-                           cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-      }
       for (int t = 0; t < nt; ++t) {
         const int32_t* q = c->h_triples.p + 4 + 4 * t;
         hits[q[0]].push_back(std::make_pair(((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3], q[1]));

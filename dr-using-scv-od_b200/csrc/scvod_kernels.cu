@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1100,7 +1101,9 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
                                                const int32_t* __restrict__ vox_pts, const float4* __restrict__ carried,
                                                const int4* __restrict__ segs, int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
-                                               float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first) {
+                                               float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
+                                               int32_t* __restrict__ out_count) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = 0;  // consumed by k_track_compact, which runs after this kernel
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
     int lo = 0, hi = nseg - 1;  // last segment with dst_off <= i
     while (lo < hi) {
@@ -1136,23 +1139,27 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
   }
 }
 
-// compaction of the (cluster, voxel) -> first-occurrence key table: out[0] = count, quads from out[4]
-__global__ void __launch_bounds__(256) k_track_compact(const unsigned long long* __restrict__ first, int ncl, int vn,
-                                                       int32_t* __restrict__ out, int cap_quads) {
+// compaction of the (cluster, voxel) -> first-occurrence key table into host-mapped pinned memory (quads from
+// out[4]; the count is published by the host-side copy of *count after the stream sync).  Every consumed entry is
+// reset to "empty", so the table needs no memset between frame pairs.
+__global__ void __launch_bounds__(256) k_track_compact(unsigned long long* __restrict__ first, int ncl, int vn,
+                                                       int32_t* __restrict__ count, int32_t* __restrict__ out, int cap_quads) {
   const int total = ncl * vn;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     unsigned long long f = first[e];
     if (f != ~0ull) {
-      int slot = atomicAdd(&out[0], 1);
+      first[e] = ~0ull;
+      int slot = atomicAdd(count, 1);
       if (slot < cap_quads) {
-        out[4 + 4 * slot] = e / vn;
-        out[4 + 4 * slot + 1] = e % vn;
-        out[4 + 4 * slot + 2] = (int)(unsigned)(f >> 32);
-        out[4 + 4 * slot + 3] = (int)(unsigned)(f & 0xffffffffu);
+        int4 q = make_int4(e / vn, e % vn, (int)(unsigned)(f >> 32), (int)(unsigned)(f & 0xffffffffu));
+        reinterpret_cast<int4*>(out + 4)[slot] = q;
       }
     }
   }
 }
+
+// publishes the quad count next to the quads (runs after k_track_compact)
+__global__ void k_track_publish(const int32_t* __restrict__ count, int32_t* __restrict__ out) { out[0] = *count; }
 
 // per-point classes of every frame of a batch from the per-voxel classes decided on the host
 __global__ void __launch_bounds__(256) k_final_labels(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
@@ -1204,6 +1211,12 @@ __global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, 
   }
 }
 
+// gather of the per-scan voxel tables into one packed buffer (one D2H instead of hundreds)
+__global__ void __launch_bounds__(256) k_pack(const PackDesc* __restrict__ descs, int32_t* __restrict__ out) {
+  const PackDesc d = descs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += gridDim.x * blockDim.x) out[d.dst + i] = d.src[i];
+}
+
 __global__ void k_atan2f_probe(const float* y, const float* x, float* out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = dev_atan2f(y[i], x[i]);
@@ -1223,6 +1236,7 @@ std::vector<double> g_ms;
 std::vector<long long> g_cnt;
 std::vector<TimedLaunch> g_pending;
 std::vector<cudaEvent_t> g_event_pool;
+std::mutex g_timing_mu;  // contexts on different host threads share the table
 
 cudaEvent_t get_event() {
   if (!g_event_pool.empty()) {
@@ -1248,15 +1262,19 @@ struct ScopedTimer {
   bool on;
   ScopedTimer(const char* name, cudaStream_t s) : st(s), on(g_timing) {
     if (on) {
-      t.name_id = name_id(name);
-      t.e0 = get_event();
-      t.e1 = get_event();
+      {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        t.name_id = name_id(name);
+        t.e0 = get_event();
+        t.e1 = get_event();
+      }
       cudaEventRecord(t.e0, st);
     }
   }
   ~ScopedTimer() {
     if (on) {
       cudaEventRecord(t.e1, st);
+      std::lock_guard<std::mutex> lk(g_timing_mu);
       g_pending.push_back(t);
     }
   }
@@ -1272,6 +1290,7 @@ void timing_reset() {
   for (auto& v : g_cnt) v = 0;
 }
 void timing_collect() {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   for (auto& t : g_pending) {
     cudaEventSynchronize(t.e1);
     float ms = 0;
@@ -1461,21 +1480,21 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
                  const int4* segs, int nseg, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
-                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* out_quads, int cap_quads, void* stream_) {
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* count_dev, int32_t* out_quads_mapped, int cap_quads,
+                 void* stream_) {
   if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
-  cudaMemsetAsync(first, 0xff, sizeof(unsigned long long) * (size_t)ncl * vn, st);
-  cudaMemsetAsync(out_quads, 0, sizeof(int32_t) * 4, st);
   Mat34 T;
   for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
   int blocks = (k + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first); }
+  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, count_dev); }
   int blocks2 = (ncl * vn + 255) / 256;
   if (blocks2 > cap) blocks2 = cap;
-  { TIMED("k_track_compact", TSTREAM); k_track_compact<<<blocks2, 256, 0, st>>>(first, ncl, vn, out_quads, cap_quads); }
-  return 2;
+  { TIMED("k_track_compact", TSTREAM); k_track_compact<<<blocks2, 256, 0, st>>>(first, ncl, vn, count_dev, out_quads_mapped, cap_quads); }
+  k_track_publish<<<1, 1, 0, st>>>(count_dev, out_quads_mapped);
+  return 3;
 }
 
 int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
@@ -1491,6 +1510,15 @@ int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, con
   if (nscans <= 0) return 0;
   dim3 grid(grid_x_for(nscans, max_scan_points, 256), nscans);
   { TIMED("k_submap", TSTREAM); k_submap<<<grid, 256, 0, (cudaStream_t)stream_>>>(pts, cls, off, Ts_dev, first_scan, out, counter, cap); }
+  return 1;
+}
+
+int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream_) {
+  if (ndesc <= 0) return 0;
+  int gx = (max_n + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  { TIMED("k_pack", TSTREAM); k_pack<<<dim3(gx, ndesc), 256, 0, (cudaStream_t)stream_>>>(descs_dev, out); }
   return 1;
 }
 

@@ -88,6 +88,8 @@ int scvod_num_kernel_launches(const scvod_ctx* ctx, int64_t* out); /* kernels la
 /* options: "inspect" (keep per-stage cluster names for scvod_frame_point_cluster; default 1),
  * "host_threads" (threads used for the per-scan cluster bookkeeping). */
 int scvod_set_option(scvod_ctx* ctx, const char* key, int value);
+/* cumulative work counters: "scans", "points", "apri_points", "voxels", "track_pairs", "track_points" */
+int scvod_get_stat(scvod_ctx* ctx, const char* key, int64_t* out);
 
 /* Run all work of this context on a caller-owned CUDA stream (e.g. torch's current stream). */
 int scvod_set_stream(scvod_ctx* ctx, void* cuda_stream);
