@@ -4,6 +4,16 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#ifdef SEG_PROF
+#include <chrono>
+#include <cstdio>
+static double g_tp[8];
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TP(i) do { double t__ = now_us(); g_tp[i] += t__ - tp_last; tp_last = t__; } while (0)
+extern "C" void seg_prof_dump() { for (int i = 0; i < 8; ++i) printf("phase %d: %.1f us\n", i, g_tp[i]); }
+#else
+#define TP(i)
+#endif
 
 namespace scvod {
 
@@ -111,28 +121,54 @@ inline bool name_in(const std::vector<int>& v, int n) { return std::find(v.begin
 }  // namespace
 
 bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClusters& out, bool keep_stages) {
+#ifdef SEG_PROF
+  double tp_last = now_us();
+#endif
   const int V = t.V;
   // ---- clusterAndCreateFrame (ssc.cpp:299-393) ---------------------------------------------------
   std::vector<int> vox_name;
-  const int last_name = replay_cluster_names(t, vox_name);
+  int last_name;
+  // cluster_pt is filled in point order, so its keys are inserted in order of each cluster's first point (:360-375)
+  std::unordered_map<int, int> cluster_pt;
+  if (t.vox_name) {  // names replayed on the device
+    vox_name.assign(t.vox_name, t.vox_name + V);
+    last_name = t.max_name;
+    std::vector<std::pair<int, int>> order;  // (first event, name)
+    for (int nm = 0; nm <= last_name; ++nm)
+      if (t.name_first[nm] != 0x7fffffff) order.push_back(std::make_pair(t.name_first[nm], nm));
+    std::sort(order.begin(), order.end());
+    for (auto& o : order) cluster_pt.insert(std::make_pair(o.second, 0));
+  } else {
+    last_name = replay_cluster_names(t, vox_name);
+    std::vector<char> seen(last_name + 2, 0);
+    for (int e = 0; e < t.n_events; ++e) {
+      int nm = vox_name[t.ev_cid[e]];
+      if (!seen[nm]) {
+        seen[nm] = 1;
+        cluster_pt.insert(std::make_pair(nm, 0));
+      }
+    }
+  }
+  TP(0);
   out.max_name = last_name;  // frame_ssc.max_name = cluster_name++ (:354)
   out.vox_label = vox_name;
   out.cluster_set.clear();
+  for (int v = 0; v < V; ++v)
+    if (vox_name[v] < 0 || vox_name[v] > last_name) return false;
 
-  // cluster_pt is filled in point order, so its keys are inserted in order of each cluster's first point (:360-375)
-  std::unordered_map<int, int> cluster_pt;
-  for (int e = 0; e < t.n_events; ++e) {
-    int nm = vox_name[t.ev_cid[e]];
-    if (cluster_pt.find(nm) == cluster_pt.end()) cluster_pt.insert(std::make_pair(nm, 0));
+  // voxels of every cluster in ascending compact id (== sorted voxel_idx): counting sort by name
+  std::vector<int> name_start(last_name + 3, 0), vox_sorted(V);
+  for (int v = 0; v < V; ++v) name_start[vox_name[v] + 1]++;
+  for (int nm = 0; nm <= last_name + 1; ++nm) name_start[nm + 1] += name_start[nm];
+  {
+    std::vector<int> cur(name_start.begin(), name_start.end() - 1);
+    for (int v = 0; v < V; ++v) vox_sorted[cur[vox_name[v]]++] = v;
   }
-  std::unordered_map<int, std::vector<int>> vox_of;  // helper only (order-free)
-  vox_of.reserve(cluster_pt.size() * 2);
-  for (int v = 0; v < V; ++v) vox_of[vox_name[v]].push_back(v);  // ascending compact id == sorted voxel_idx
-  std::unordered_map<int, std::vector<int>> roots_of;          // cluster name -> CVC component roots it contains
+  std::unordered_map<int, std::vector<int>> roots_of;  // cluster name -> CVC component roots it contains
   for (auto& c : cluster_pt) {  // (:377-385) same iteration order as the reference's cluster_pt
     HCluster cl;
     cl.name = c.first;
-    cl.occupy_voxels.swap(vox_of[c.first]);
+    cl.occupy_voxels.assign(vox_sorted.begin() + name_start[c.first], vox_sorted.begin() + name_start[c.first + 1]);
     cl.part_end.push_back((int)cl.occupy_voxels.size());
     int np = 0;
     for (int v : cl.occupy_voxels) np += t.vox_cnt[v];
@@ -144,17 +180,22 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   if (keep_stages) out.vox_name_stage[0] = vox_name;
   // the replayed name partition must coincide with the GPU's connected components
   {
-    std::unordered_map<int, int> root_name;
+    std::vector<int> root_name(V, -1);
+    int nroots = 0;
     for (int v = 0; v < V; ++v) {
-      auto it = root_name.find(t.vox_root[v]);
-      if (it == root_name.end())
-        root_name.insert(std::make_pair(t.vox_root[v], vox_name[v]));
-      else if (it->second != vox_name[v])
+      int r = t.vox_root[v];
+      if (r < 0 || r >= V) return false;
+      if (root_name[r] == -1) {
+        root_name[r] = vox_name[v];
+        ++nroots;
+      } else if (root_name[r] != vox_name[v]) {
         return false;
+      }
     }
-    if (root_name.size() != out.cluster_set.size()) return false;
+    if (nroots != (int)out.cluster_set.size()) return false;
   }
 
+  TP(1);
   // ---- refineClusterByIntensity (ssc.cpp:571-635) at component granularity -------------------------
   // E(K): components reached from component K by a voxel pair passing the similarity test (:588-594)
   std::unordered_map<int, std::vector<int>> comp_edges;
@@ -218,6 +259,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   out.n_clusters[1] = (int)out.cluster_set.size();
   if (keep_stages) out.vox_name_stage[1] = vox_label;
 
+  TP(2);
   // ---- refineClusterByBoundingBox (ssc.cpp:437-467) ------------------------------------------------
   std::vector<int> erase_id;
   for (auto& c : out.cluster_set) {
@@ -244,6 +286,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   out.n_clusters[2] = (int)out.cluster_set.size();
   if (keep_stages) out.vox_name_stage[2] = vox_label;
 
+  TP(3);
   // ---- recognize (ssc.cpp:834-895; features :723-751) ------------------------------------------------
   for (auto& c : out.cluster_set) {
     HCluster& cl = c.second;
@@ -259,6 +302,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
       cl.type = p.tree;
     }
   }
+  TP(4);
   return true;
 }
 

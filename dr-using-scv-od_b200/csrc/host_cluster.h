@@ -43,6 +43,10 @@ struct ScanTables {
   const float* vox_bbox = nullptr;    // [V][6]
   const int32_t* ev_cid = nullptr;    // [n_events]
   const int32_t* edges = nullptr;     // [n_edges][2] (root_from, root_to)
+  // cluster names replayed on the device (k_name_replay); when null the host replays them from ev_cid / vox_nbr
+  const int32_t* vox_name = nullptr;    // [V]
+  const int32_t* name_first = nullptr;  // [max_name + 1] first event of every name (0x7fffffff: name vanished)
+  int max_name = 0;
 };
 
 struct FrameClusters {

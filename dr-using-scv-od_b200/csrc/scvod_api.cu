@@ -191,6 +191,8 @@ struct scvod_ctx {
   DevBuf<int32_t> d_pack;
   PinBuf<PackDesc> h_desc;
   DevBuf<PackDesc> d_desc;
+  DevBuf<int32_t> d_vox_name, d_name_first;
+  int name_cap = 0;
   // tracking buffers: packed request (segments + own indices), ping-pong transformed clouds, hit table
   DevBuf<int32_t> d_treq, d_triples;
   DevBuf<unsigned long long> d_first;
@@ -332,6 +334,9 @@ static int alloc_workspace(scvod_ctx* c) {
   CU(c->d_edge_hash.alloc(S * w.hash_cap));
   CU(c->d_T.alloc(16));
   CU(c->d_counter.alloc(1));
+  c->name_cap = c->max_points + 8;
+  CU(c->d_vox_name.alloc(P));
+  CU(c->d_name_first.alloc(S * (size_t)c->name_cap));
   w.off = c->d_off.p;
   w.patch_of = c->d_patch_of.p;
   w.slot_patch = c->d_slot_patch.p;
@@ -409,7 +414,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->h_treq.release(); c->h_triples.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
   c->d_Ts.release(); c->h_Ts.release();
   c->d_counter.release();
-  c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release();
+  c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return SCVOD_OK;
@@ -576,48 +581,56 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   }
 
   std::chrono::steady_clock::time_point td0 = std::chrono::steady_clock::now();
-  // one packed gather + one D2H for all per-scan tables: [cnt Vt][root Vt][nbr 27Vt][bbox 6Vt][events Et][edges 2Gt]
-  const int64_t Vt = vbase[nscans], Et = ebase[nscans], Gt = gbase[nscans];
-  const int64_t o_cnt = 0, o_root = Vt, o_nbr = 2 * Vt, o_bbox = 29 * Vt, o_ev = 35 * Vt, o_edge = 35 * Vt + Et;
-  const int64_t pack_ints = std::max<int64_t>(1, 35 * Vt + Et + 2 * Gt);
+  // cluster names: one warp per scan replays the reference's sequential naming on the device
+  int max_vox = 1;
+  for (int s = 0; s < nscans; ++s) max_vox = std::max(max_vox, sc[s * 8 + 3]);
+  c->launches += launch_name_replay(w, nscans, max_vox, c->d_vox_name.p, c->d_name_first.p, c->name_cap, st);
+  CU(cudaGetLastError());
+  // one packed gather + one D2H for all per-scan tables: [cnt Vt][root Vt][name Vt][bbox 6Vt][name_first Nt][edges 2Gt][max_name S]
+  const int64_t Vt = vbase[nscans], Gt = gbase[nscans];
+  std::vector<int64_t> nbase(nscans + 1, 0);
+  for (int s = 0; s < nscans; ++s) nbase[s + 1] = nbase[s] + std::min<int64_t>(c->name_cap, (int64_t)sc[s * 8 + 3] + 6);
+  const int64_t Nt = nbase[nscans];
+  const int64_t o_cnt = 0, o_root = Vt, o_name = 2 * Vt, o_bbox = 3 * Vt, o_nf = 9 * Vt, o_edge = 9 * Vt + Nt, o_max = 9 * Vt + Nt + 2 * Gt;
+  const int64_t pack_ints = std::max<int64_t>(1, o_max + (int64_t)nscans * 8);
   CU(c->h_pack.alloc(pack_ints));
   CU(c->d_pack.alloc(pack_ints));
-  CU(c->h_desc.alloc((size_t)nscans * 6));
-  CU(c->d_desc.alloc((size_t)nscans * 6));
+  CU(c->h_desc.alloc((size_t)nscans * 6 + 1));
+  CU(c->d_desc.alloc((size_t)nscans * 6 + 1));
   int nd = 0, max_desc_n = 1;
+  auto add = [&](const void* src, int64_t dst, int n) {
+    if (n <= 0) return;
+    PackDesc d;
+    d.src = reinterpret_cast<const int32_t*>(src);
+    d.dst = dst;
+    d.n = n;
+    d.pad = 0;
+    c->h_desc.p[nd++] = d;
+    max_desc_n = std::max(max_desc_n, n);
+  };
   for (int s = 0; s < nscans; ++s) {
-    int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
+    int V = sc[s * 8 + 3], G = sc[s * 8 + 7];
     int64_t b = off[s];
-    auto add = [&](const void* src, int64_t dst, int n) {
-      if (n <= 0) return;
-      PackDesc d;
-      d.src = reinterpret_cast<const int32_t*>(src);
-      d.dst = dst;
-      d.n = n;
-      d.pad = 0;
-      c->h_desc.p[nd++] = d;
-      max_desc_n = std::max(max_desc_n, n);
-    };
     add(w.vox_cnt + b, o_cnt + vbase[s], V);
     add(w.vox_root + b, o_root + vbase[s], V);
-    add(w.vox_nbr + b * 27, o_nbr + vbase[s] * 27, V * 27);
+    add(c->d_vox_name.p + b, o_name + vbase[s], V);
     add(w.vox_bbox + b * 6, o_bbox + vbase[s] * 6, V * 6);
-    add(w.ev_cid + b, o_ev + ebase[s], E);
+    add(c->d_name_first.p + (size_t)s * c->name_cap, o_nf + nbase[s], (int)(nbase[s + 1] - nbase[s]));
     add(w.edge_buf + (size_t)s * w.edge_cap * 2, o_edge + gbase[s] * 2, G * 2);
   }
-  if (nd > 0) {
-    CU(cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, sizeof(PackDesc) * nd, cudaMemcpyHostToDevice, st));
-    c->launches += launch_pack(c->d_desc.p, nd, max_desc_n, c->d_pack.p, st);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_pack.p, c->d_pack.p, sizeof(int32_t) * pack_ints, cudaMemcpyDeviceToHost, st));
-  }
+  add(w.scan_counts, o_max, nscans * 8);  // re-read the counters: slot 6 now holds max_name
+  CU(cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, sizeof(PackDesc) * nd, cudaMemcpyHostToDevice, st));
+  c->launches += launch_pack(c->d_desc.p, nd, max_desc_n, c->d_pack.p, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_pack.p, c->d_pack.p, sizeof(int32_t) * pack_ints, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   const int32_t* hp_cnt = c->h_pack.p + o_cnt;
   const int32_t* hp_root = c->h_pack.p + o_root;
-  const int32_t* hp_nbr = c->h_pack.p + o_nbr;
+  const int32_t* hp_name = c->h_pack.p + o_name;
   const float* hp_bbox = reinterpret_cast<const float*>(c->h_pack.p + o_bbox);
-  const int32_t* hp_ev = c->h_pack.p + o_ev;
+  const int32_t* hp_nf = c->h_pack.p + o_nf;
   const int32_t* hp_edge = c->h_pack.p + o_edge;
+  const int32_t* hp_sc2 = c->h_pack.p + o_max;
   if (g_prof.on) g_prof.add("  d2h voxel tables", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td0).count());
   std::chrono::steady_clock::time_point th0 = std::chrono::steady_clock::now();
   // host cluster bookkeeping, one scan per task
@@ -646,10 +659,12 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
       t.n_edges = sc[s * 8 + 7];
       t.vox_cnt = hp_cnt + vbase[s];
       t.vox_root = hp_root + vbase[s];
-      t.vox_nbr = hp_nbr + vbase[s] * 27;
       t.vox_bbox = hp_bbox + vbase[s] * 6;
-      t.ev_cid = hp_ev + ebase[s];
       t.edges = hp_edge + gbase[s] * 2;
+      t.vox_name = hp_name + vbase[s];
+      t.name_first = hp_nf + nbase[s];
+      t.max_name = hp_sc2[s * 8 + 6];
+      if (t.max_name + 1 > (int)(nbase[s + 1] - nbase[s])) bad.store(1);
       fr.vox_cnt.assign(t.vox_cnt, t.vox_cnt + t.V);
       if (!segment_and_recognize(c->hp.p, t, fr.fc, c->inspect)) bad.store(1);
     }

@@ -104,6 +104,8 @@ int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nsca
                         const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream);
 int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,
                   int max_scan_points, float4* out, unsigned long long* counter, long long cap, void* stream);
+// cluster-name replay (one warp per scan); vox_name is indexed like the voxel arrays, name_first is [nscans][name_cap]
+int launch_name_replay(BatchDev& d, int nscans, int max_vox, int32_t* vox_name, int32_t* name_first, int name_cap, void* stream);
 int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
 

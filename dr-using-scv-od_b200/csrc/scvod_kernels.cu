@@ -1049,6 +1049,145 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster names of SSC::clusterAndCreateFrame (ssc.cpp:299-354) replayed on the device, one warp per scan.
+//
+// The reference walks the apri points in order and propagates names through the <=27 voxels around each
+// point (oc/nc rules of :323-351, mergeClusters :413-419 renames the current point's cluster to the
+// neighbour's), so names depend on the visiting sequence.  At voxel granularity (no index is -1):
+//   * a voxel is unlabelled / only its first point labelled / fully labelled, and its labelled points are in
+//     one set;  an unlabelled visitor skips unlabelled voxels until the first labelled one (position p),
+//     adopts that set, and from then on labels or merges everything it meets;
+//   * the union keeps the name of the LAST set met for the first time (every merge renames the current
+//     set to the neighbour's), i.e. of the highest lane whose root occurs for the first time;
+//   * after an event whose point was already labelled, or that skipped nothing, the voxel is "stable":
+//     all 27 neighbours share its set for good and later points of the voxel are no-ops.  Only the
+//     first three points of a voxel can find it unstable: those are the events (k_events).
+// One event = one warp step: lane k owns neighbour k (findVoxelNeighbors order), union-find with path
+// halving lives in shared memory, the order-dependent part is resolved with ballot / match_any.
+// ------------------------------------------------------------------------------------------------
+template <bool GLOBAL>
+__global__ void __launch_bounds__(32) k_name_replay(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
+                                                    const int32_t* __restrict__ ev_cid, const int32_t* __restrict__ vox_nbr,
+                                                    int32_t* __restrict__ g_parent, int32_t* __restrict__ g_setname,
+                                                    int32_t* __restrict__ g_first, int32_t* __restrict__ g_state,
+                                                    int32_t* __restrict__ vox_name, int32_t* __restrict__ name_first, int name_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  const int E = scan_counts[b * 8 + 5];
+  const int lane = threadIdx.x;
+  int32_t *parent, *setname, *first_ev;
+  uint8_t *state, *stable;
+  if (GLOBAL) {
+    parent = g_parent + base;
+    setname = g_setname + base;
+    first_ev = g_first + base;
+    state = reinterpret_cast<uint8_t*>(g_state + base);
+    stable = state + V;  // g_state has 4 bytes per voxel
+  } else {
+    parent = reinterpret_cast<int32_t*>(smem_raw);
+    setname = parent + V;
+    first_ev = setname + V;
+    state = reinterpret_cast<uint8_t*>(first_ev + V);
+    stable = state + V;
+  }
+  for (int v = lane; v < V; v += 32) {
+    parent[v] = v;
+    setname[v] = -1;
+    first_ev[v] = 0x7fffffff;
+    state[v] = 0;
+    stable[v] = 0;
+  }
+  __syncwarp();
+  auto find = [&](int v) {
+    int r = v;
+    while (true) {
+      int pr = parent[r];
+      if (pr == r) break;
+      int gp = parent[pr];
+      if (gp != pr) parent[r] = gp;
+      r = pr;
+    }
+    return r;
+  };
+  int cluster_name = 4;  // ssc.cpp:300
+  const int32_t* ev = ev_cid + base;
+  const int32_t* nbr = vox_nbr + 27 * base;
+  for (int e = 0; e < E; ++e) {
+    const int W = ev[e];
+    if (lane == 0 && first_ev[W] == 0x7fffffff) first_ev[W] = e;
+    if (stable[W]) continue;  // warp-uniform
+    const int Vn = (lane < 27) ? nbr[27 * (size_t)W + lane] : -1;
+    const bool exist = Vn >= 0;
+    const int st = exist ? state[Vn] : 0;
+    const bool lab = exist && st != 0;
+    const int r = lab ? find(Vn) : -1;
+    const bool labelled = (state[W] == 2);
+    const int oc0 = labelled ? find(W) : -1;
+    __syncwarp();
+    const unsigned lab_mask = __ballot_sync(0xffffffffu, lab);
+    const unsigned unl_mask = __ballot_sync(0xffffffffu, exist && !lab);
+    if (!labelled && lab_mask == 0u) {  // a new class (:345-351)
+      ++cluster_name;
+      if (lane == 0) {
+        parent[W] = W;
+        setname[W] = cluster_name;
+        state[W] = 2;
+        stable[W] = 1;
+      }
+      __syncwarp();
+      if (exist && Vn != W) {
+        parent[Vn] = W;
+        state[Vn] = 2;
+      }
+      __syncwarp();
+      continue;
+    }
+    // roots met for the first time, in visit order (a root equal to oc0 was "met" before the loop)
+    const unsigned same = __match_any_sync(0xffffffffu, lab ? r : (-2 - lane));
+    const bool first_occ = lab && (r != oc0) && ((same & ((1u << lane) - 1u)) == 0u);
+    const unsigned fo_mask = __ballot_sync(0xffffffffu, first_occ);
+    int f;  // surviving root: the last first-met set (mergeClusters renames oc to nc each time)
+    if (fo_mask) {
+      f = __shfl_sync(0xffffffffu, r, 31 - __clz(fo_mask));
+    } else {
+      f = oc0;
+    }
+    const int p = labelled ? -1 : (__ffs(lab_mask) - 1);  // position where the visitor becomes labelled
+    if (first_occ && r != f) parent[r] = f;
+    if (lane == 0 && labelled && oc0 != f) parent[oc0] = f;
+    __syncwarp();
+    if (lab) state[Vn] = 2;
+    const bool take = exist && !lab && lane > p;  // unlabelled voxels met after the visitor got its label (:338)
+    if (take) {
+      parent[Vn] = f;
+      state[Vn] = 2;
+    }
+    const unsigned skipped = unl_mask & ((p >= 0) ? ((1u << p) - 1u) : 0u);
+    __syncwarp();
+    if (lane == 0) {
+      if (state[W] == 0) {  // only this (first) point of W got the label
+        state[W] = 1;
+        parent[W] = f;
+      }
+      stable[W] = skipped ? 0 : 1;
+    }
+    __syncwarp();
+  }
+  // final names + first point (event) of every name, which fixes the insertion order of cluster_pt (:360-375)
+  int32_t* nf = name_first + (size_t)b * name_cap;
+  for (int i = lane; i <= cluster_name && i < name_cap; i += 32) nf[i] = 0x7fffffff;
+  __syncwarp();
+  for (int v = lane; v < V; v += 32) {
+    int nm = setname[find(v)];
+    vox_name[base + v] = nm;
+    if (nm >= 0 && nm < name_cap) atomicMin(&nf[nm], first_ev[v]);
+  }
+  if (lane == 0) scan_counts[b * 8 + 6] = cluster_name;
+}
+
 // ordered compaction of the apri points whose rank inside their voxel is < 3 ("clustering events")
 __global__ void __launch_bounds__(1024) k_events(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
                                                  const int32_t* __restrict__ apri_cid, const int32_t* __restrict__ apri_rank,
@@ -1510,6 +1649,22 @@ int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, con
   if (nscans <= 0) return 0;
   dim3 grid(grid_x_for(nscans, max_scan_points, 256), nscans);
   { TIMED("k_submap", TSTREAM); k_submap<<<grid, 256, 0, (cudaStream_t)stream_>>>(pts, cls, off, Ts_dev, first_scan, out, counter, cap); }
+  return 1;
+}
+
+int launch_name_replay(BatchDev& d, int nscans, int max_vox, int32_t* vox_name, int32_t* name_first, int name_cap, void* stream_) {
+  if (nscans <= 0) return 0;
+  const size_t smem = (size_t)max_vox * 14 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_name_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  if (smem <= 220 * 1024) {
+    { TIMED("k_name_replay", TSTREAM); k_name_replay<false><<<nscans, 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_nbr, nullptr, nullptr, nullptr, nullptr, vox_name, name_first, name_cap); }
+  } else {  // very dense scans: union-find state in (L2-resident) global scratch
+    { TIMED("k_name_replay_global", TSTREAM); k_name_replay<true><<<nscans, 32, 0, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_nbr, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, vox_name, name_first, name_cap); }
+  }
   return 1;
 }
 
