@@ -71,6 +71,8 @@ __constant__ int c_zone_ring0[4] = {0, 2, 6, 10};  // concentric_idx of the zone
 __constant__ double c_elev_thr[4] = {-1.2, -0.9984, -0.851, -0.605};
 __constant__ double c_flat_thr[4] = {0.0, 0.000125, 0.000185, 0.000185};
 
+constexpr int kTrackSegSmem = 8192;  // segments whose start offsets are staged in shared memory by k_track
+
 struct Mat34 {
   float m[12];
 };
@@ -1115,11 +1117,42 @@ __global__ void __launch_bounds__(32) k_name_replay(const int64_t* __restrict__ 
   int cluster_name = 4;  // ssc.cpp:300
   const int32_t* ev = ev_cid + base;
   const int32_t* nbr = vox_nbr + 27 * base;
+  // Neighbour rows are fetched kLook events ahead with cp.async into a small shared-memory ring, so the L2
+  // latency of a row hides behind the union-find work of the events in between.  A row is only requested
+  // when its voxel is not yet stable (stable never resets): the common no-op events never touch global memory.
+  constexpr int kLook = 8;
+  __shared__ int s_ring[kLook][32];
+  // events are read 32 at a time (one coalesced load per chunk); chA holds the chunk of event e, chB the next one
+  int chA = (lane < E) ? ev[lane] : 0;
+  int chB = (32 + lane < E) ? ev[32 + lane] : 0;
+  auto event_at = [&](int e2, int e_cur) {  // e2 is in the chunk of e_cur or in the next one
+    return ((e2 >> 5) == (e_cur >> 5)) ? __shfl_sync(0xffffffffu, chA, e2 & 31) : __shfl_sync(0xffffffffu, chB, e2 & 31);
+  };
+  auto issue = [&](int e2, int e_cur) {
+    if (e2 < E) {
+      const int W2 = event_at(e2, e_cur);
+      if (!stable[W2] && lane < 27) {
+        unsigned dst = (unsigned)__cvta_generic_to_shared(&s_ring[e2 % kLook][lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(nbr + 27 * (size_t)W2 + lane));
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  for (int e2 = 0; e2 < kLook; ++e2) issue(e2, 0);
   for (int e = 0; e < E; ++e) {
-    const int W = ev[e];
+    if (e > 0 && (e & 31) == 0) {
+      chA = chB;
+      chB = (e + 32 + lane < E) ? ev[e + 32 + lane] : 0;
+    }
+    const int W = __shfl_sync(0xffffffffu, chA, e & 31);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kLook - 1));
+    __syncwarp();
+    int Vn = (lane < 27) ? s_ring[e % kLook][lane] : -1;
+    const bool was_stable = stable[W];
+    __syncwarp();
+    issue(e + kLook, e);  // reuses the ring slot that was just read
     if (lane == 0 && first_ev[W] == 0x7fffffff) first_ev[W] = e;
-    if (stable[W]) continue;  // warp-uniform
-    const int Vn = (lane < 27) ? nbr[27 * (size_t)W + lane] : -1;
+    if (was_stable) continue;  // warp-uniform
     const bool exist = Vn >= 0;
     const int st = exist ? state[Vn] : 0;
     const bool lab = exist && st != 0;
@@ -1242,12 +1275,21 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
                                                float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
                                                int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = 0;  // consumed by k_track_compact, which runs after this kernel
+  // segment start offsets staged in shared memory: the per-point binary search then never leaves the SM
+  int* s_dst = reinterpret_cast<int*>(smem_raw);
+  const bool staged = nseg <= kTrackSegSmem;
+  if (staged) {
+    for (int t = threadIdx.x; t < nseg; t += blockDim.x) s_dst[t] = segs[t].x;
+    __syncthreads();
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
     int lo = 0, hi = nseg - 1;  // last segment with dst_off <= i
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
-      if (segs[mid].x <= i)
+      int d = staged ? s_dst[mid] : segs[mid].x;
+      if (d <= i)
         lo = mid;
       else
         hi = mid - 1;
@@ -1628,7 +1670,7 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   int blocks = (k + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, count_dev); }
+  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, (nseg <= kTrackSegSmem ? nseg : 0) * sizeof(int), st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, count_dev); }
   int blocks2 = (ncl * vn + 255) / 256;
   if (blocks2 > cap) blocks2 = cap;
   { TIMED("k_track_compact", TSTREAM); k_track_compact<<<blocks2, 256, 0, st>>>(first, ncl, vn, count_dev, out_quads_mapped, cap_quads); }
