@@ -35,6 +35,26 @@ class Params(ctypes.Structure):
     )
 
 
+class GicpParams(ctypes.Structure):
+    """scvod_gicp_params (docs/gicp_spec.md §1)."""
+
+    _fields_ = [("cov_radius", ctypes.c_float), ("max_corr_dist", ctypes.c_float), ("cov_eps", ctypes.c_float), ("planarity", ctypes.c_float),
+                ("min_neighbors", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("rot_eps", ctypes.c_float), ("trans_eps", ctypes.c_float)]
+
+
+class GicpResult(ctypes.Structure):
+    """scvod_gicp_result."""
+
+    _fields_ = [("T", ctypes.c_float * 12), ("pose6", ctypes.c_float * 6), ("H", ctypes.c_double * 36), ("b", ctypes.c_double * 6),
+                ("cost", ctypes.c_double), ("iterations", ctypes.c_int32), ("n_corr", ctypes.c_int32), ("converged", ctypes.c_int32),
+                ("n_src_valid", ctypes.c_int32), ("n_tgt_valid", ctypes.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {"T": np.array(self.T, np.float32).reshape(3, 4), "pose6": np.array(self.pose6, np.float32),
+                "H": np.array(self.H, np.float64).reshape(6, 6), "b": np.array(self.b, np.float64), "cost": float(self.cost),
+                "iterations": int(self.iterations), "n_corr": int(self.n_corr), "converged": bool(self.converged)}
+
+
 class Grid(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("range_num", "sector_num", "azimuth_num", "bin_num")]
 
@@ -46,6 +66,8 @@ EXPORTS = (
     "scvod_labels_range", "scvod_frame_counts", "scvod_frame_ground_order", "scvod_frame_apri", "scvod_frame_voxels",
     "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
     "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
+    "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
+    "scvod_gicp_normals", "scvod_pose_matrix",
 )
 
 _lib = None
@@ -64,6 +86,8 @@ def load_library() -> ctypes.CDLL:
         lib.scvod_relative_pose.restype = None
         lib.scvod_params_semantickitti.restype = None
         lib.scvod_params_parkinglot.restype = None
+        lib.scvod_gicp_default_params.restype = None
+        lib.scvod_pose_matrix.restype = None
         _lib = lib
     return _lib
 
@@ -115,6 +139,20 @@ def relative_pose(pose_next: np.ndarray, pose_pre: np.ndarray) -> np.ndarray:
     b = np.ascontiguousarray(pose_pre, np.float32)
     load_library().scvod_relative_pose(_ptr(a), _ptr(b), _ptr(T))
     return T.reshape(3, 4)
+
+
+def pose_matrix(pose6: np.ndarray) -> np.ndarray:
+    """pcl::getTransformation(x,y,z,roll,pitch,yaw) as a 3x4 float matrix (reference src/ssc.cpp:1255)."""
+    T = np.zeros(12, np.float32)
+    a = np.ascontiguousarray(pose6, np.float32)
+    load_library().scvod_pose_matrix(_ptr(a), _ptr(T))
+    return T.reshape(3, 4)
+
+
+def gicp_default_params() -> GicpParams:
+    p = GicpParams()
+    load_library().scvod_gicp_default_params(ctypes.byref(p))
+    return p
 
 
 def kernel_timing(enable: bool):
@@ -326,3 +364,34 @@ class SSC:
         n = ctypes.c_int64()
         _check(self._lib.scvod_static_submap_dev(self._ctx, f0, f1, _ptr(poses), ctypes.c_void_p(out_dev_ptr), ctypes.c_int64(cap_points), ctypes.byref(n)))
         return n.value
+
+    # -- GICP scan-to-map (docs/gicp_spec.md; the reference names the stage but has no code for it) --------
+    def gicp_set_target(self, cloud: np.ndarray, params: Optional[GicpParams] = None):
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+        _check(self._lib.scvod_gicp_set_target(self._ctx, _ptr(cloud), len(cloud), ctypes.byref(params) if params is not None else None))
+
+    def gicp_set_target_device(self, dev_ptr: int, n: int, params: Optional[GicpParams] = None):
+        _check(self._lib.scvod_gicp_set_target_dev(self._ctx, ctypes.c_void_p(dev_ptr), int(n), ctypes.byref(params) if params is not None else None))
+
+    def gicp_align(self, cloud: np.ndarray, T0: np.ndarray) -> dict:
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+        T0 = np.ascontiguousarray(T0, np.float32).reshape(12)
+        res = GicpResult()
+        _check(self._lib.scvod_gicp_align(self._ctx, _ptr(cloud), len(cloud), _ptr(T0), ctypes.byref(res)))
+        return res.as_dict()
+
+    def gicp_align_device(self, dev_ptr: int, n: int, T0: np.ndarray) -> dict:
+        T0 = np.ascontiguousarray(T0, np.float32).reshape(12)
+        res = GicpResult()
+        _check(self._lib.scvod_gicp_align_dev(self._ctx, ctypes.c_void_p(dev_ptr), int(n), _ptr(T0), ctypes.byref(res)))
+        return res.as_dict()
+
+    def gicp_normals(self, cloud: np.ndarray, params: Optional[GicpParams] = None):
+        """Radius-search kernel alone: (normals [n,3], valid [n], neighbour count [n]) in input order."""
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+        n = len(cloud)
+        nm = np.zeros((max(n, 1), 3), np.float32)
+        va = np.zeros(max(n, 1), np.uint8)
+        cn = np.zeros(max(n, 1), np.int32)
+        _check(self._lib.scvod_gicp_normals(self._ctx, _ptr(cloud), n, ctypes.byref(params) if params is not None else None, _ptr(nm), _ptr(va), _ptr(cn)))
+        return nm[:n], va[:n], cn[:n]

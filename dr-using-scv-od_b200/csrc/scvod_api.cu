@@ -212,7 +212,18 @@ struct scvod_ctx {
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
   int track_name = 0;  // SSC::name (ssc.h:49)
   int64_t stat_track_points = 0, stat_track_pairs = 0, stat_scans = 0, stat_points = 0, stat_apri = 0, stat_voxels = 0;
+  void* gicp = nullptr;  // GICP state (scvod_gicp.cu)
+  void (*gicp_free)(void*) = nullptr;
 };
+
+namespace scvod {
+void* ctx_stream(scvod_ctx* c) { return (void*)c->stream; }
+int ctx_device(const scvod_ctx* c) { return c->device; }
+void ctx_add_launches(scvod_ctx* c, int n) { c->launches += n; }
+void** ctx_gicp_slot(scvod_ctx* c) { return &c->gicp; }
+void ctx_set_gicp_free(scvod_ctx* c, void (*fn)(void*)) { c->gicp_free = fn; }
+int api_fail(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace scvod
 
 static void params_common(scvod_params* p) {
   // Utility() defaults (reference include/utility.h:283-313) for keys a YAML file may omit
@@ -299,6 +310,7 @@ extern "C" const char* scvod_last_error(void) { return g_err.c_str(); }
 extern "C" void scvod_relative_pose(const float pose_next6[6], const float pose_pre6[6], float T[12]) {
   relative_pose(pose_next6, pose_pre6, T);
 }
+extern "C" void scvod_pose_matrix(const float pose6[6], float T[12]) { pose_matrix(pose6, T); }
 
 static int alloc_workspace(scvod_ctx* c) {
   const size_t P = (size_t)c->max_points * c->max_batch;  // total points per batch
@@ -400,6 +412,8 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   g_prof.dump();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->gicp && c->gicp_free) c->gicp_free(c->gicp);
+  c->gicp = nullptr;
   for (auto& b : c->batches)
     if (b) b->release();
   for (auto& b : c->batch_pool)

@@ -109,6 +109,24 @@ int launch_name_replay(BatchDev& d, int nscans, int max_vox, int32_t* vox_name, 
 int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
 
+// context accessors for the translation units that do not see struct scvod_ctx (scvod_gicp.cu)
+void* ctx_stream(scvod_ctx* c);
+int ctx_device(const scvod_ctx* c);
+void ctx_add_launches(scvod_ctx* c, int n);
+void** ctx_gicp_slot(scvod_ctx* c);                          // opaque GICP state owned by scvod_gicp.cu
+void ctx_set_gicp_free(scvod_ctx* c, void (*fn)(void*));     // called by scvod_destroy
+int api_fail(int code, const std::string& msg);               // sets scvod_last_error()
+
+// RAII CUDA-event timer around a kernel launch (active only while scvod_kernel_timing is enabled)
+struct LaunchTimer {
+  void* st;
+  int id;
+  void *e0, *e1;
+  bool on;
+  LaunchTimer(const char* name, void* stream);
+  ~LaunchTimer();
+};
+
 // per-kernel CUDA-event timing (process-wide; used by bench.py for the roofline block)
 void timing_enable(bool on);
 void timing_collect();

@@ -1462,6 +1462,29 @@ struct ScopedTimer {
 };
 }  // namespace
 #define TIMED(name, st) ScopedTimer timer__(name, st)
+
+LaunchTimer::LaunchTimer(const char* name, void* stream) : st(stream), id(0), e0(nullptr), e1(nullptr), on(g_timing) {
+  if (on) {
+    {
+      std::lock_guard<std::mutex> lk(g_timing_mu);
+      id = name_id(name);
+      e0 = (void*)get_event();
+      e1 = (void*)get_event();
+    }
+    cudaEventRecord((cudaEvent_t)e0, (cudaStream_t)st);
+  }
+}
+LaunchTimer::~LaunchTimer() {
+  if (on) {
+    cudaEventRecord((cudaEvent_t)e1, (cudaStream_t)st);
+    TimedLaunch t;
+    t.name_id = id;
+    t.e0 = (cudaEvent_t)e0;
+    t.e1 = (cudaEvent_t)e1;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_pending.push_back(t);
+  }
+}
 #define TSTREAM ((cudaStream_t)stream_)
 
 void timing_enable(bool on) { g_timing = on; }

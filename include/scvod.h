@@ -163,6 +163,44 @@ int scvod_frame_clusters(scvod_ctx* ctx, int frame, int cap, int32_t* name, int3
 int scvod_static_submap_dev(scvod_ctx* ctx, int f0, int f1, const float* poses6, void* out_xyzi_dev,
                             int64_t cap_points, int64_t* n_points);
 
+/* ---- GICP scan-to-map stage ------------------------------------------------------------------ */
+/* The reference names this stage but holds no code for it: src/gicp.cpp:1-57 is a PCD merge tool,
+ * src/ssc.cpp:1458,1467 are commented-out "TODO: gicp" lines.  Definition: docs/gicp_spec.md
+ * (plane-to-plane Generalized-ICP, Gauss-Newton, fixed-radius neighbourhoods in a uniform grid). */
+typedef struct scvod_gicp_params {
+  float cov_radius;     /* r: neighbourhood radius of the per-point covariance (m)      */
+  float max_corr_dist;  /* d_max: correspondence gate (m)                               */
+  float cov_eps;        /* epsilon of the (1,1,eps) covariance regularisation           */
+  float planarity;      /* a point is usable iff lambda2 <= planarity * lambda1          */
+  int32_t min_neighbors;
+  int32_t max_iter;
+  float rot_eps, trans_eps; /* convergence thresholds on |omega| (rad) and |v| (m)      */
+} scvod_gicp_params;
+
+typedef struct scvod_gicp_result {
+  float T[12];     /* source -> target, row-major 3x4                                           */
+  float pose6[6];  /* {x,y,z,roll,pitch,yaw}: Utility::rotationMatrixToEulerAngles convention   */
+                   /* (utility.h:488-505), i.e. pcl::getTransformation(pose6) == T              */
+  double H[36];    /* normal equations of the last evaluated iteration                          */
+  double b[6];
+  double cost;
+  int32_t iterations, n_corr, converged, n_src_valid, n_tgt_valid;
+} scvod_gicp_result;
+
+void scvod_gicp_default_params(scvod_gicp_params* p);
+/* Target (map) side: grid + per-point normals, kept on the device until replaced. */
+int scvod_gicp_set_target(scvod_ctx* ctx, const float* tgt_xyzi, int n, const scvod_gicp_params* p);
+int scvod_gicp_set_target_dev(scvod_ctx* ctx, const void* tgt_xyzi_dev, int n, const scvod_gicp_params* p);
+/* Align one source scan to the current target starting from T0 (12 floats, row-major 3x4). */
+int scvod_gicp_align(scvod_ctx* ctx, const float* src_xyzi, int n, const float T0[12], scvod_gicp_result* out);
+int scvod_gicp_align_dev(scvod_ctx* ctx, const void* src_xyzi_dev, int n, const float T0[12], scvod_gicp_result* out);
+/* The radius-search kernel alone (docs/gicp_spec.md section 3): unit normal, validity and neighbour
+ * count of every point of one cloud, in input order.  Any output may be NULL. */
+int scvod_gicp_normals(scvod_ctx* ctx, const float* xyzi, int n, const scvod_gicp_params* p, float* normals3,
+                       uint8_t* valid, int32_t* count);
+/* pcl::getTransformation(x,y,z,roll,pitch,yaw) as 12 floats (the matrix SSC::tracking builds, ssc.cpp:1255). */
+void scvod_pose_matrix(const float pose6[6], float T[12]);
+
 /* Per-patch plane fits of the most recent ground pass of batch slot `slot`: 504 rows of 12 floats
  * {normal[3], mean[3], singular values[3], d, decision, npts}; rows of skipped patches are stale. */
 int scvod_last_patch_records(scvod_ctx* ctx, int slot, float* rec504x12);

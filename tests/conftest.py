@@ -167,6 +167,25 @@ class Oracle:
         self.lib.orc_svd3(_ptr(A), _ptr(U), _ptr(sv))
         return U.reshape(3, 3), sv
 
+    # GICP (oracle/gicp_oracle.cpp; docs/gicp_spec.md)
+    def gicp_normals(self, xyzi, gparams):
+        xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = len(xyzi)
+        nm = np.zeros((max(n, 1), 3), np.float32)
+        va = np.zeros(max(n, 1), np.uint8)
+        cn = np.zeros(max(n, 1), np.int32)
+        self.lib.orc_gicp_normals(_ptr(xyzi), n, ctypes.byref(gparams), _ptr(nm), _ptr(va), _ptr(cn))
+        return nm[:n], va[:n], cn[:n]
+
+    def gicp_align(self, src, tgt, T0, gparams):
+        pkg = load_package()
+        src = np.ascontiguousarray(src, np.float32).reshape(-1, 4)
+        tgt = np.ascontiguousarray(tgt, np.float32).reshape(-1, 4)
+        T0 = np.ascontiguousarray(T0, np.float32).reshape(12)
+        res = pkg.GicpResult()
+        self.lib.orc_gicp_align(_ptr(src), len(src), _ptr(tgt), len(tgt), _ptr(T0), ctypes.byref(gparams), ctypes.byref(res))
+        return res.as_dict()
+
     def run_sequence(self, scans, poses, nthreads=1, want_labels=True):
         off = np.zeros(len(scans) + 1, np.int64)
         off[1:] = np.cumsum([len(s) for s in scans])
