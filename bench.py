@@ -222,8 +222,8 @@ def main():
             self.submap_free.set()
 
     workers = [Worker(w) for w in range(W)]
-    gathered = torch.empty((world * max_pts, 4), dtype=torch.float32, device=dev) if world > 1 else None
-    counts_all = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
+    par = entry._load_parallel()
+    gatherer = par.SubmapGatherer(max_pts, dev) if world > 1 else None  # one NCCL all-gather of the static submaps per step
 
     def step(wk, i, host_io):
         b = batches[i % len(batches)]
@@ -276,9 +276,7 @@ def main():
                     if errors:
                         return
                     wk, n_static = done.pop(i)
-                mine = torch.tensor([n_static], dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(counts_all, mine)
-                dist.all_gather_into_tensor(gathered, wk.submap)
+                gatherer.gather(wk.submap, n_static)
                 torch.cuda.current_stream().synchronize()
                 wk.submap_free.set()
 
@@ -316,10 +314,7 @@ def main():
         if with_kernel_timing:
             pkg.kernel_timing(False)
         secs = max(ev, wall)  # every step ends with host-side bookkeeping, so wall >= device time
-        t = torch.tensor([secs], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), sum(wk.ssc.kernel_launches for wk in workers) - l0, clocks, rep
+        return par.max_over_ranks(secs, dev), sum(wk.ssc.kernel_launches for wk in workers) - l0, clocks, rep
 
     secs_dev, launches, clocks, _ = timed(False, False)
     secs_e2e, _, clocks_e2e, _ = timed(True, False)

@@ -1,0 +1,100 @@
+"""Multi-GPU plumbing of the SCV-OD path: scan sharding and the static-submap merge.
+
+The path shards embarrassingly: per-scan stages are independent per scan and the tracking
+diff is a chain *inside* a sequence, so whole sequence chunks are dealt to ranks (one process per GPU,
+``torch.distributed``) and no data-path collective exists until the per-GPU static submaps are merged — the
+reference's ``*instance_map += *rgb_ptr`` (src/ssc.cpp:553-555: plain concatenation, no dedup) becomes ONE
+all-gather of the map-frame static points per step.  Nothing here computes on points: the submap tensor is
+written by ``k_submap`` (scvod_static_submap_dev) straight into the send buffer.
+
+Works with the ``nccl`` backend (CUDA tensors, NVLink/NVSwitch) and with ``gloo`` (CPU tensors; used by the
+world_size-2 tests that run without a GPU).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Block partition of ``n_items`` consecutive items: rank g owns [g*n/world, (g+1)*n/world)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    return (rank * n_items) // world, ((rank + 1) * n_items) // world
+
+
+def chunk_sequence(n_scans: int, chunk: int) -> List[Tuple[int, int]]:
+    """Cuts a sequence of n_scans frames into chunks of at most ``chunk`` consecutive frames.
+
+    The tracking chain runs inside a chunk; at a cut the first frame of the next chunk is tracked only against its
+    own successor (documented deviation from one unbroken chain)."""
+    if chunk <= 0:
+        raise ValueError("chunk must be positive")
+    return [(s, min(n_scans, s + chunk)) for s in range(0, n_scans, chunk)]
+
+
+def shard_chunks(n_scans: int, chunk: int, world: int, rank: int) -> List[Tuple[int, int]]:
+    """The chunks of a sequence owned by ``rank``: consecutive chunks stay on one GPU (block partition)."""
+    chunks = chunk_sequence(n_scans, chunk)
+    lo, hi = shard_range(len(chunks), world, rank)
+    return chunks[lo:hi]
+
+
+class SubmapGatherer:
+    """All-gather of variable-length per-rank static submaps ([n_r, 4] float32 xyzi in the map frame).
+
+    One count exchange + one padded ``all_gather_into_tensor`` per call; buffers are allocated once for
+    ``cap_points`` per rank.  ``gather`` returns (merged buffer [world*cap, 4], counts [world]); rank r's points
+    are ``merged[r*cap : r*cap + counts[r]]`` — ``compact`` concatenates them in rank order, which is the
+    reference's concatenation order when ranks own consecutive chunks.
+    """
+
+    def __init__(self, cap_points: int, device: torch.device, group=None):
+        self.cap = int(cap_points)
+        self.device = device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.merged = torch.empty((self.world * self.cap, 4), dtype=torch.float32, device=device)
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self._mine = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def gather(self, submap: torch.Tensor, n_points: int):
+        if submap.shape[0] < self.cap or submap.shape[1] != 4 or submap.dtype != torch.float32:
+            raise ValueError("submap must be a [>=cap, 4] float32 tensor")
+        if n_points > self.cap:
+            raise ValueError("submap holds more points than the gather capacity")
+        self._mine.fill_(int(n_points))
+        if self.world == 1:
+            self.counts.copy_(self._mine)
+            self.merged[: self.cap].copy_(submap[: self.cap])
+            return self.merged, self.counts
+        dist.all_gather_into_tensor(self.counts, self._mine, group=self.group)
+        dist.all_gather_into_tensor(self.merged, submap[: self.cap].contiguous(), group=self.group)
+        return self.merged, self.counts
+
+    def compact(self) -> torch.Tensor:
+        """Concatenation of every rank's valid points, in rank order."""
+        counts = [int(c) for c in self.counts.tolist()]
+        return torch.cat([self.merged[r * self.cap: r * self.cap + counts[r]] for r in range(self.world)], dim=0)
+
+
+def max_over_ranks(seconds: float, device: torch.device, group=None) -> float:
+    """Timing rule of the bench: a multi-GPU number is the MAX over ranks."""
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def merge_labels_host(per_rank_labels: Sequence[Sequence], order: Sequence[Tuple[int, int, int]]):
+    """Re-assembles per-frame label arrays computed on different ranks into sequence order.
+
+    ``order`` lists (rank, local_index, global_frame) triples; returns a list indexed by global frame."""
+    n = max(g for _, _, g in order) + 1 if order else 0
+    out = [None] * n
+    for r, i, g in order:
+        out[g] = per_rank_labels[r][i]
+    return out
