@@ -183,6 +183,7 @@ struct scvod_ctx {
   DevBuf<int32_t> d_patch_cnt, d_patch_off, d_patch_cur, d_sorted_idx, d_slot_pos, d_slot_apos, d_slot_vid, d_patch_out,
       d_patch_out_off, d_scan_counts, d_apri_rank, d_vox_cur, d_vox_pts_tmp, d_vox_nbr, d_vox_root, d_ev_cid, d_edge_buf;
   DevBuf<uint64_t> d_bucket_kv, d_edge_hash;
+  DevBuf<float4> d_sorted_xyz;
   DevBuf<float> d_patch_dbg, d_vox_bbox, d_T;
   // pinned host mirrors of what the host logic reads per batch
   PinBuf<int32_t> h_scan_counts, h_vox_cnt, h_vox_root, h_vox_nbr, h_ev_cid, h_edge_buf;
@@ -327,11 +328,12 @@ static int alloc_workspace(scvod_ctx* c) {
   CU(c->d_patch_off.alloc(S * (kNumPatches + 1)));
   CU(c->d_patch_cur.alloc(S * kNumPatches));
   CU(c->d_bucket_kv.alloc(P));
+  CU(c->d_sorted_xyz.alloc(P));
   CU(c->d_sorted_idx.alloc(P));
   CU(c->d_slot_pos.alloc(P));
   CU(c->d_slot_apos.alloc(P));
   CU(c->d_slot_vid.alloc(P));
-  CU(c->d_patch_out.alloc(S * kNumPatches * 4));
+  CU(c->d_patch_out.alloc(S * kNumPatches * 8));
   CU(c->d_patch_out_off.alloc(S * (kNumPatches + 1) * 3));
   CU(c->d_patch_dbg.alloc(S * kNumPatches * 12));
   CU(c->d_scan_counts.alloc(S * 8 + 8));
@@ -356,6 +358,7 @@ static int alloc_workspace(scvod_ctx* c) {
   w.patch_off = c->d_patch_off.p;
   w.patch_cur = c->d_patch_cur.p;
   w.bucket_kv = c->d_bucket_kv.p;
+  w.sorted_xyz = c->d_sorted_xyz.p;
   w.sorted_idx = c->d_sorted_idx.p;
   w.slot_pos = c->d_slot_pos.p;
   w.slot_apos = c->d_slot_apos.p;
@@ -422,7 +425,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_patch_cur.release(); c->d_sorted_idx.release(); c->d_slot_pos.release(); c->d_slot_apos.release(); c->d_slot_vid.release();
   c->d_patch_out.release(); c->d_patch_out_off.release(); c->d_scan_counts.release(); c->d_apri_rank.release(); c->d_vox_cur.release();
   c->d_vox_pts_tmp.release(); c->d_vox_nbr.release(); c->d_vox_root.release(); c->d_ev_cid.release(); c->d_edge_buf.release();
-  c->d_bucket_kv.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
+  c->d_bucket_kv.release(); c->d_sorted_xyz.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
   c->h_scan_counts.release(); c->h_vox_cnt.release(); c->h_vox_root.release(); c->h_vox_nbr.release(); c->h_ev_cid.release();
   c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_treq.release(); c->d_first.release(); c->d_triples.release();
   c->h_treq.release(); c->h_triples.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();

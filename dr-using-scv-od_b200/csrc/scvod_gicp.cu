@@ -36,6 +36,7 @@ namespace {
 struct GGrid {
   float ox, oy, oz, h;
   int nx, ny, nz, ncells;
+  int rings;  // ceil(max_corr_dist / h): cell rings a correspondence search may have to visit (spec §2)
 };
 
 constexpr int kWarpsPerCta = 8;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_gicp_normals(const float4
           for (int t = 0; t < m; ++t) {
             const float4 cnd = tile[t];
             const float d0 = cnd.x - q.x, d1 = cnd.y - q.y, d2 = cnd.z - q.z;
-            const float dd = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            const float dd = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
             if (dd <= r2) {
               ++k;
               s1x += d0; s1y += d1; s1z += d2;
@@ -415,38 +416,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_gicp_corr(const float4* _
     const int cz = c % g.nz, cy = (c / g.nz) % g.ny, cx = c / (g.nz * g.ny);
     float best = 3.0e38f;
     int best_pos = -1, best_idx = 0x7fffffff;
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int x = cx + dx;
-      if (x < 0 || x >= g.nx) continue;
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int y = cy + dy;
-        if (y < 0 || y >= g.ny) continue;
-        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.nz - 1);
-        const int lo = tgt_start[(x * g.ny + y) * g.nz + z0], hi = tgt_start[(x * g.ny + y) * g.nz + z1 + 1];
-        for (int base = lo; base < hi; base += kTile) {
-          const int m = min(kTile, hi - base);
-          for (int t = lane; t < m; t += 32) {
-            float4 cnd = __ldg(&tgt_sorted[base + t]);
-            // an invalid target point can never be a correspondence: poison its coordinates once, at staging time
-            if (__ldg(&tgt_normal[base + t]).w == 0.f) cnd.x = 3.0e18f;
-            tile[t] = cnd;
-          }
-          __syncwarp();
-#pragma unroll 4
-          for (int t = 0; t < m; ++t) {
-            const float4 cnd = tile[t];
-            const float d0 = q.x - cnd.x, d1 = q.y - cnd.y, d2 = q.z - cnd.z;
-            const float dd = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
-            const int idx = __float_as_int(cnd.w);
-            if (dd < best || (dd == best && idx < best_idx)) {
-              best = dd;
-              best_pos = base + t;
-              best_idx = idx;
-            }
-          }
-          __syncwarp();
+    // one contiguous run of cells (x, y, z0..z1) streamed through the warp's tile
+    auto scan_run = [&](int x, int y, int z0, int z1) {
+      z0 = max(z0, 0);
+      z1 = min(z1, g.nz - 1);
+      if (x < 0 || x >= g.nx || y < 0 || y >= g.ny || z0 > z1) return;
+      const int lo = tgt_start[(x * g.ny + y) * g.nz + z0], hi = tgt_start[(x * g.ny + y) * g.nz + z1 + 1];
+      for (int base = lo; base < hi; base += kTile) {
+        const int m = min(kTile, hi - base);
+        for (int t = lane; t < m; t += 32) {
+          float4 cnd = __ldg(&tgt_sorted[base + t]);
+          // an invalid target point can never be a correspondence: poison its coordinates once, at staging time
+          if (__ldg(&tgt_normal[base + t]).w == 0.f) cnd.x = 3.0e18f;
+          tile[t] = cnd;
         }
+        __syncwarp();
+#pragma unroll 4
+        for (int t = 0; t < m; ++t) {
+          const float4 cnd = tile[t];
+          const float d0 = q.x - cnd.x, d1 = q.y - cnd.y, d2 = q.z - cnd.z;
+          const float dd = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+          const int idx = __float_as_int(cnd.w);
+          if (dd < best || (dd == best && idx < best_idx)) {
+            best = dd;
+            best_pos = base + t;
+            best_idx = idx;
+          }
+        }
+        __syncwarp();
       }
+    };
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy) scan_run(cx + dx, cy + dy, cz - 1, cz + 1);
+    // Every unvisited point is at least one cell edge away from every query of this cell, so the first ring is final
+    // for a query whose best distance is already <= h; only groups with a worse query look further (rare once the
+    // alignment has started to converge).
+    const int K = g.rings;
+    if (K > 1 && __any_sync(0xffffffffu, active && best > g.h * g.h)) {
+      for (int dx = -K; dx <= K; ++dx)
+        for (int dy = -K; dy <= K; ++dy) {
+          if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
+            scan_run(cx + dx, cy + dy, cz - K, cz - 2);
+            scan_run(cx + dx, cy + dy, cz + 2, cz + K);
+          } else {
+            scan_run(cx + dx, cy + dy, cz - K, cz + K);
+          }
+        }
     }
     // per-correspondence terms in double (once per query and iteration: negligible next to the search)
     double v[kNumAcc];
@@ -614,16 +629,18 @@ int build_cloud(scvod_ctx* c, GicpState& S, GCloud& cl, int n, const scvod_gicp_
     hi[a] = n > 0 ? ord2f(S.h_box[3 + a]) : 0.f;
     if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return api_fail(SCVOD_ERR_ARG, "GICP cloud holds non-finite coordinates");
   }
-  float h = std::max(P.cov_radius, P.max_corr_dist);
+  float h = P.cov_radius;
   GGrid g;
-  for (;;) {
+  for (;;) {  // spec §2: cell edge = cov_radius (doubled while the grid is too large), margin = `rings` empty layers
     g.h = h;
-    g.ox = lo[0] - h;
-    g.oy = lo[1] - h;
-    g.oz = lo[2] - h;
-    g.nx = (int)floorf((hi[0] - g.ox) / h) + 2;
-    g.ny = (int)floorf((hi[1] - g.oy) / h) + 2;
-    g.nz = (int)floorf((hi[2] - g.oz) / h) + 2;
+    g.rings = std::max(1, (int)std::ceil(P.max_corr_dist / h));
+    const float margin = (float)g.rings * h;
+    g.ox = lo[0] - margin;
+    g.oy = lo[1] - margin;
+    g.oz = lo[2] - margin;
+    g.nx = (int)floorf((hi[0] - g.ox) / h) + 1 + g.rings;
+    g.ny = (int)floorf((hi[1] - g.oy) / h) + 1 + g.rings;
+    g.nz = (int)floorf((hi[2] - g.oz) / h) + 1 + g.rings;
     if ((double)g.nx * g.ny * g.nz <= (double)kMaxCells) break;
     h = h * 2.f;
   }
@@ -652,7 +669,7 @@ int build_cloud(scvod_ctx* c, GicpState& S, GCloud& cl, int n, const scvod_gicp_
     { GT("k_gicp_fill_tmp"); k_gicp_fill_tmp<<<gb, 256, 0, st>>>(n, cl.cell_of.p, cl.slot_in_cell.p, cl.start.p, cl.tmp.p); }
     { GT("k_gicp_place_ranked"); k_gicp_place_ranked<<<gb, 256, 0, st>>>(cl.pts.p, n, cl.cell_of.p, cl.start.p, cl.tmp.p, cl.sorted.p, cl.sorted_cell.p, cl.groups.p, S.counters.p); }
     const float r2 = P.cov_radius * P.cov_radius;
-    { GT("k_gicp_normals"); k_gicp_normals<<<S.sms * 2, kWarpsPerCta * 32, 0, st>>>(cl.sorted.p, cl.sorted_cell.p, cl.start.p, cl.groups.p, S.counters.p, g, r2,
+    { GT("k_gicp_normals"); k_gicp_normals<<<S.sms * 4, kWarpsPerCta * 32, 0, st>>>(cl.sorted.p, cl.sorted_cell.p, cl.start.p, cl.groups.p, S.counters.p, g, r2,
                                                                                    P.min_neighbors, P.planarity, cl.normal.p, cl.count.p); }
     ctx_add_launches(c, 3);
   }
@@ -773,7 +790,7 @@ int align_impl(scvod_ctx* c, const void* xyzi, int n, const float T0[12], scvod_
     rc = run_scan(c, S, S.q_cnt.p, tg.ncells, S.q_start.p, S.q_block_sum, st);
     if (rc) return rc;
     { GT("k_gicp_src_place"); k_gicp_src_place<<<gb, 256, 0, st>>>(S.moved.p, n, S.q_cell_of.p, S.q_slot.p, S.q_start.p, S.q_sorted.p, S.q_cell.p, S.q_groups.p, S.counters.p); }
-    { GT("k_gicp_corr"); k_gicp_corr<<<S.sms * 2, kWarpsPerCta * 32, 0, st>>>(S.q_sorted.p, S.q_cell.p, S.q_start.p, S.q_groups.p, S.counters.p, S.src.normal.p, S.tgt.sorted.p,
+    { GT("k_gicp_corr"); k_gicp_corr<<<S.sms * 4, kWarpsPerCta * 32, 0, st>>>(S.q_sorted.p, S.q_cell.p, S.q_start.p, S.q_groups.p, S.counters.p, S.src.normal.p, S.tgt.sorted.p,
                                                                              S.tgt.normal.p, S.tgt.start.p, tg, T, dmax2, k1, S.acc.p); }
     ctx_add_launches(c, 3);
     GCU(cudaGetLastError());

@@ -13,7 +13,6 @@ namespace scvod {
 constexpr int kNumZones = 4;
 constexpr int kNumPatches = 504;  // 2*16 + 4*32 + 4*54 + 4*32
 constexpr int kMinPatchPts = 10;  // num_min_pts_: patches need > 10 points (patchwork.h:331)
-constexpr int kFitLarge = 9400;    // points per patch of the largest shared-memory fit tile (24 B/pt)
 
 struct GridSpec {
   int range_num, sector_num, azimuth_num, bin_num;
@@ -36,12 +35,13 @@ struct BatchDev {
   int32_t* patch_off = nullptr;    // [scans][505] exclusive (relative to scan base)
   int32_t* patch_cur = nullptr;    // [scans][504] scatter cursors
   uint64_t* bucket_kv = nullptr;   // per bucket slot: (zkey<<32 | local idx)
+  float4* sorted_xyz = nullptr;    // per bucket slot: the point, z-sorted inside its patch (k_patch_sort -> chain / rank)
   int32_t* sorted_idx = nullptr;   // per bucket slot after sort: local point idx
   int32_t* slot_pos = nullptr;     // per bucket slot: role<<30 | local position in ground / nonground list
   int32_t* slot_apos = nullptr;    // per bucket slot: local position in apri list or -1
   int32_t* slot_vid = nullptr;     // per bucket slot: voxel_idx (apri points)
   int16_t* slot_patch = nullptr;   // per bucket slot: patch id
-  int32_t* patch_out = nullptr;    // [scans][504][4]: n_ground, n_nonground, n_apri, quirk count
+  int32_t* patch_out = nullptr;    // [scans][504][8]: n_ground, n_nonground, n_apri, quirk count, |ground set|, its gate-passing part, rejected
   int32_t* patch_out_off = nullptr;  // [scans][505][3] exclusive offsets
   float* patch_dbg = nullptr;      // [scans][504][12] normal, mean, sv, d, decision, npts (debug/inspection)
   int32_t* scan_counts = nullptr;  // [scans][8]: n_ground, n_ng, n_apri, n_voxels, n_quirk, n_events, n_comp, n_edges

@@ -308,13 +308,16 @@ __device__ void dev_svd3(const float A[3][3], float U[3][3], float sv[3]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// G4: one CTA per (patch, scan): z-sort of the patch in shared memory, seed selection, three
-// sequential-order plane fits (R-GPF), gating, ordered ranks of ground / nonground / apri points and
-// the curved-voxel index of every surviving nonground point.
-//   patchwork.h:235-268 (seeds), :217-232 (plane), :463-504 (iterations), :331-384 (gating)
-//   ssc.cpp:158-172,185-188 (binning of the nonground points, fused here)
-// The covariance sums are accumulated strictly in z-sorted order, one lane per accumulator, because
-// PCL's single-pass float accumulation is order dependent (SURVEY.md hard part 3).
+// G4: R-GPF of one patch, split in three kernels so that each one maps to what bounds it:
+//   G4a k_patch_sort   CTA per (patch, scan): z-sort of the patch in shared memory (8 B/point), points
+//                      written back in sorted order                                       (patchwork.h:289-295)
+//   G4b k_patch_chain  WARP per (patch, scan): seeds + the three plane fits.  PCL's single-pass float
+//                      covariance is order dependent (SURVEY.md hard part 3), so the sums are accumulated
+//                      strictly sequentially, one lane per accumulator; the chain is latency bound, hence one
+//                      warp per patch, many patches per SM, points streamed through a small cp.async ring
+//                      instead of a whole-patch shared-memory tile   (patchwork.h:235-268, 217-232, 463-504)
+//   G4c k_patch_rank   CTA per (patch, scan): final ground test, gating outcome, curved-voxel binning of the
+//                      nonground points (ssc.cpp:158-172,185-188) and ordered ranks     (patchwork.h:331-384)
 // ------------------------------------------------------------------------------------------------
 struct FitArgs {
   const float4* pts;
@@ -322,55 +325,31 @@ struct FitArgs {
   const int32_t* patch_cnt;
   const int32_t* patch_off;
   uint64_t* bucket_kv;
-  float4* scratch4;  // GLOBAL tier only: per-slot float4 scratch (the not-yet-written apri_xyzi array)
+  float4* sorted_xyz;  // per bucket slot: the point, in z-sorted order inside its patch
   int32_t* sorted_idx;
   int32_t* slot_pos;
   int32_t* slot_apos;
   int32_t* slot_vid;
   int16_t* slot_patch;
-  int32_t* patch_out;
-  float* patch_dbg;
+  int32_t* patch_out;  // [scans][504][8]
+  float* patch_plane;  // [scans][504][12]: normal, mean, singular values, d, decision, npts
   uint8_t* cls;
   int32_t* err;
   GroundConst gc;
   BinParams bp;
 };
 
-constexpr uint32_t F_G = 1u;      // in the current ground set / final ground
-constexpr uint32_t F_PASS = 2u;   // survives the SSC gates
-constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md hard part 7)
+constexpr int kPatchOutStride = 8;  // n_ground_out, n_nonground_out, n_apri, n_quirk, nG, nGP, rejected, -
 
-// Shared-memory layout per point: one float4 {x, y, z, flag bits} (a single broadcast LDS.128 feeds the
-// sequential chain) + one 64-bit sort key whose words are reused after the sort (low: voxel_idx).
-// GLOBAL = true is the overflow tier for patches that do not fit the largest shared-memory tile: the
-// same code runs with its scratch arrays in the (L2-resident) global buffers of the patch itself.
 template <int MAXN, int MINN, int THREADS, bool GLOBAL>
-__global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
+__global__ void __launch_bounds__(THREADS) k_patch_sort(FitArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float s_plane[4];  // n0 n1 n2 th_dist_d
-  __shared__ float s_stat[8];   // mean z, sv0..2, d, mean x, mean y
-  __shared__ int s_int[4];
-  __shared__ double s_lpr;
-  __shared__ int s_scan[THREADS / 32 + 1];
-
   const int p = blockIdx.x, b = blockIdx.y;
   const int n = a.patch_cnt[b * kNumPatches + p];
   if (n <= MINN || n > MAXN) return;
   const int64_t base = a.off[b];
   const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
-  float4* P;
-  uint64_t* kv;
-  if (GLOBAL) {
-    P = a.scratch4 + base + slot0;
-    kv = a.bucket_kv + base + slot0;  // sorted in place
-  } else {
-    P = reinterpret_cast<float4*>(smem_raw);
-    kv = reinterpret_cast<uint64_t*>(P + MAXN);
-  }
-  uint32_t* kv32 = reinterpret_cast<uint32_t*>(kv);  // [2*j] = low word, [2*j+1] = high word
   const int tid = threadIdx.x;
-  int32_t* pout = a.patch_out + (b * kNumPatches + p) * 4;
-
   if (n <= kMinPatchPts) {  // patchwork.h:331: the patch vanishes from both outputs
     for (int j = tid; j < n; j += THREADS) {
       int idx = (int)(uint32_t)a.bucket_kv[base + slot0 + j];
@@ -378,18 +357,12 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
       a.slot_pos[base + slot0 + j] = (3 << 30);
       a.slot_patch[base + slot0 + j] = (int16_t)p;
     }
-    if (tid == 0) {
-      pout[0] = 0;
-      pout[1] = 0;
-      pout[2] = 0;
-      pout[3] = 0;
-    }
+    if (tid < kPatchOutStride) a.patch_out[(b * kNumPatches + p) * kPatchOutStride + tid] = 0;
     return;
   }
-
-  // ---- load + bitonic sort by (z key, original index) ---------------------------------------
-  // Bitonic network with a "flip" first step per merge, so every compare-exchange is ascending and
-  // the virtual +inf padding above n never moves: indices >= n are simply skipped.
+  uint64_t* kv = GLOBAL ? (a.bucket_kv + base + slot0) : reinterpret_cast<uint64_t*>(smem_raw);
+  // Bitonic network with a "flip" first step per merge, so every compare-exchange is ascending and the
+  // virtual +inf padding above n never moves: indices >= n are simply skipped.  Keys are (z key, index).
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   if (!GLOBAL) {
@@ -425,242 +398,261 @@ __global__ void __launch_bounds__(THREADS) k_patch_fit(FitArgs a) {
       __syncthreads();
     }
   }
-  // ---- gather the points in sorted order ------------------------------------------------------
   for (int j = tid; j < n; j += THREADS) {
-    int idx = (int)kv32[2 * j];
+    const int idx = (int)(uint32_t)kv[j];
     float4 q = __ldg(&a.pts[base + idx]);
-    q.w = __uint_as_float(0u);
-    P[j] = q;
+    q.w = 0.f;
+    a.sorted_xyz[base + slot0 + j] = q;
     a.sorted_idx[base + slot0 + j] = idx;
     a.slot_patch[base + slot0 + j] = (int16_t)p;
   }
-  __syncthreads();
+}
 
+constexpr int kChainWarps = 4;   // warps (= patches) per CTA of k_patch_chain
+constexpr int kChainStages = 4;  // cp.async ring depth, 32 points per stage
+
+// smallest float >= d: for a float z, ((double)z < d) == (z < float_at_or_above(d))
+__device__ __forceinline__ float float_at_or_above(double d) { return __double2float_ru(d); }
+
+__global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int nscans) {
+  __shared__ float4 s_ring[kChainWarps][kChainStages][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = blockIdx.x * kChainWarps + wid;
+  if (g >= kNumPatches * nscans) return;
+  // zone-0 patches (the largest) are handed out first so that the long chains start early
+  const int p = g / nscans, b = g - p * nscans;
+  const int n = a.patch_cnt[b * kNumPatches + p];
+  if (n <= kMinPatchPts) return;
+  const int64_t base = a.off[b];
+  const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+  const float4* __restrict__ S = a.sorted_xyz + base + slot0;
+  float4(*ring)[32] = s_ring[wid];
   const int zone = (p < 32) ? 0 : (p < 160) ? 1 : (p < 376) ? 2 : 3;
-  // ---- seeds (patchwork.h:235-268) --------------------------------------------------------------
-  {
-    int c = 0;
-    if (zone == 0)
-      for (int j = tid; j < n; j += THREADS) c += ((double)P[j].z < a.gc.seed_thr) ? 1 : 0;
-    int total;
-    block_excl_scan<THREADS>(c, &total, s_scan);
-    if (tid == 0) {
-      int init_idx = total;  // sorted ascending => the points below the margin form a prefix
-      double sum = 0;
-      int cnt = 0;
-      for (int i = init_idx; i < n && cnt < 20; ++i) {
-        sum = __dadd_rn(sum, (double)P[i].z);
-        cnt++;
-      }
-      s_lpr = cnt != 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
-    }
-    __syncthreads();
-    double thr = __dadd_rn(s_lpr, 0.3);
-    if (tid == 0) s_int[1] = 0;
-    __syncthreads();
-    int local = 0;
-    for (int j = tid; j < n; j += THREADS) {
-      bool in = (double)P[j].z < thr;
-      P[j].w = __uint_as_float(in ? F_G : 0u);
-      local += in ? 1 : 0;
-    }
-    if (local) atomicAdd(&s_int[1], local);
-    __syncthreads();
-  }
 
-  // ---- three plane fits -------------------------------------------------------------------------
-  for (int it = 0; it < 3; ++it) {
-    if (tid < 32) {
-      const int lane = tid;
-      // lane L accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix: xx xy xz yy yz zz x y z.
-      // Strictly sequential in z-sorted order (PCL's float single pass is order dependent); points
-      // outside the ground set contribute -0.0f, which is an exact identity for float addition, so
-      // the loop is branch free and the only loop-carried dependency is one FADD.
-      // Each lane reads its two factors straight from shared memory with a lane-specific word offset
-      // inside the point's float4 (no selects, no divergence); lanes 6..8 multiply by 1.
-      const int ia = (lane < 3 || lane == 6) ? 0 : ((lane == 3 || lane == 4 || lane == 7) ? 1 : 2);
-      const int ib = (lane == 0) ? 0 : ((lane == 1 || lane == 3) ? 1 : 2);
-      const bool plain_sum = lane >= 6;
-      const float* pa = reinterpret_cast<const float*>(P) + ia;
-      const float* pb = reinterpret_cast<const float*>(P) + ib;
-      const uint32_t* pf = reinterpret_cast<const uint32_t*>(P) + 3;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < n; ++j) {
-        const float av = pa[4 * j];
-        float bv = pb[4 * j];
-        const uint32_t fl = pf[4 * j];
-        bv = plain_sum ? 1.0f : bv;
-        float term = dm(av, bv);
-        term = (fl & F_G) ? term : -0.0f;
-        acc = da(acc, term);
+  // ---- seeds (patchwork.h:235-268): sorted ascending => the points below the margin form a prefix ----
+  int init_idx = 0;
+  if (zone == 0) {
+    const float margin = float_at_or_above(a.gc.seed_thr);
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool below = (j < n) && (__ldg(&S[j]).z < margin);
+      const unsigned m = __ballot_sync(0xffffffffu, below);
+      init_idx += __popc(m);
+      if (m != 0xffffffffu) break;
+    }
+  }
+  double lpr;
+  {
+    const int j = init_idx + lane;
+    const float zv = (lane < 20 && j < n) ? __ldg(&S[j]).z : 0.f;
+    const int cnt = min(20, n - init_idx);
+    double sum = 0;
+    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, zv, i));
+    lpr = cnt > 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
+  }
+  const float seed_cut = float_at_or_above(__dadd_rn(lpr, 0.3));
+
+  // lane L accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix: xx xy xz yy yz zz x y z
+  const int ia = (lane < 3 || lane == 6) ? 0 : ((lane == 3 || lane == 4 || lane == 7) ? 1 : 2);
+  const int ib = (lane == 0) ? 0 : ((lane == 1 || lane == 3) ? 1 : 2);
+  const bool plain_sum = lane >= 6;
+
+  float n0 = 0.f, n1 = 0.f, n2 = 0.f, th = 0.f;
+  float st_meanx = 0.f, st_meany = 0.f, st_meanz = 0.f, st_sv0 = 0.f, st_sv1 = 0.f, st_sv2 = 0.f, st_d = 0.f;
+  const int nstages = (n + 31) >> 5;
+  auto issue = [&](int st) {
+    if (st < nstages) {
+      const int j = st * 32 + lane;
+      if (j < n) {
+        unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[st % kChainStages][lane]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(S + j));
       }
-      const int cnt = s_int[1];
-      float accu[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) accu[k] = __shfl_sync(0xffffffffu, acc, k);
-      if (lane == 0) {
-        if (cnt == 0) {
-          atomicOr(a.err, 2);  // cannot happen for finite input; plane kept
-        } else {
-          float fn = (float)cnt;
-#pragma unroll
-          for (int k = 0; k < 9; ++k) accu[k] = dd(accu[k], fn);
-          float C[3][3];
-          C[0][0] = ds(accu[0], dm(accu[6], accu[6]));
-          C[0][1] = ds(accu[1], dm(accu[6], accu[7]));
-          C[0][2] = ds(accu[2], dm(accu[6], accu[8]));
-          C[1][1] = ds(accu[3], dm(accu[7], accu[7]));
-          C[1][2] = ds(accu[4], dm(accu[7], accu[8]));
-          C[2][2] = ds(accu[5], dm(accu[8], accu[8]));
-          C[1][0] = C[0][1];
-          C[2][0] = C[0][2];
-          C[2][1] = C[1][2];
-          float U[3][3], sv[3];
-          dev_svd3(C, U, sv);
-          float n0 = U[0][2], n1 = U[1][2], n2 = U[2][2];
-          // d_ = -(normal^T * mean): Eigen 3-term unrolled redux a0 + (a1 + a2)
-          float dval = -da(dm(n0, accu[6]), da(dm(n1, accu[7]), dm(n2, accu[8])));
-          s_plane[0] = n0;
-          s_plane[1] = n1;
-          s_plane[2] = n2;
-          s_plane[3] = (float)__dsub_rn(0.1, (double)dval);  // th_dist_d_ = th_dist_ - d_
-          s_stat[0] = accu[8];
-          s_stat[1] = sv[0];
-          s_stat[2] = sv[1];
-          s_stat[3] = sv[2];
-          s_stat[4] = dval;
-          s_stat[5] = accu[6];
-          s_stat[6] = accu[7];
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  for (int it = 0; it < 3; ++it) {
+    float acc = 0.f;
+    int cnt = 0;
+    for (int st = 0; st < kChainStages; ++st) issue(st);
+    for (int st = 0; st < nstages; ++st) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));
+      __syncwarp();
+      const float4* tile = ring[st % kChainStages];
+      const int m = min(32, n - st * 32);
+      // Strictly sequential in z-sorted order; a point outside the current ground set contributes -0.0f, an exact
+      // identity of float addition, so the loop is branch free and its only loop-carried dependency is one FADD.
+      if (it == 0) {
+#pragma unroll 8
+        for (int t = 0; t < m; ++t) {
+          const float4 q = tile[t];
+          const bool in = q.z < seed_cut;  // z < lpr + th_seeds_ (patchwork.h:262)
+          const float fa_ = (ia == 0) ? q.x : (ia == 1) ? q.y : q.z;
+          const float fb_ = plain_sum ? 1.0f : ((ib == 0) ? q.x : (ib == 1) ? q.y : q.z);
+          float term = dm(fa_, fb_);
+          term = in ? term : -0.0f;
+          acc = da(acc, term);
+          cnt += in ? 1 : 0;
+        }
+      } else {
+#pragma unroll 8
+        for (int t = 0; t < m; ++t) {
+          const float4 q = tile[t];
+          // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
+          const float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
+          const bool in = res < th;
+          const float fa_ = (ia == 0) ? q.x : (ia == 1) ? q.y : q.z;
+          const float fb_ = plain_sum ? 1.0f : ((ib == 0) ? q.x : (ib == 1) ? q.y : q.z);
+          float term = dm(fa_, fb_);
+          term = in ? term : -0.0f;
+          acc = da(acc, term);
+          cnt += in ? 1 : 0;
         }
       }
+      __syncwarp();
+      issue(st + kChainStages);  // refills the slot that was just consumed
     }
-    __syncthreads();
-    const float n0 = s_plane[0], n1 = s_plane[1], n2 = s_plane[2], th = s_plane[3];
-    if (tid == 0) s_int[1] = 0;
-    __syncthreads();
-    int local = 0;
-    for (int j = tid; j < n; j += THREADS) {
-      // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
-      const float4 q = P[j];
-      float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
-      bool in = res < th;
-      P[j].w = __uint_as_float(in ? F_G : 0u);
-      local += in ? 1 : 0;
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    float accu[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) accu[k] = __shfl_sync(0xffffffffu, acc, k);
+    if (cnt == 0) {
+      if (lane == 0) atomicOr(a.err, 2);  // cannot happen for finite input; plane kept
+    } else {  // every lane evaluates the (tiny) plane solve redundantly: no broadcast, no divergence
+      const float fn = (float)cnt;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) accu[k] = dd(accu[k], fn);
+      float C[3][3];
+      C[0][0] = ds(accu[0], dm(accu[6], accu[6]));
+      C[0][1] = ds(accu[1], dm(accu[6], accu[7]));
+      C[0][2] = ds(accu[2], dm(accu[6], accu[8]));
+      C[1][1] = ds(accu[3], dm(accu[7], accu[7]));
+      C[1][2] = ds(accu[4], dm(accu[7], accu[8]));
+      C[2][2] = ds(accu[5], dm(accu[8], accu[8]));
+      C[1][0] = C[0][1];
+      C[2][0] = C[0][2];
+      C[2][1] = C[1][2];
+      float U[3][3], sv[3];
+      dev_svd3(C, U, sv);
+      n0 = U[0][2];
+      n1 = U[1][2];
+      n2 = U[2][2];
+      // d_ = -(normal^T * mean): Eigen 3-term unrolled redux a0 + (a1 + a2)
+      st_d = -da(dm(n0, accu[6]), da(dm(n1, accu[7]), dm(n2, accu[8])));
+      th = (float)__dsub_rn(0.1, (double)st_d);  // th_dist_d_ = th_dist_ - d_
+      st_meanx = accu[6];
+      st_meany = accu[7];
+      st_meanz = accu[8];
+      st_sv0 = sv[0];
+      st_sv1 = sv[1];
+      st_sv2 = sv[2];
     }
-    if (local) atomicAdd(&s_int[1], local);
-    __syncthreads();
   }
-
-  // ---- gating (patchwork.h:339-384) ---------------------------------------------------------------
-  if (tid == 0) {
-    const double ground_z_vec = (double)fabsf(s_plane[2]);
-    const double ground_z_elevation = (double)s_stat[0];
-    const float minsv = fminf(s_stat[1], fminf(s_stat[2], s_stat[3]));
-    const double surface_variable = (double)dd(minsv, da(da(s_stat[1], s_stat[2]), s_stat[3]));
-    const int ring = (p - c_zone_base[zone]) / c_zone_sectors[zone];
-    const int concentric_idx = c_zone_ring0[zone] + ring;
+  // ---- gating (patchwork.h:339-384) ------------------------------------------------------------------
+  if (lane == 0) {
+    const double ground_z_vec = (double)fabsf(n2);
+    const double ground_z_elevation = (double)st_meanz;
+    const float minsv = fminf(st_sv0, fminf(st_sv1, st_sv2));
+    const double surface_variable = (double)dd(minsv, da(da(st_sv0, st_sv1), st_sv2));
+    const int ring_i = (p - c_zone_base[zone]) / c_zone_sectors[zone];
+    const int concentric_idx = c_zone_ring0[zone] + ring_i;
     int decision = 0;
     if (ground_z_vec < 0.707) {
       decision = 1;
     } else if (concentric_idx < 4) {
-      if (ground_z_elevation > c_elev_thr[ring + 2 * zone]) decision = (c_flat_thr[ring + 2 * zone] > surface_variable) ? 3 : 2;
+      if (ground_z_elevation > c_elev_thr[ring_i + 2 * zone]) decision = (c_flat_thr[ring_i + 2 * zone] > surface_variable) ? 3 : 2;
     }
-    s_int[0] = decision;
-    if (a.patch_dbg) {
-      float* dbg = a.patch_dbg + (size_t)(b * kNumPatches + p) * 12;
-      dbg[0] = s_plane[0];
-      dbg[1] = s_plane[1];
-      dbg[2] = s_plane[2];
-      dbg[3] = s_stat[5];
-      dbg[4] = s_stat[6];
-      dbg[5] = s_stat[0];
-      dbg[6] = s_stat[1];
-      dbg[7] = s_stat[2];
-      dbg[8] = s_stat[3];
-      dbg[9] = s_stat[4];
-      dbg[10] = (float)decision;
-      dbg[11] = (float)n;
-    }
+    float* rec = a.patch_plane + (size_t)(b * kNumPatches + p) * 12;
+    rec[0] = n0;
+    rec[1] = n1;
+    rec[2] = n2;
+    rec[3] = st_meanx;
+    rec[4] = st_meany;
+    rec[5] = st_meanz;
+    rec[6] = st_sv0;
+    rec[7] = st_sv1;
+    rec[8] = st_sv2;
+    rec[9] = st_d;
+    rec[10] = (float)decision;
+    rec[11] = (float)n;
   }
-  __syncthreads();
-  const bool rejected = (s_int[0] == 1 || s_int[0] == 2);
+}
 
-  // ---- curved-voxel binning of every point that ends up in cloud_nonground ------------------------
-  for (int j = tid; j < n; j += THREADS) {
-    const float4 q = P[j];
-    uint32_t f = __float_as_uint(q.w) & F_G;
+constexpr uint32_t F_G = 1u;      // final ground set
+constexpr uint32_t F_PASS = 2u;   // survives the SSC gates
+constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md hard part 7)
+
+// slot_pos encoding: role << 30 | in-ground-set << 29 | rank inside its class (ground set / complement);
+// slot_apos: rank among the gate-passing points of the same class, or -1.  k_emit turns them into positions with
+// the per-patch totals of patch_out (a rejected patch emits [ground set][complement] into cloud_nonground).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_patch_rank(FitArgs a) {
+  __shared__ int s_scan[THREADS / 32 + 1];
+  const int p = blockIdx.x, b = blockIdx.y;
+  const int n = a.patch_cnt[b * kNumPatches + p];
+  if (n <= kMinPatchPts) return;
+  const int64_t base = a.off[b];
+  const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+  const float4* __restrict__ S = a.sorted_xyz + base + slot0;
+  const float* rec = a.patch_plane + (size_t)(b * kNumPatches + p) * 12;
+  const float n0 = rec[0], n1 = rec[1], n2 = rec[2];
+  const float th = (float)__dsub_rn(0.1, (double)rec[9]);
+  const int decision = (int)rec[10];
+  const bool rejected = (decision == 1 || decision == 2);
+  const int tid = threadIdx.x;
+  int cG = 0, cGP = 0, cNP = 0, cQ = 0;  // running totals (block uniform)
+  for (int j0 = 0; j0 < n; j0 += THREADS) {
+    const int j = j0 + tid;
+    const bool valid = j < n;
+    uint32_t f = 0;
     int vid = 0;
-    if (rejected || !(f & F_G)) {
-      BinResult r = dev_bin_point(q.x, q.y, q.z, a.bp);
-      if (r.pass) {
-        f |= F_PASS;
-        if (r.ri < 0 || r.si < 0 || r.ei < 0) f |= F_QUIRK;
-      }
-      vid = r.vid;
-    }
-    P[j].w = __uint_as_float(f);
-    kv32[2 * j] = (uint32_t)vid;
-  }
-  __syncthreads();
-
-  // ---- ordered ranks: ground list, nonground list ([G part][NG part] when rejected), apri list ------
-  const int chunk = (n + THREADS - 1) / THREADS;
-  const int j0 = min(n, tid * chunk), j1 = min(n, j0 + chunk);
-  int cG = 0, cGP = 0, cNP = 0, cQ = 0;
-  for (int j = j0; j < j1; ++j) {
-    uint32_t f = __float_as_uint(P[j].w);
-    bool g = f & F_G, ps = f & F_PASS;
-    cG += g;
-    cGP += (g && ps);
-    cNP += (!g && ps);
-    cQ += (f & F_QUIRK) ? 1 : 0;
-  }
-  int tG, tGP, tNP, tQ;
-  int eG = block_excl_scan<THREADS>(cG, &tG, s_scan);
-  int eGP = block_excl_scan<THREADS>(cGP, &tGP, s_scan);
-  int eNP = block_excl_scan<THREADS>(cNP, &tNP, s_scan);
-  block_excl_scan<THREADS>(cQ, &tQ, s_scan);
-  const int nG = tG, nN = n - tG;
-  {
-    int rG = eG, rGP = eGP, rNP = eNP;
-    for (int j = j0; j < j1; ++j) {
-      uint32_t f = __float_as_uint(P[j].w);
-      bool g = f & F_G, ps = f & F_PASS;
-      int rN = j - rG;  // nonground points before j
-      int pos, apos = -1, role;
-      if (!rejected) {
-        if (g) {
-          role = 0;
-          pos = rG;
-        } else {
-          pos = rN;
-          role = ps ? 2 : 1;
-          if (ps) apos = rNP;
+    if (valid) {
+      const float4 q = __ldg(&S[j]);
+      const float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
+      if (res < th) f |= F_G;
+      if (rejected || !(f & F_G)) {
+        BinResult r = dev_bin_point(q.x, q.y, q.z, a.bp);
+        if (r.pass) {
+          f |= F_PASS;
+          if (r.ri < 0 || r.si < 0 || r.ei < 0) f |= F_QUIRK;
         }
-      } else {
-        pos = g ? rG : nG + rN;
-        role = ps ? 2 : 1;
-        if (ps) apos = g ? rGP : tGP + rNP;
+        vid = r.vid;
       }
-      P[j].x = __int_as_float((role << 30) | pos);  // x, y are dead from here on
-      P[j].y = __int_as_float(apos);
-      rG += g;
-      rGP += (g && ps);
-      rNP += (!g && ps);
     }
-  }
-  __syncthreads();
-  for (int j = tid; j < n; j += THREADS) {
-    a.slot_pos[base + slot0 + j] = __float_as_int(P[j].x);
-    a.slot_apos[base + slot0 + j] = __float_as_int(P[j].y);
-    a.slot_vid[base + slot0 + j] = (int)kv32[2 * j];
+    const bool g = f & F_G, ps = f & F_PASS;
+    // chunk counts are <= THREADS <= 512: three 10-bit fields in one scan
+    const int packed = (g ? 1 : 0) | ((g && ps) ? (1 << 10) : 0) | ((!g && ps) ? (1 << 20) : 0);
+    int total;
+    const int ex = block_excl_scan<THREADS>(packed, &total, s_scan);
+    const int nq = __syncthreads_count((f & F_QUIRK) ? 1 : 0);
+    if (valid) {
+      const int rG = cG + (ex & 1023), rGP = cGP + ((ex >> 10) & 1023), rNP = cNP + ((ex >> 20) & 1023);
+      const int rN = j - rG;  // complement points before j
+      int role, apos = -1;
+      if (!rejected && g) {
+        role = 0;
+      } else {
+        role = ps ? 2 : 1;
+        if (ps) apos = g ? rGP : rNP;
+      }
+      a.slot_pos[base + slot0 + j] = (role << 30) | (g ? (1 << 29) : 0) | (g ? rG : rN);
+      a.slot_apos[base + slot0 + j] = apos;
+      a.slot_vid[base + slot0 + j] = vid;
+    }
+    cG += total & 1023;
+    cGP += (total >> 10) & 1023;
+    cNP += (total >> 20) & 1023;
+    cQ += nq;
   }
   if (tid == 0) {
-    pout[0] = rejected ? 0 : nG;
-    pout[1] = rejected ? n : nN;
-    pout[2] = rejected ? (tGP + tNP) : tNP;
-    pout[3] = tQ;
+    int32_t* pout = a.patch_out + (b * kNumPatches + p) * kPatchOutStride;
+    pout[0] = rejected ? 0 : cG;
+    pout[1] = rejected ? n : n - cG;
+    pout[2] = rejected ? (cGP + cNP) : cNP;
+    pout[3] = cQ;
+    pout[4] = cG;
+    pout[5] = cGP;
+    pout[6] = rejected ? 1 : 0;
+    pout[7] = 0;
   }
 }
 
@@ -673,7 +665,7 @@ __global__ void __launch_bounds__(512) k_patch_out_scan(const int32_t* __restric
   const bool live = t < kNumPatches && patch_cnt[b * kNumPatches + t] > 0;
   int v[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = live ? patch_out[(b * kNumPatches + t) * 4 + k] : 0;
+  for (int k = 0; k < 4; ++k) v[k] = live ? patch_out[(b * kNumPatches + t) * kPatchOutStride + k] : 0;
   int tot[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -690,33 +682,40 @@ __global__ void __launch_bounds__(512) k_patch_out_scan(const int32_t* __restric
 
 // G6: emit cloud_out / cloud_nonground order and the apri arrays
 __global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ pts, const int64_t* __restrict__ off,
-                                              const int32_t* __restrict__ patch_off, const int32_t* __restrict__ patch_out_off,
-                                              const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ slot_pos,
-                                              const int32_t* __restrict__ slot_apos, const int32_t* __restrict__ slot_vid,
-                                              const int16_t* __restrict__ slot_patch, int32_t* __restrict__ ground_src,
-                                              int32_t* __restrict__ ng_src, int32_t* __restrict__ apri_src,
-                                              int32_t* __restrict__ apri_vid, float4* __restrict__ apri_xyzi,
-                                              uint8_t* __restrict__ cls) {
+                                              const int32_t* __restrict__ patch_off, const int32_t* __restrict__ patch_out,
+                                              const int32_t* __restrict__ patch_out_off, const int32_t* __restrict__ sorted_idx,
+                                              const int32_t* __restrict__ slot_pos, const int32_t* __restrict__ slot_apos,
+                                              const int32_t* __restrict__ slot_vid, const int16_t* __restrict__ slot_patch,
+                                              int32_t* __restrict__ ground_src, int32_t* __restrict__ ng_src,
+                                              int32_t* __restrict__ apri_src, int32_t* __restrict__ apri_vid,
+                                              float4* __restrict__ apri_xyzi, uint8_t* __restrict__ cls) {
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int nslots = patch_off[b * (kNumPatches + 1) + kNumPatches];
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nslots; q += gridDim.x * blockDim.x) {
-    int sp = slot_pos[base + q];
-    int role = (sp >> 30) & 3;
+    const int sp = slot_pos[base + q];
+    const int role = (sp >> 30) & 3;
     if (role == 3) continue;
-    int pos = sp & 0x3fffffff;
-    int p = slot_patch[base + q];
-    int idx = sorted_idx[base + q];
+    const bool g = (sp >> 29) & 1;
+    const int rank = sp & 0x1fffffff;
+    const int p = slot_patch[base + q];
+    const int idx = sorted_idx[base + q];
     const int32_t* o = patch_out_off + (b * (kNumPatches + 1) + p) * 3;
+    const int32_t* po = patch_out + (b * kNumPatches + p) * kPatchOutStride;
     if (role == 0) {
-      ground_src[base + o[0] + pos] = idx;
+      ground_src[base + o[0] + rank] = idx;
       cls[base + idx] = SCVOD_PT_GROUND;
     } else {
+      // cloud_nonground: the complement of the ground set, or [ground set][complement] for a rejected patch
+      // (patchwork.h:348-349,373-374)
+      const bool rejected = po[6] != 0;
+      const int pos = (rejected && !g) ? po[4] + rank : rank;
       ng_src[base + o[1] + pos] = idx;
       if (role == 1) {
         cls[base + idx] = SCVOD_PT_GATED_OUT;
       } else {
-        int m = o[2] + slot_apos[base + q];
+        const int ar = slot_apos[base + q];
+        const int m = o[2] + ((rejected && !g) ? po[5] + ar : ar);
         apri_src[base + m] = idx;
         apri_vid[base + m] = slot_vid[base + q];
         apri_xyzi[base + m] = __ldg(&pts[base + idx]);
@@ -1596,49 +1595,47 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   fa.patch_cnt = d.patch_cnt;
   fa.patch_off = d.patch_off;
   fa.bucket_kv = d.bucket_kv;
-  fa.scratch4 = d.apri_xyzi;
+  fa.sorted_xyz = d.sorted_xyz;
   fa.sorted_idx = d.sorted_idx;
   fa.slot_pos = d.slot_pos;
   fa.slot_apos = d.slot_apos;
   fa.slot_vid = d.slot_vid;
   fa.slot_patch = d.slot_patch;
   fa.patch_out = d.patch_out;
-  fa.patch_dbg = d.patch_dbg;
+  fa.patch_plane = d.patch_dbg;
   fa.cls = d.cls;
   fa.err = d.scan_counts + (size_t)d.cap_scans * 8;  // one extra int past the per-scan counters
   fa.gc = gc;
   fa.bp = bp;
   static bool attr_set = false;
-  constexpr int kT0 = 1024, kT1 = 2048, kT2 = 4096;
+  constexpr int kT0 = 1024, kT1 = 4096, kT2 = 16384;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_patch_fit<kT0, 0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT0 * 24);
-    cudaFuncSetAttribute(k_patch_fit<kT1, kT0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1 * 24);
-    cudaFuncSetAttribute(k_patch_fit<kT2, kT1, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2 * 24);
-    cudaFuncSetAttribute(k_patch_fit<kFitLarge, kT2, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitLarge * 24);
+    cudaFuncSetAttribute(k_patch_sort<kT1, kT0, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1 * 8);
+    cudaFuncSetAttribute(k_patch_sort<kT2, kT1, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2 * 8);
     attr_set = true;
   }
   dim3 gfit(kNumPatches, nscans);
-  { TIMED("k_patch_fit_1k", TSTREAM); k_patch_fit<kT0, 0, 128, false><<<gfit, 128, kT0 * 24, st>>>(fa); }
+  { TIMED("k_patch_sort_1k", TSTREAM); k_patch_sort<kT0, 0, 128, false><<<gfit, 128, kT0 * 8, st>>>(fa); }
+  launches += 1;
   if (max_scan_points > kT0) {
-    { TIMED("k_patch_fit_2k", TSTREAM); k_patch_fit<kT1, kT0, 128, false><<<gfit, 128, kT1 * 24, st>>>(fa); }
+    { TIMED("k_patch_sort_4k", TSTREAM); k_patch_sort<kT1, kT0, 256, false><<<gfit, 256, kT1 * 8, st>>>(fa); }
     launches += 1;
   }
   if (max_scan_points > kT1) {
-    { TIMED("k_patch_fit_4k", TSTREAM); k_patch_fit<kT2, kT1, 256, false><<<gfit, 256, kT2 * 24, st>>>(fa); }
+    { TIMED("k_patch_sort_16k", TSTREAM); k_patch_sort<kT2, kT1, 512, false><<<gfit, 512, kT2 * 8, st>>>(fa); }
     launches += 1;
   }
-  if (max_scan_points > kT2) {
-    { TIMED("k_patch_fit_9k", TSTREAM); k_patch_fit<kFitLarge, kT2, 256, false><<<gfit, 256, kFitLarge * 24, st>>>(fa); }
+  if (max_scan_points > kT2) {  // overflow tier: sorted in place in global memory
+    { TIMED("k_patch_sort_overflow", TSTREAM); k_patch_sort<0x3fffffff, kT2, 512, true><<<gfit, 512, 0, st>>>(fa); }
     launches += 1;
   }
-  if (max_scan_points > kFitLarge) {  // overflow tier: scratch in global memory
-    { TIMED("k_patch_fit_overflow", TSTREAM); k_patch_fit<0x3fffffff, kFitLarge, 256, true><<<gfit, 256, 0, st>>>(fa); }
-    launches += 1;
-  }
+  { TIMED("k_patch_chain", TSTREAM); k_patch_chain<<<(kNumPatches * nscans + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, st>>>(fa, nscans); }
+  { TIMED("k_patch_rank", TSTREAM); k_patch_rank<256><<<gfit, 256, 0, st>>>(fa); }
+  launches += 2;
   { TIMED("k_patch_out_scan", TSTREAM); k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts); }
-  { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
+  { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
                              d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls); }
-  launches += 6;
+  launches += 5;
   return launches;
 }
 

@@ -24,6 +24,7 @@ struct GParams {  // mirrors scvod_gicp_params (include/scvod.h)
 struct Grid {  // spec §2
   float ox, oy, oz, h;
   int nx, ny, nz;
+  int rings;               // ceil(max_corr_dist / h)
   std::vector<int> start;  // ncells + 1
   std::vector<int> order;  // point indices, cell-major, ascending index inside a cell
   int ncells() const { return nx * ny * nz; }
@@ -44,15 +45,17 @@ void build_grid(const float* xyzi, int n, const GParams& P, Grid& g) {
       hi[a] = std::max(hi[a], xyzi[4 * i + a]);
     }
   if (n == 0) lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f;
-  float h = std::max(P.cov_radius, P.max_corr_dist);
+  float h = P.cov_radius;
   for (;;) {
     g.h = h;
-    g.ox = lo[0] - h;
-    g.oy = lo[1] - h;
-    g.oz = lo[2] - h;
-    g.nx = (int)floorf((hi[0] - g.ox) / h) + 2;
-    g.ny = (int)floorf((hi[1] - g.oy) / h) + 2;
-    g.nz = (int)floorf((hi[2] - g.oz) / h) + 2;
+    g.rings = std::max(1, (int)std::ceil(P.max_corr_dist / h));
+    const float margin = (float)g.rings * h;
+    g.ox = lo[0] - margin;
+    g.oy = lo[1] - margin;
+    g.oz = lo[2] - margin;
+    g.nx = (int)floorf((hi[0] - g.ox) / h) + 1 + g.rings;
+    g.ny = (int)floorf((hi[1] - g.oy) / h) + 1 + g.rings;
+    g.nz = (int)floorf((hi[2] - g.oz) / h) + 1 + g.rings;
     if ((double)g.nx * g.ny * g.nz <= (double)(1 << 22)) break;
     h = h * 2.f;
   }
@@ -290,9 +293,10 @@ int orc_gicp_align(const float* src, int n_src, const float* tgt, int n_tgt, con
       if (!gt.inside(c)) continue;
       double best = 1e300;
       int bj = -1;
-      for (int dx = -1; dx <= 1; ++dx)
-        for (int dy = -1; dy <= 1; ++dy)
-          for (int dz = -1; dz <= 1; ++dz) {
+      const int K = gt.rings;
+      for (int dx = -K; dx <= K; ++dx)
+        for (int dy = -K; dy <= K; ++dy)
+          for (int dz = -K; dz <= K; ++dz) {
             int cc[3] = {c[0] + dx, c[1] + dy, c[2] + dz};
             if (!gt.inside(cc)) continue;
             int l = gt.lin(cc[0], cc[1], cc[2]);
