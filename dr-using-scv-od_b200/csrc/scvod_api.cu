@@ -195,7 +195,7 @@ struct scvod_ctx {
   DevBuf<int32_t> d_vox_name, d_name_first;
   int name_cap = 0;
   // tracking buffers: packed request (segments + own indices), ping-pong transformed clouds, hit table
-  DevBuf<int32_t> d_treq, d_triples;
+  DevBuf<int32_t> d_treq, d_triples, d_track_ctr, d_track_list;
   DevBuf<unsigned long long> d_first;
   PinBuf<int32_t> h_treq, h_triples;
   DevBuf<float4> d_tout[2];
@@ -428,7 +428,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_bucket_kv.release(); c->d_sorted_xyz.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
   c->h_scan_counts.release(); c->h_vox_cnt.release(); c->h_vox_root.release(); c->h_vox_nbr.release(); c->h_ev_cid.release();
   c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_treq.release(); c->d_first.release(); c->d_triples.release();
-  c->h_treq.release(); c->h_triples.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
+  c->h_treq.release(); c->h_triples.release(); c->d_track_ctr.release(); c->d_track_list.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
   c->d_Ts.release(); c->h_Ts.release();
   c->d_counter.release();
   c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
@@ -814,24 +814,33 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       CU(c->d_tout[out_buf].alloc(K));
       {
         const size_t need = (size_t)ncl * vn;
-        if (need > c->d_first.n) {  // (re)allocation: the table must start out "empty"; afterwards k_track_compact keeps it so
+        if (need > c->d_first.n) {  // (re)allocation: the table must start out "empty"; afterwards the epilogue of k_track keeps it so
           CU(c->d_first.alloc(need));
           CU(cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream));
         }
       }
-      CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));  // pinned + device-accessible (UVA): the kernel writes the hits straight to the host
+      CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));
+      if (!c->d_track_ctr.p) {
+        CU(c->d_track_ctr.alloc(4));
+        CU(cudaMemsetAsync(c->d_track_ctr.p, 0, sizeof(int32_t) * c->d_track_ctr.n, c->stream));
+      }
+      CU(c->d_track_list.alloc((size_t)cap_quads));  // pinned + device-accessible (UVA): the kernel writes the hits straight to the host
       PersistBatch& pbp = *c->batches[pre.batch];
       PersistBatch& pbn = *c->batches[next.batch];
       CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4), cudaMemcpyHostToDevice, c->stream));
       c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                   reinterpret_cast<const int4*>(c->d_treq.p), (int)si, (int)K, T,
                                   pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
-                                  vn, c->d_tout[out_buf].p, c->d_first.p, reinterpret_cast<int32_t*>(c->d_counter.p), c->h_triples.p, cap_quads,
+                                  vn, c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads,
                                   c->stream);
       CU(cudaGetLastError());
       CU(cudaStreamSynchronize(c->stream));
       int nt = c->h_triples.p[0];
-      if (nt > cap_quads) return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
+      if (nt > cap_quads) {  // entries past the list were not reset by the kernel epilogue: wipe the table before giving up
+        cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream);
+        cudaStreamSynchronize(c->stream);
+        return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
+      }
       for (int t = 0; t < nt; ++t) {
         const int32_t* q = c->h_triples.p + 4 + 4 * t;
         hits[q[0]].push_back(std::make_pair(((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3], q[1]));

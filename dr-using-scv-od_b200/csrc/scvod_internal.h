@@ -98,8 +98,8 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 // tracking diff of one frame pair: segments {dst_off, source (>=0 voxel of frame_pre_ / <0 carried range), cluster, order}
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
                  const int4* segs, int nseg, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
-                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* count_dev, int32_t* out_quads_mapped, int cap_quads,
-                 void* stream);
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
+                 int cap_quads, void* stream);
 int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
                         const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream);
 int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,

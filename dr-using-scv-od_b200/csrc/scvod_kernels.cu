@@ -408,14 +408,17 @@ __global__ void __launch_bounds__(THREADS) k_patch_sort(FitArgs a) {
   }
 }
 
-constexpr int kChainWarps = 4;   // warps (= patches) per CTA of k_patch_chain
-constexpr int kChainStages = 4;  // cp.async ring depth, 32 points per stage
+constexpr int kChainWarps = 4;    // warps (= patches) per CTA of k_patch_chain
+constexpr int kChainStages = 4;   // cp.async ring depth, 32 points per stage
+constexpr int kChainCtasPerSm = 2;  // residency cap: the chain is latency bound, so few warps per scheduler keep the
+                                    // long (zone-0) patches fast while the many short ones fill the remaining slots
 
 // smallest float >= d: for a float z, ((double)z < d) == (z < float_at_or_above(d))
 __device__ __forceinline__ float float_at_or_above(double d) { return __double2float_ru(d); }
 
 __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int nscans) {
   __shared__ float4 s_ring[kChainWarps][kChainStages][32];
+  __shared__ float s_prod[kChainWarps][2][32 * 9];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = blockIdx.x * kChainWarps + wid;
   if (g >= kNumPatches * nscans) return;
@@ -450,12 +453,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
     for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, (double)__shfl_sync(0xffffffffu, zv, i));
     lpr = cnt > 0 ? __ddiv_rn(sum, (double)cnt) : 0.0;
   }
-  const float seed_cut = float_at_or_above(__dadd_rn(lpr, 0.3));
-
-  // lane L accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix: xx xy xz yy yz zz x y z
-  const int ia = (lane < 3 || lane == 6) ? 0 : ((lane == 3 || lane == 4 || lane == 7) ? 1 : 2);
-  const int ib = (lane == 0) ? 0 : ((lane == 1 || lane == 3) ? 1 : 2);
-  const bool plain_sum = lane >= 6;
+  const float seed_cut = float_at_or_above(__dadd_rn(lpr, 0.3));  // z < lpr + th_seeds_ (patchwork.h:262)
 
   float n0 = 0.f, n1 = 0.f, n2 = 0.f, th = 0.f;
   float st_meanx = 0.f, st_meany = 0.f, st_meanz = 0.f, st_sv0 = 0.f, st_sv1 = 0.f, st_sv2 = 0.f, st_d = 0.f;
@@ -470,6 +468,13 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
+  // Lane L < 9 accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix (xx xy xz yy yz zz x y z) STRICTLY in
+  // z-sorted order — PCL's single-pass float sums are order dependent.  Per stage of 32 points the work is split:
+  //   parallel part   lane t takes point t: ground-set test, its nine terms (a point outside the set, or past the
+  //                   end of the patch, contributes -0.0f: an exact identity of float addition), written to
+  //                   shared memory as a 32 x 9 tile;
+  //   sequential part lane L walks column L of the tile: one LDS + one dependent FADD per point.
+  const int col = lane < 9 ? lane : 8;
   for (int it = 0; it < 3; ++it) {
     float acc = 0.f;
     int cnt = 0;
@@ -477,39 +482,31 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
     for (int st = 0; st < nstages; ++st) {
       asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));
       __syncwarp();
-      const float4* tile = ring[st % kChainStages];
-      const int m = min(32, n - st * 32);
-      // Strictly sequential in z-sorted order; a point outside the current ground set contributes -0.0f, an exact
-      // identity of float addition, so the loop is branch free and its only loop-carried dependency is one FADD.
+      const bool live = st * 32 + lane < n;
+      const float4 q = live ? ring[st % kChainStages][lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+      bool in;
       if (it == 0) {
-#pragma unroll 8
-        for (int t = 0; t < m; ++t) {
-          const float4 q = tile[t];
-          const bool in = q.z < seed_cut;  // z < lpr + th_seeds_ (patchwork.h:262)
-          const float fa_ = (ia == 0) ? q.x : (ia == 1) ? q.y : q.z;
-          const float fb_ = plain_sum ? 1.0f : ((ib == 0) ? q.x : (ib == 1) ? q.y : q.z);
-          float term = dm(fa_, fb_);
-          term = in ? term : -0.0f;
-          acc = da(acc, term);
-          cnt += in ? 1 : 0;
-        }
+        in = live && (q.z < seed_cut);
       } else {
-#pragma unroll 8
-        for (int t = 0; t < m; ++t) {
-          const float4 q = tile[t];
-          // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
-          const float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
-          const bool in = res < th;
-          const float fa_ = (ia == 0) ? q.x : (ia == 1) ? q.y : q.z;
-          const float fb_ = plain_sum ? 1.0f : ((ib == 0) ? q.x : (ib == 1) ? q.y : q.z);
-          float term = dm(fa_, fb_);
-          term = in ? term : -0.0f;
-          acc = da(acc, term);
-          cnt += in ? 1 : 0;
-        }
+        // result = points * normal_ : (x*n0 + y*n1) + z*n2, three rounded products (patchwork.h:486)
+        in = live && (da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2)) < th);
       }
+      cnt += __popc(__ballot_sync(0xffffffffu, in));
+      float* pr = s_prod[wid][st & 1] + lane * 9;
+      pr[0] = in ? dm(q.x, q.x) : -0.0f;
+      pr[1] = in ? dm(q.x, q.y) : -0.0f;
+      pr[2] = in ? dm(q.x, q.z) : -0.0f;
+      pr[3] = in ? dm(q.y, q.y) : -0.0f;
+      pr[4] = in ? dm(q.y, q.z) : -0.0f;
+      pr[5] = in ? dm(q.z, q.z) : -0.0f;
+      pr[6] = in ? q.x : -0.0f;
+      pr[7] = in ? q.y : -0.0f;
+      pr[8] = in ? q.z : -0.0f;
       __syncwarp();
-      issue(st + kChainStages);  // refills the slot that was just consumed
+      issue(st + kChainStages);  // refills the ring slot that was just consumed
+      const float* pc = s_prod[wid][st & 1] + col;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) acc = da(acc, pc[t * 9]);
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
     float accu[9];
@@ -1273,9 +1270,10 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
                                                const int4* __restrict__ segs, int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
                                                float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
-                                               int32_t* __restrict__ out_count) {
+                                               int32_t* __restrict__ ctr /* [0] distinct hits, [1] finished CTAs */,
+                                               int32_t* __restrict__ hit_list, int32_t* __restrict__ out_quads, int cap_quads) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = 0;  // consumed by k_track_compact, which runs after this kernel
+  __shared__ int s_last;
   // segment start offsets staged in shared memory: the per-point binary search then never leaves the SM
   int* s_dst = reinterpret_cast<int*>(smem_raw);
   const bool staged = nseg <= kTrackSegSmem;
@@ -1315,31 +1313,38 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
     out_xyzi[i] = q;
     BinResult r = dev_bin_point(q.x, q.y, q.z, bp);
     int hit = vox_lookup(bm, wr, g, r.vid);
-    if (hit >= 0) atomicMin(&first[(size_t)sg.z * vn + hit], ((unsigned long long)(unsigned)sg.w << 32) | low);
-  }
-}
-
-// compaction of the (cluster, voxel) -> first-occurrence key table into host-mapped pinned memory (quads from
-// out[4]; the count is published by the host-side copy of *count after the stream sync).  Every consumed entry is
-// reset to "empty", so the table needs no memset between frame pairs.
-__global__ void __launch_bounds__(256) k_track_compact(unsigned long long* __restrict__ first, int ncl, int vn,
-                                                       int32_t* __restrict__ count, int32_t* __restrict__ out, int cap_quads) {
-  const int total = ncl * vn;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    unsigned long long f = first[e];
-    if (f != ~0ull) {
-      first[e] = ~0ull;
-      int slot = atomicAdd(count, 1);
-      if (slot < cap_quads) {
-        int4 q = make_int4(e / vn, e % vn, (int)(unsigned)(f >> 32), (int)(unsigned)(f & 0xffffffffu));
-        reinterpret_cast<int4*>(out + 4)[slot] = q;
+    if (hit >= 0) {
+      const int e = sg.z * vn + hit;
+      const unsigned long long old = atomicMin(&first[e], ((unsigned long long)(unsigned)sg.w << 32) | low);
+      if (old == ~0ull) {  // first point to touch this (cluster, voxel): remember the entry for the epilogue
+        const int slot = atomicAdd(&ctr[0], 1);
+        if (slot < cap_quads) hit_list[slot] = e;
       }
     }
   }
+  // ---- epilogue by the last CTA to finish: (cluster, voxel, first-occurrence key) quads straight into host-mapped
+  // pinned memory; every consumed table entry goes back to "empty", so the table needs no memset between pairs ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctr[1], 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nh = *reinterpret_cast<volatile int32_t*>(&ctr[0]);
+  const int take = min(nh, cap_quads);
+  for (int t = threadIdx.x; t < take; t += blockDim.x) {
+    const int e = hit_list[t];
+    const unsigned long long f = first[e];
+    first[e] = ~0ull;
+    reinterpret_cast<int4*>(out_quads + 4)[t] = make_int4(e / vn, e % vn, (int)(unsigned)(f >> 32), (int)(unsigned)(f & 0xffffffffu));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out_quads[0] = nh;  // > cap_quads tells the host that the table overflowed
+    ctr[0] = 0;
+    ctr[1] = 0;
+  }
 }
-
-// publishes the quad count next to the quads (runs after k_track_compact)
-__global__ void k_track_publish(const int32_t* __restrict__ count, int32_t* __restrict__ out) { out[0] = *count; }
 
 // per-point classes of every frame of a batch from the per-voxel classes decided on the host
 __global__ void __launch_bounds__(256) k_final_labels(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
@@ -1607,13 +1612,12 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   fa.err = d.scan_counts + (size_t)d.cap_scans * 8;  // one extra int past the per-scan counters
   fa.gc = gc;
   fa.bp = bp;
-  static bool attr_set = false;
   constexpr int kT0 = 1024, kT1 = 4096, kT2 = 16384;
-  if (!attr_set) {
+  static std::once_flag sort_once;
+  std::call_once(sort_once, [] {
     cudaFuncSetAttribute(k_patch_sort<kT1, kT0, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1 * 8);
     cudaFuncSetAttribute(k_patch_sort<kT2, kT1, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2 * 8);
-    attr_set = true;
-  }
+  });
   dim3 gfit(kNumPatches, nscans);
   { TIMED("k_patch_sort_1k", TSTREAM); k_patch_sort<kT0, 0, 128, false><<<gfit, 128, kT0 * 8, st>>>(fa); }
   launches += 1;
@@ -1629,7 +1633,24 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
     { TIMED("k_patch_sort_overflow", TSTREAM); k_patch_sort<0x3fffffff, kT2, 512, true><<<gfit, 512, 0, st>>>(fa); }
     launches += 1;
   }
-  { TIMED("k_patch_chain", TSTREAM); k_patch_chain<<<(kNumPatches * nscans + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, st>>>(fa, nscans); }
+  {
+    // dynamic shared memory is requested only to cap the residency at kChainCtasPerSm CTAs per SM (see the kernel)
+    static int chain_pad = 0;
+    static std::once_flag chain_once;  // several host threads (one context each) may get here at the same time
+    std::call_once(chain_once, [] {
+      int dev = 0, smem_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      cudaFuncAttributes fattr;
+      cudaFuncGetAttributes(&fattr, k_patch_chain);
+      int pad = smem_sm / kChainCtasPerSm - (int)fattr.sharedSizeBytes - 2048;
+      if (pad < 0) pad = 0;
+      cudaFuncSetAttribute(k_patch_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+      chain_pad = pad;
+    });
+    TIMED("k_patch_chain", TSTREAM);
+    k_patch_chain<<<(kNumPatches * nscans + kChainWarps - 1) / kChainWarps, kChainWarps * 32, chain_pad, st>>>(fa, nscans);
+  }
   { TIMED("k_patch_rank", TSTREAM); k_patch_rank<256><<<gfit, 256, 0, st>>>(fa); }
   launches += 2;
   { TIMED("k_patch_out_scan", TSTREAM); k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts); }
@@ -1681,8 +1702,8 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
                  const int4* segs, int nseg, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
-                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* count_dev, int32_t* out_quads_mapped, int cap_quads,
-                 void* stream_) {
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
+                 int cap_quads, void* stream_) {
   if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
   Mat34 T;
@@ -1690,12 +1711,8 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   int blocks = (k + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, (nseg <= kTrackSegSmem ? nseg : 0) * sizeof(int), st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, count_dev); }
-  int blocks2 = (ncl * vn + 255) / 256;
-  if (blocks2 > cap) blocks2 = cap;
-  { TIMED("k_track_compact", TSTREAM); k_track_compact<<<blocks2, 256, 0, st>>>(first, ncl, vn, count_dev, out_quads_mapped, cap_quads); }
-  k_track_publish<<<1, 1, 0, st>>>(count_dev, out_quads_mapped);
-  return 3;
+  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, (nseg <= kTrackSegSmem ? nseg : 0) * sizeof(int), st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
+  return 1;
 }
 
 int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
@@ -1717,11 +1734,8 @@ int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, con
 int launch_name_replay(BatchDev& d, int nscans, int max_vox, int32_t* vox_name, int32_t* name_first, int name_cap, void* stream_) {
   if (nscans <= 0) return 0;
   const size_t smem = (size_t)max_vox * 14 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_name_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
+  static std::once_flag replay_once;
+  std::call_once(replay_once, [] { cudaFuncSetAttribute(k_name_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
   if (smem <= 220 * 1024) {
     { TIMED("k_name_replay", TSTREAM); k_name_replay<false><<<nscans, 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_nbr, nullptr, nullptr, nullptr, nullptr, vox_name, name_first, name_cap); }
   } else {  // very dense scans: union-find state in (L2-resident) global scratch
