@@ -193,7 +193,7 @@ def main():
     params = pkg.semantickitti_params()
     S = args.scans_per_step
     local_world = env_int("LOCAL_WORLD_SIZE", world)
-    W = args.workers if args.workers > 0 else max(1, min(8, (os.cpu_count() or 8) // (2 * max(1, local_world))))
+    W = args.workers if args.workers > 0 else max(1, min(16, (os.cpu_count() or 8) // max(1, local_world)))
     # each rank owns its own sequence chunks (scan-sharding, no data-path collective before the submap merge)
     batches = []
     for b in range(args.pool):
@@ -214,7 +214,7 @@ def main():
             self.stream = torch.cuda.Stream(device=dev)
             self.ssc = pkg.SSC(params, device=local_rank, max_points=RINGS * COLS, max_batch=S)
             self.ssc.set_option("inspect", 0)
-            self.ssc.set_option("host_threads", max(2, (os.cpu_count() or 8) // W))
+            self.ssc.set_option("host_threads", max(1, (os.cpu_count() or 8) // W))
             self.ssc.set_stream(self.stream.cuda_stream)
             self.labels_host = torch.empty(max_pts, dtype=torch.uint8).pin_memory()
             self.submap = torch.empty((max_pts, 4), dtype=torch.float32, device=dev)

@@ -176,12 +176,13 @@ struct scvod_ctx {
   int64_t launches = 0;
   int host_threads = 1;
   bool inspect = true;
+  bool replay_global = false;  // test hook: force the global-memory variant of k_name_replay
 
   BatchDev ws;  // transient workspace (pointers into the DevBufs below and into the current PersistBatch)
   DevBuf<int64_t> d_off;
   DevBuf<int16_t> d_patch_of, d_slot_patch;
   DevBuf<int32_t> d_patch_cnt, d_patch_off, d_patch_cur, d_sorted_idx, d_slot_pos, d_slot_apos, d_slot_vid, d_patch_out,
-      d_patch_out_off, d_scan_counts, d_apri_rank, d_vox_cur, d_vox_pts_tmp, d_vox_nbr, d_vox_root, d_ev_cid, d_edge_buf;
+      d_patch_out_off, d_scan_counts, d_sort_ctr, d_sort_list, d_apri_rank, d_vox_cur, d_vox_pts_tmp, d_vox_nbr, d_vox_root, d_ev_cid, d_edge_buf;
   DevBuf<uint64_t> d_bucket_kv, d_edge_hash;
   DevBuf<float4> d_sorted_xyz;
   DevBuf<float> d_patch_dbg, d_vox_bbox, d_T;
@@ -327,6 +328,8 @@ static int alloc_workspace(scvod_ctx* c) {
   CU(c->d_patch_cnt.alloc(S * kNumPatches));
   CU(c->d_patch_off.alloc(S * (kNumPatches + 1)));
   CU(c->d_patch_cur.alloc(S * kNumPatches));
+  CU(c->d_sort_ctr.alloc(8));
+  CU(c->d_sort_list.alloc(3 * S * kNumPatches));
   CU(c->d_bucket_kv.alloc(P));
   CU(c->d_sorted_xyz.alloc(P));
   CU(c->d_sorted_idx.alloc(P));
@@ -357,6 +360,8 @@ static int alloc_workspace(scvod_ctx* c) {
   w.patch_cnt = c->d_patch_cnt.p;
   w.patch_off = c->d_patch_off.p;
   w.patch_cur = c->d_patch_cur.p;
+  w.sort_ctr = c->d_sort_ctr.p;
+  w.sort_list = c->d_sort_list.p;
   w.bucket_kv = c->d_bucket_kv.p;
   w.sorted_xyz = c->d_sorted_xyz.p;
   w.sorted_idx = c->d_sorted_idx.p;
@@ -422,7 +427,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   for (auto& b : c->batch_pool)
     if (b) b->release();
   c->d_off.release(); c->d_patch_of.release(); c->d_slot_patch.release(); c->d_patch_cnt.release(); c->d_patch_off.release();
-  c->d_patch_cur.release(); c->d_sorted_idx.release(); c->d_slot_pos.release(); c->d_slot_apos.release(); c->d_slot_vid.release();
+  c->d_patch_cur.release(); c->d_sort_ctr.release(); c->d_sort_list.release(); c->d_sorted_idx.release(); c->d_slot_pos.release(); c->d_slot_apos.release(); c->d_slot_vid.release();
   c->d_patch_out.release(); c->d_patch_out_off.release(); c->d_scan_counts.release(); c->d_apri_rank.release(); c->d_vox_cur.release();
   c->d_vox_pts_tmp.release(); c->d_vox_nbr.release(); c->d_vox_root.release(); c->d_ev_cid.release(); c->d_edge_buf.release();
   c->d_bucket_kv.release(); c->d_sorted_xyz.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
@@ -463,6 +468,8 @@ extern "C" int scvod_set_option(scvod_ctx* c, const char* key, int value) {
     c->inspect = value != 0;
   else if (k == "host_threads")
     c->host_threads = std::max(1, value);
+  else if (k == "replay_global")
+    c->replay_global = value != 0;
   else
     return fail(SCVOD_ERR_ARG, "unknown option " + k);
   return SCVOD_OK;
@@ -599,9 +606,12 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
 
   std::chrono::steady_clock::time_point td0 = std::chrono::steady_clock::now();
   // cluster names: one warp per scan replays the reference's sequential naming on the device
-  int max_vox = 1;
-  for (int s = 0; s < nscans; ++s) max_vox = std::max(max_vox, sc[s * 8 + 3]);
-  c->launches += launch_name_replay(w, nscans, max_vox, c->d_vox_name.p, c->d_name_first.p, c->name_cap, st);
+  int max_vox = 1, max_ev = 1;
+  for (int s = 0; s < nscans; ++s) {
+    max_vox = std::max(max_vox, sc[s * 8 + 3]);
+    max_ev = std::max(max_ev, sc[s * 8 + 5]);
+  }
+  c->launches += launch_name_replay(w, nscans, max_vox, max_ev, c->replay_global, c->d_vox_name.p, c->d_name_first.p, c->name_cap, st);
   CU(cudaGetLastError());
   // one packed gather + one D2H for all per-scan tables: [cnt Vt][root Vt][name Vt][bbox 6Vt][name_first Nt][edges 2Gt][max_name S]
   const int64_t Vt = vbase[nscans], Gt = gbase[nscans];
@@ -827,6 +837,9 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       CU(c->d_track_list.alloc((size_t)cap_quads));  // pinned + device-accessible (UVA): the kernel writes the hits straight to the host
       PersistBatch& pbp = *c->batches[pre.batch];
       PersistBatch& pbn = *c->batches[next.batch];
+      *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
+      std::atomic_thread_fence(std::memory_order_release);
+      PROF("    track: enqueue+wait+read");
       CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4), cudaMemcpyHostToDevice, c->stream));
       c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                   reinterpret_cast<const int4*>(c->d_treq.p), (int)si, (int)K, T,
@@ -834,8 +847,35 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
                                   vn, c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads,
                                   c->stream);
       CU(cudaGetLastError());
-      CU(cudaStreamSynchronize(c->stream));
-      int nt = c->h_triples.p[0];
+      // The kernel's last CTA writes the hits and then their count straight into this pinned buffer: poll the count
+      // instead of paying a stream synchronisation per frame pair (stream order still protects every device buffer).
+      int nt;
+      static const bool sync_wait = getenv("SCVOD_TRACK_SYNC") != nullptr;  // A/B switch: stream synchronisation instead of polling
+      if (sync_wait) {
+        PROF("    track: wait (sync)");
+        CU(cudaStreamSynchronize(c->stream));
+        nt = c->h_triples.p[0];
+      } else {
+        PROF("    track: wait (poll)");
+        volatile int32_t* flag = c->h_triples.p;
+        int spins = 0;
+        while ((nt = *flag) < 0) {
+          if (++spins >= 2000) {  // ~every few tens of microseconds: make sure the stream is still alive
+            spins = 0;
+            cudaError_t qe = cudaStreamQuery(c->stream);
+            if (qe == cudaSuccess) {
+              nt = *flag;
+              if (nt < 0) return fail(SCVOD_ERR_CUDA, "k_track finished without publishing its hit count");
+              break;
+            }
+            if (qe != cudaErrorNotReady) return fail(SCVOD_ERR_CUDA, std::string("k_track: ") + cudaGetErrorString(qe));
+          }
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+      }
       if (nt > cap_quads) {  // entries past the list were not reset by the kernel epilogue: wipe the table before giving up
         cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream);
         cudaStreamSynchronize(c->stream);

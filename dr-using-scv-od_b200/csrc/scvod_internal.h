@@ -34,6 +34,8 @@ struct BatchDev {
   int32_t* patch_cnt = nullptr;    // [scans][504]
   int32_t* patch_off = nullptr;    // [scans][505] exclusive (relative to scan base)
   int32_t* patch_cur = nullptr;    // [scans][504] scatter cursors
+  int32_t* sort_ctr = nullptr;     // [3][2]: count, cursor of the worklist of each upper sort tier
+  int32_t* sort_list = nullptr;    // [3][cap_scans*504]: scan*504 + patch of every patch above 1024 points, by tier
   uint64_t* bucket_kv = nullptr;   // per bucket slot: (zkey<<32 | local idx)
   float4* sorted_xyz = nullptr;    // per bucket slot: the point, z-sorted inside its patch (k_patch_sort -> chain / rank)
   int32_t* sorted_idx = nullptr;   // per bucket slot after sort: local point idx
@@ -104,8 +106,10 @@ int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nsca
                         const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream);
 int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,
                   int max_scan_points, float4* out, unsigned long long* counter, long long cap, void* stream);
-// cluster-name replay (one warp per scan); vox_name is indexed like the voxel arrays, name_first is [nscans][name_cap]
-int launch_name_replay(BatchDev& d, int nscans, int max_vox, int32_t* vox_name, int32_t* name_first, int name_cap, void* stream);
+// cluster-name replay (one CTA per scan, components dealt to its warps); vox_name is indexed like the voxel arrays,
+// name_first is [nscans][name_cap]
+int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, bool force_global, int32_t* vox_name, int32_t* name_first, int name_cap,
+                       void* stream);
 int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
 

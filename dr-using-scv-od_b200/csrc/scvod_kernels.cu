@@ -127,9 +127,10 @@ __global__ void __launch_bounds__(256) k_patch_assign(const float4* __restrict__
   }
 }
 
-// G2: exclusive scan over the 504 patch counts of a scan
+// G2: exclusive scan over the 504 patch counts of a scan; patches above 1024 points go on the worklist of their sort tier
 __global__ void __launch_bounds__(512) k_patch_scan(const int32_t* __restrict__ patch_cnt, int32_t* __restrict__ patch_off,
-                                                    int32_t* __restrict__ patch_cur) {
+                                                    int32_t* __restrict__ patch_cur, int32_t* __restrict__ sort_ctr /* [3][2] */,
+                                                    int32_t* __restrict__ sort_list /* [3][list_cap] */, int list_cap) {
   __shared__ int s_w[17];
   const int b = blockIdx.x;
   int v = (threadIdx.x < kNumPatches) ? patch_cnt[b * kNumPatches + threadIdx.x] : 0;
@@ -138,23 +139,47 @@ __global__ void __launch_bounds__(512) k_patch_scan(const int32_t* __restrict__ 
   if (threadIdx.x < kNumPatches) {
     patch_off[b * (kNumPatches + 1) + threadIdx.x] = ex;
     patch_cur[b * kNumPatches + threadIdx.x] = 0;
+    if (v > 1024) {
+      const int tier = (v <= 4096) ? 0 : (v <= 16384) ? 1 : 2;
+      const int slot = atomicAdd(&sort_ctr[2 * tier], 1);
+      sort_list[(size_t)tier * list_cap + slot] = b * kNumPatches + threadIdx.x;
+    }
   }
   if (threadIdx.x == 0) patch_off[b * (kNumPatches + 1) + kNumPatches] = total;
 }
 
-// G3: scatter (z key, local index) into the patch buckets
+// G3: scatter (z key, local index) into the patch buckets.  A CTA owns a contiguous chunk of the scan: it counts its
+// points per patch in shared memory, reserves one range per (CTA, patch) with a single global atomic, and hands out
+// the slots inside the range with shared-memory atomics (the order inside a bucket is irrelevant: it is sorted next).
 __global__ void __launch_bounds__(256) k_patch_scatter(const float4* __restrict__ pts, const int64_t* __restrict__ off,
                                                        const int16_t* __restrict__ patch_of,
                                                        const int32_t* __restrict__ patch_off, int32_t* __restrict__ patch_cur,
                                                        uint64_t* __restrict__ bucket_kv) {
+  __shared__ int s_cnt[kNumPatches];
+  __shared__ int s_base[kNumPatches];
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int n = (int)(off[b + 1] - base);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int pid = patch_of[base + i];
+  const int chunk = (n + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
+  for (int i = threadIdx.x; i < kNumPatches; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const int pid = patch_of[base + i];
+    if (pid >= 0) atomicAdd(&s_cnt[pid], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumPatches; i += blockDim.x) {
+    const int c = s_cnt[i];
+    s_base[i] = c ? patch_off[b * (kNumPatches + 1) + i] + atomicAdd(&patch_cur[b * kNumPatches + i], c) : 0;
+    s_cnt[i] = 0;
+  }
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const int pid = patch_of[base + i];
     if (pid < 0) continue;
-    float z = __ldg(&pts[base + i]).z;
-    int slot = patch_off[b * (kNumPatches + 1) + pid] + atomicAdd(&patch_cur[b * kNumPatches + pid], 1);
+    const float z = __ldg(&pts[base + i]).z;
+    const int slot = s_base[pid] + atomicAdd(&s_cnt[pid], 1);
     bucket_kv[base + slot] = ((uint64_t)float_sort_key(z) << 32) | (uint32_t)i;
   }
 }
@@ -341,26 +366,18 @@ struct FitArgs {
 
 constexpr int kPatchOutStride = 8;  // n_ground_out, n_nonground_out, n_apri, n_quirk, nG, nGP, rejected, -
 
-template <int MAXN, int MINN, int THREADS, bool GLOBAL>
-__global__ void __launch_bounds__(THREADS) k_patch_sort(FitArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int p = blockIdx.x, b = blockIdx.y;
-  const int n = a.patch_cnt[b * kNumPatches + p];
-  if (n <= MINN || n > MAXN) return;
+// tiers of k_patch_sort by patch size: <= 1024 points (direct grid, almost every patch, bitonic network in shared memory),
+// <= 4096 (radix sort in a double-buffered 64 KB shared-memory tile) and above (radix sort through L2).  The patches
+// above 1024 points are put on per-tier worklists by k_patch_scan and sorted by persistent CTAs, instead of launching
+// 504 x scans CTAs per tier that mostly exit at once.
+constexpr int kSortT0 = 1024, kSortT1 = 4096, kSortT2 = 16384;
+
+template <int THREADS, bool GLOBAL>
+__device__ __forceinline__ void sort_one_patch(const FitArgs& a, int p, int b, int n, uint64_t* kv_smem) {
   const int64_t base = a.off[b];
   const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
   const int tid = threadIdx.x;
-  if (n <= kMinPatchPts) {  // patchwork.h:331: the patch vanishes from both outputs
-    for (int j = tid; j < n; j += THREADS) {
-      int idx = (int)(uint32_t)a.bucket_kv[base + slot0 + j];
-      a.cls[base + idx] = SCVOD_PT_DROPPED_SPARSE;
-      a.slot_pos[base + slot0 + j] = (3 << 30);
-      a.slot_patch[base + slot0 + j] = (int16_t)p;
-    }
-    if (tid < kPatchOutStride) a.patch_out[(b * kNumPatches + p) * kPatchOutStride + tid] = 0;
-    return;
-  }
-  uint64_t* kv = GLOBAL ? (a.bucket_kv + base + slot0) : reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* kv = GLOBAL ? (a.bucket_kv + base + slot0) : kv_smem;
   // Bitonic network with a "flip" first step per merge, so every compare-exchange is ascending and the
   // virtual +inf padding above n never moves: indices >= n are simply skipped.  Keys are (z key, index).
   int np2 = 1;
@@ -408,6 +425,174 @@ __global__ void __launch_bounds__(THREADS) k_patch_sort(FitArgs a) {
   }
 }
 
+// lowest tier: one CTA per (patch, scan)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_patch_sort(FitArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = blockIdx.x, b = blockIdx.y;
+  const int n = a.patch_cnt[b * kNumPatches + p];
+  if (n > kSortT0) return;
+  if (n <= kMinPatchPts) {  // patchwork.h:331: the patch vanishes from both outputs
+    const int64_t base = a.off[b];
+    const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+    const int tid = threadIdx.x;
+    for (int j = tid; j < n; j += THREADS) {
+      int idx = (int)(uint32_t)a.bucket_kv[base + slot0 + j];
+      a.cls[base + idx] = SCVOD_PT_DROPPED_SPARSE;
+      a.slot_pos[base + slot0 + j] = (3 << 30);
+      a.slot_patch[base + slot0 + j] = (int16_t)p;
+    }
+    if (tid < kPatchOutStride) a.patch_out[(b * kNumPatches + p) * kPatchOutStride + tid] = 0;
+    return;
+  }
+  sort_one_patch<THREADS, false>(a, p, b, n, reinterpret_cast<uint64_t*>(smem_raw));
+}
+
+// Upper tiers: persistent CTAs pull (scan, patch) items from the tier's worklist and sort them with a stable LSD radix
+// sort on the 32-bit z key (4 passes of 8 bits; 16 B of shared-memory or L2 traffic per element and pass instead of the
+// log^2 n passes of the bitonic network).  Every warp owns a contiguous slice: pass = count digits per (warp, digit),
+// prefix over (digit, warp), then scatter with match_any ranks, which keeps equal digits in slice order.
+// Equal z keys would keep the (arbitrary) bucket order, so a patch that contains a tie is re-sorted by the bitonic
+// network on the full (z key, index) pair: the result is always the order of that pair.
+template <int THREADS>
+__device__ __forceinline__ void radix_sort_kv(uint64_t* bufA, uint64_t* bufB, int n, int* s_cnt /* [THREADS/32][256] */,
+                                              int* s_scan /* THREADS/32 + 1 */) {
+  constexpr int W = THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int slice = (((n + W - 1) / W) + 31) & ~31;
+  const int j_lo = min(n, wid * slice), j_hi = min(n, j_lo + slice);
+  uint64_t* src = bufA;
+  uint64_t* dst = bufB;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 32 + 8 * pass;
+    for (int i = tid; i < W * 256; i += THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    for (int j = j_lo + lane; j < j_hi; j += 32) atomicAdd(&s_cnt[wid * 256 + (int)((src[j] >> shift) & 255u)], 1);
+    __syncthreads();
+    // exclusive prefix in (digit, warp) order: THREADS >= 256, thread d < 256 owns digit d
+    int tot = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const int c = s_cnt[w * 256 + tid];
+        s_cnt[w * 256 + tid] = tot;
+        tot += c;
+      }
+    }
+    int all;
+    const int ex = block_excl_scan<THREADS>(tid < 256 ? tot : 0, &all, s_scan);
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) s_cnt[w * 256 + tid] += ex;
+    }
+    __syncthreads();
+    for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < j_hi;
+      const uint64_t kv = valid ? src[j] : 0ull;
+      const int d = valid ? (int)((kv >> shift) & 255u) : 256 + lane;
+      const unsigned same = __match_any_sync(0xffffffffu, d);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      int basepos = 0;
+      if (valid) basepos = s_cnt[wid * 256 + d];
+      __syncwarp();
+      if (valid) {
+        dst[basepos + rank] = kv;
+        if (rank == 0) s_cnt[wid * 256 + d] = basepos + __popc(same);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    uint64_t* t = src;
+    src = dst;
+    dst = t;
+  }
+  // four passes: the sorted data is back in bufA
+}
+
+template <int THREADS, bool GLOBAL>
+__device__ __forceinline__ void radix_sort_one_patch(const FitArgs& a, int p, int b, int n, unsigned char* smem_raw, int smem_elems) {
+  __shared__ int s_cnt[(THREADS / 32) * 256];
+  __shared__ int s_scan[THREADS / 32 + 1];
+  const int64_t base = a.off[b];
+  const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
+  const int tid = threadIdx.x;
+  uint64_t *bufA, *bufB;
+  if (GLOBAL) {
+    bufA = a.bucket_kv + base + slot0;
+    bufB = reinterpret_cast<uint64_t*>(a.sorted_xyz + base + slot0);  // scratch until the sorted points are written below
+  } else {
+    bufA = reinterpret_cast<uint64_t*>(smem_raw);
+    bufB = bufA + smem_elems;
+    for (int j = tid; j < n; j += THREADS) bufA[j] = a.bucket_kv[base + slot0 + j];
+  }
+  __syncthreads();
+  radix_sort_kv<THREADS>(bufA, bufB, n, s_cnt, s_scan);
+  int tie = 0;
+  for (int j = tid; j + 1 < n; j += THREADS) tie |= ((bufA[j] >> 32) == (bufA[j + 1] >> 32)) ? 1 : 0;
+  if (__syncthreads_or(tie)) {  // rare: equal z inside the patch -> order by (z key, index) with the bitonic network
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+      const int hk = k >> 1;
+      for (int t = tid; t < (np2 >> 1); t += THREADS) {
+        int blk = t / hk, j = t - blk * hk;
+        int i = blk * k + j, l = blk * k + k - 1 - j;
+        if (l < n) {
+          uint64_t x = bufA[i], y = bufA[l];
+          if (x > y) {
+            bufA[i] = y;
+            bufA[l] = x;
+          }
+        }
+      }
+      __syncthreads();
+      for (int s2 = hk >> 1; s2 > 0; s2 >>= 1) {
+        for (int t = tid; t < (np2 >> 1); t += THREADS) {
+          int i = ((t & ~(s2 - 1)) << 1) | (t & (s2 - 1));
+          int l = i | s2;
+          if (l < n) {
+            uint64_t x = bufA[i], y = bufA[l];
+            if (x > y) {
+              bufA[i] = y;
+              bufA[l] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // GLOBAL: the scratch half (bufB) aliases sorted_xyz; after four passes the data is in bufA, so it is free to be written
+  for (int j = tid; j < n; j += THREADS) {
+    const int idx = (int)(uint32_t)bufA[j];
+    float4 q = __ldg(&a.pts[base + idx]);
+    q.w = 0.f;
+    a.sorted_xyz[base + slot0 + j] = q;
+    a.sorted_idx[base + slot0 + j] = idx;
+    a.slot_patch[base + slot0 + j] = (int16_t)p;
+  }
+}
+
+template <int THREADS, bool GLOBAL>
+__global__ void __launch_bounds__(THREADS) k_patch_sort_list(FitArgs a, const int32_t* __restrict__ list, int32_t* __restrict__ ctr /* [0] count, [1] cursor */,
+                                                             int smem_elems) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_item;
+  const int count = ctr[0];
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&ctr[1], 1);
+    __syncthreads();
+    const int it = s_item;
+    __syncthreads();
+    if (it >= count) break;
+    const int g = list[it];
+    const int b = g / kNumPatches, p = g - b * kNumPatches;
+    radix_sort_one_patch<THREADS, GLOBAL>(a, p, b, a.patch_cnt[g], smem_raw, smem_elems);
+    __syncthreads();
+  }
+}
+
 constexpr int kChainWarps = 4;    // warps (= patches) per CTA of k_patch_chain
 constexpr int kChainStages = 4;   // cp.async ring depth, 32 points per stage
 constexpr int kChainCtasPerSm = 2;  // residency cap: the chain is latency bound, so few warps per scheduler keep the
@@ -416,16 +601,33 @@ constexpr int kChainCtasPerSm = 2;  // residency cap: the chain is latency bound
 // smallest float >= d: for a float z, ((double)z < d) == (z < float_at_or_above(d))
 __device__ __forceinline__ float float_at_or_above(double d) { return __double2float_ru(d); }
 
-__global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int nscans) {
+__global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int nscans, const int32_t* __restrict__ sort_list,
+                                                                  int32_t* __restrict__ sort_ctr, int list_cap) {
   __shared__ float4 s_ring[kChainWarps][kChainStages][32];
   __shared__ float s_prod[kChainWarps][2][32 * 9];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int g = blockIdx.x * kChainWarps + wid;
-  if (g >= kNumPatches * nscans) return;
-  // zone-0 patches (the largest) are handed out first so that the long chains start early
-  const int p = g / nscans, b = g - p * nscans;
+  // Persistent warps pull patches from one queue, longest chains first: the worklists of the sort tiers (above 16384,
+  // above 4096, above 1024 points), then every remaining (patch, scan) in patch-major order (zone 0 = the largest first).
+  const int c2 = sort_ctr[4], c1 = sort_ctr[2], c0 = sort_ctr[0];
+  const int n_listed = c2 + c1 + c0;
+  const int n_items = n_listed + kNumPatches * nscans;
+  for (;;) {
+  int item = 0;
+  if (lane == 0) item = atomicAdd(&sort_ctr[6], 1);
+  item = __shfl_sync(0xffffffffu, item, 0);
+  if (item >= n_items) break;
+  int p, b;
+  if (item < n_listed) {
+    const int g = (item < c2) ? sort_list[2 * (size_t)list_cap + item] : (item < c2 + c1) ? sort_list[(size_t)list_cap + item - c2] : sort_list[item - c2 - c1];
+    b = g / kNumPatches;
+    p = g - b * kNumPatches;
+  } else {
+    const int g = item - n_listed;
+    p = g / nscans;
+    b = g - p * nscans;
+  }
   const int n = a.patch_cnt[b * kNumPatches + p];
-  if (n <= kMinPatchPts) return;
+  if (n <= kMinPatchPts || (item >= n_listed && n > kSortT0)) continue;
   const int64_t base = a.off[b];
   const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
   const float4* __restrict__ S = a.sorted_xyz + base + slot0;
@@ -572,6 +774,8 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
     rec[10] = (float)decision;
     rec[11] = (float)n;
   }
+  __syncwarp();
+  }  // queue loop
 }
 
 constexpr uint32_t F_G = 1u;      // final ground set
@@ -829,6 +1033,11 @@ __global__ void __launch_bounds__(256) k_vox_fill(const int64_t* __restrict__ of
 // One warp per voxel: order the voxel's points by m (rank by counting), then the strictly sequential
 // float intensity mean / population variance of ssc.cpp:261-287, voxel "centre" (:271-277), the index
 // triple of the first inserted point (:268-270) and the voxel's bounding box.
+// The sums are order dependent, so they stay a chain of dependent adds — but only the adds: the intensities are
+// staged in m order (shared memory, or the freshly written CSR for very full voxels), read 32 at a time by the
+// whole warp and fed to the chain with shuffles, so no memory latency sits on the dependent path.
+constexpr int kVoxStage = 512;  // intensities staged in shared memory per warp
+
 __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
                                                    const int32_t* __restrict__ vox_cnt, const int32_t* __restrict__ vox_off,
                                                    const int32_t* __restrict__ vox_pts_tmp, const float4* __restrict__ apri_xyzi,
@@ -836,15 +1045,25 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
                                                    int32_t* __restrict__ apri_rank, float* __restrict__ vox_av,
                                                    float* __restrict__ vox_cov, float* __restrict__ vox_center,
                                                    int32_t* __restrict__ vox_tri, float* __restrict__ vox_bbox) {
+  __shared__ float s_val[8][kVoxStage];
+  __shared__ int s_seg[8][kVoxStage];
+  __shared__ float4 s_first[8];
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int V = scan_counts[b * 8 + 3];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
+  float* sv = s_val[wid];
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
     const int k = vox_cnt[base + v];
     const int o = vox_off[base + v];
     const int32_t* seg = vox_pts_tmp + base + o;
+    const bool staged = k <= kVoxStage;
+    if (staged) {
+      for (int e = lane; e < k; e += 32) s_seg[wid][e] = seg[e];
+      __syncwarp();
+      seg = s_seg[wid];
+    }
     float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
     for (int e = lane; e < k; e += 32) {
       int me = seg[e];
@@ -853,6 +1072,8 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
       vox_pts[base + o + r] = me;
       apri_rank[base + me] = r;
       float4 q = __ldg(&apri_xyzi[base + me]);
+      if (staged) sv[r] = q.w;
+      if (r == 0) s_first[wid] = q;
       lo[0] = fminf(lo[0], q.x);
       lo[1] = fminf(lo[1], q.y);
       lo[2] = fminf(lo[2], q.z);
@@ -867,22 +1088,30 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
         lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
         hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
       }
-    __syncwarp();
     __threadfence_block();
+    __syncwarp();
+    const int32_t* srt = vox_pts + base + o;
+    auto value_at = [&](int e) { return staged ? sv[e] : apri_xyzi[base + srt[e]].w; };
+    float sum = 0.f;  // every lane runs the same chain: no broadcast at the end
+    for (int e0 = 0; e0 < k; e0 += 32) {
+      const float mine = (e0 + lane < k) ? value_at(e0 + lane) : 0.f;
+      const int m = min(32, k - e0);
+      for (int t = 0; t < m; ++t) sum = da(sum, __shfl_sync(0xffffffffu, mine, t));
+    }
+    const float av = dd(sum, (float)k);
+    float cov = 0.f;
+    for (int e0 = 0; e0 < k; e0 += 32) {
+      const float mine = (e0 + lane < k) ? value_at(e0 + lane) : 0.f;
+      const float dlt = ds(mine, av);
+      const double sq = __dmul_rn((double)dlt, (double)dlt);  // std::pow(in - av, 2) in double (ssc.cpp:285)
+      const int m = min(32, k - e0);
+      for (int t = 0; t < m; ++t) cov = (float)__dadd_rn((double)cov, __shfl_sync(0xffffffffu, sq, t));
+    }
+    cov = dd(cov, (float)k);
     if (lane == 0) {
-      const int32_t* srt = vox_pts + base + o;
-      float sum = 0.f;
-      for (int e = 0; e < k; ++e) sum = da(sum, apri_xyzi[base + srt[e]].w);
-      float av = dd(sum, (float)k);
-      float cov = 0.f;
-      for (int e = 0; e < k; ++e) {
-        float dlt = ds(apri_xyzi[base + srt[e]].w, av);
-        cov = (float)__dadd_rn((double)cov, __dmul_rn((double)dlt, (double)dlt));
-      }
-      cov = dd(cov, (float)k);
       vox_av[base + v] = av;
       vox_cov[base + v] = cov;
-      float4 q0 = apri_xyzi[base + srt[0]];
+      const float4 q0 = s_first[wid];
       BinResult r = dev_bin_point(q0.x, q0.y, q0.z, bp);
       vox_tri[3 * (base + v) + 0] = r.ri;
       vox_tri[3 * (base + v) + 1] = r.si;
@@ -899,6 +1128,7 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
         vox_bbox[6 * (base + v) + 3 + d] = hi[d];
       }
     }
+    __syncwarp();
   }
 }
 
@@ -985,7 +1215,9 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(const int64_t* __restrict__
 }
 
 // directed component edges (root(v) -> root(n)) for every voxel pair that satisfies the intensity
-// similarity test of refineClusterByIntensity (ssc.cpp:588-594); self pairs included.
+// similarity test of refineClusterByIntensity (ssc.cpp:588-594); self pairs included.  One warp per voxel:
+// the lanes share the up to 125 neighbour lookups (two dependent L2 loads each), duplicates inside a round are
+// dropped with match_any, the rest by the per-scan hash set.
 __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts, GridSpec g,
                                                        const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
                                                        const int32_t* __restrict__ vox_tri, const float* __restrict__ vox_av,
@@ -999,48 +1231,47 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
   const uint32_t* bm = bitmap + (size_t)b * g.words;
   const int32_t* wr = word_rank + (size_t)b * g.words;
   unsigned long long* table = edge_hash + (size_t)b * hash_cap;
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-    int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
-    int size = ((double)ri > (double)g.range_num * 0.6) ? 1 : search_c;  // ssc.cpp:397-399
-    float avv = vox_av[base + v];
-    int rv = vox_root[base + v];
-    int last = -1;
-    for (int x = ri - size; x <= ri + size; ++x) {
-      if (x > g.range_num - 1 || x < 0) continue;
-      for (int y = si - size; y <= si + size; ++y) {
-        if (y > g.sector_num - 1 || y < 0) continue;
-        for (int z = ei - size; z <= ei + size; ++z) {
-          if (z > g.azimuth_num - 1 || z < 0) continue;
-          int u = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
-          if (u < 0) continue;
-          if (vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) {
-            int ru = vox_root[base + u];
-            if (ru == last) continue;
-            last = ru;
-            unsigned long long key = ((unsigned long long)(uint32_t)rv << 32) | (uint32_t)ru;
-            unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
-            int slot = (int)(h >> 40) % hash_cap;
-            bool inserted = false, done = false;
-            for (int probe = 0; probe < hash_cap && !done; ++probe) {
-              unsigned long long old = atomicCAS(&table[slot], ~0ull, key);
-              if (old == ~0ull) {
-                inserted = true;
-                done = true;
-              } else if (old == key) {
-                done = true;
-              } else {
-                slot = (slot + 1 == hash_cap) ? 0 : slot + 1;
-              }
-            }
-            if (!done) atomicExch(&scan_counts[b * 8 + 7], -1 << 20);  // table full
-            if (inserted) {
-              int e = atomicAdd(&scan_counts[b * 8 + 7], 1);
-              if (e >= 0 && e < edge_cap) {
-                edge_buf[((size_t)b * edge_cap + e) * 2] = rv;
-                edge_buf[((size_t)b * edge_cap + e) * 2 + 1] = ru;
-              }
-            }
-          }
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+    const int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
+    const int size = ((double)ri > (double)g.range_num * 0.6) ? 1 : search_c;  // ssc.cpp:397-399
+    const int side = 2 * size + 1, total = side * side * side;
+    const float avv = vox_av[base + v];
+    const int rv = vox_root[base + v];
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      int ru = -1;
+      if (t < total) {
+        const int x = ri - size + t / (side * side), y = si - size + (t / side) % side, z = ei - size + t % side;
+        if (!(x > g.range_num - 1 || x < 0 || y > g.sector_num - 1 || y < 0 || z > g.azimuth_num - 1 || z < 0)) {
+          const int u = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
+          if (u >= 0 && vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) ru = vox_root[base + u];
+        }
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, ru);
+      if (ru < 0 || (same & ((1u << lane) - 1u))) continue;  // nothing, or a lower lane inserts this root
+      unsigned long long key = ((unsigned long long)(uint32_t)rv << 32) | (uint32_t)ru;
+      unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
+      int slot = (int)(h >> 40) % hash_cap;
+      bool inserted = false, done = false;
+      for (int probe = 0; probe < hash_cap && !done; ++probe) {
+        unsigned long long old = atomicCAS(&table[slot], ~0ull, key);
+        if (old == ~0ull) {
+          inserted = true;
+          done = true;
+        } else if (old == key) {
+          done = true;
+        } else {
+          slot = (slot + 1 == hash_cap) ? 0 : slot + 1;
+        }
+      }
+      if (!done) atomicExch(&scan_counts[b * 8 + 7], -1 << 20);  // table full
+      if (inserted) {
+        int e = atomicAdd(&scan_counts[b * 8 + 7], 1);
+        if (e >= 0 && e < edge_cap) {
+          edge_buf[((size_t)b * edge_cap + e) * 2] = rv;
+          edge_buf[((size_t)b * edge_cap + e) * 2 + 1] = ru;
         }
       }
     }
@@ -1048,7 +1279,7 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cluster names of SSC::clusterAndCreateFrame (ssc.cpp:299-354) replayed on the device, one warp per scan.
+// Cluster names of SSC::clusterAndCreateFrame (ssc.cpp:299-354) replayed on the device.
 //
 // The reference walks the apri points in order and propagates names through the <=27 voxels around each
 // point (oc/nc rules of :323-351, mergeClusters :413-419 renames the current point's cluster to the
@@ -1063,42 +1294,191 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
 //     first three points of a voxel can find it unstable: those are the events (k_events).
 // One event = one warp step: lane k owns neighbour k (findVoxelNeighbors order), union-find with path
 // halving lives in shared memory, the order-dependent part is resolved with ballot / match_any.
+//
+// Parallelism.  An event only touches voxels of its own 26-connected component (k_ccl_*), so components
+// replay independently; the single coupling is the name counter (:345-346), and the k-th "new class" event
+// of the scan in event order simply gets name 5 + k.  One CTA per scan therefore
+//   A. counts the events of every component, deals the components to its NW warps (largest first to the
+//      least loaded warp, the many small ones by water-filling) ...
+//   B. ... and splits the ordered event list into one ordered list per warp (stable partition);
+//   C. every warp replays its own list; a new class records its creating event instead of a number;
+//   D. names = 5 + rank of the creating event among all creating events (popcount prefix over a bit per event).
 // ------------------------------------------------------------------------------------------------
-template <bool GLOBAL>
-__global__ void __launch_bounds__(32) k_name_replay(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
-                                                    const int32_t* __restrict__ ev_cid, const int32_t* __restrict__ vox_nbr,
-                                                    int32_t* __restrict__ g_parent, int32_t* __restrict__ g_setname,
-                                                    int32_t* __restrict__ g_first, int32_t* __restrict__ g_state,
-                                                    int32_t* __restrict__ vox_name, int32_t* __restrict__ name_first, int name_cap) {
+constexpr int kReplayWarps = 8;  // warps per scan: components are dealt to them by event count
+constexpr int kReplayRows = 32;   // events per chunk; neighbour rows of the next chunk are prefetched while one is replayed
+
+template <int NW, bool GLOBAL>
+__global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
+                                                         const int32_t* __restrict__ ev_cid, const int32_t* __restrict__ vox_root,
+                                                         const int32_t* __restrict__ vox_nbr, int2* __restrict__ ev_list,
+                                                         int32_t* __restrict__ g_parent, int32_t* __restrict__ g_setname,
+                                                         int32_t* __restrict__ g_first, int32_t* __restrict__ g_state,
+                                                         int32_t* __restrict__ g_flags, int32_t* __restrict__ vox_name,
+                                                         int32_t* __restrict__ name_first, int name_cap) {
+  constexpr int T = NW * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_scan[T / 32 + 1];
+  __shared__ int s_load[NW], s_lbase[NW + 1], s_cursor[NW], s_free[NW + 1];
+  __shared__ int s_wcnt[NW][NW];
+  __shared__ int s_big[32], s_nbig, s_target;
   const int b = blockIdx.x;
   const int64_t base = off[b];
   const int V = scan_counts[b * 8 + 3];
   const int E = scan_counts[b * 8 + 5];
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nfw = (E + 31) >> 5;  // one "new class" bit per event
+  // dynamic shared memory: [neighbour-row ring NW x 2 x 32 x 32 ints][union-find state 14 B / voxel][flags + prefix]
+  int(*ring)[kReplayRows][32] = reinterpret_cast<int(*)[kReplayRows][32]>(smem_raw) + 2 * wid;
+  unsigned char* sm_state = smem_raw + sizeof(int) * NW * 2 * kReplayRows * 32;
   int32_t *parent, *setname, *first_ev;
   uint8_t *state, *stable;
+  uint32_t* flags;
+  int32_t* fprefix;
   if (GLOBAL) {
     parent = g_parent + base;
     setname = g_setname + base;
     first_ev = g_first + base;
     state = reinterpret_cast<uint8_t*>(g_state + base);
     stable = state + V;  // g_state has 4 bytes per voxel
+    flags = reinterpret_cast<uint32_t*>(g_flags + base);  // E <= M <= N ints available: nfw flags, then nfw prefixes
+    fprefix = g_flags + base + nfw;
   } else {
-    parent = reinterpret_cast<int32_t*>(smem_raw);
+    parent = reinterpret_cast<int32_t*>(sm_state);
     setname = parent + V;
     first_ev = setname + V;
-    state = reinterpret_cast<uint8_t*>(first_ev + V);
+    flags = reinterpret_cast<uint32_t*>(first_ev + V);
+    fprefix = reinterpret_cast<int32_t*>(flags + nfw);
+    state = reinterpret_cast<uint8_t*>(fprefix + nfw);
     stable = state + V;
   }
-  for (int v = lane; v < V; v += 32) {
+  const int32_t* ev = ev_cid + base;
+  const int32_t* root = vox_root + base;
+  const int32_t* nbr = vox_nbr + 27 * base;
+  int2* lst = ev_list + base;
+
+  // ---- A. events per component (cnt lives in parent[], the owner warp of a root in state[]) ---------------
+  int32_t* cnt = parent;
+  uint8_t* owner = state;
+  for (int v = tid; v < V; v += T) cnt[v] = 0;
+  if (tid < NW) {
+    s_load[tid] = 0;
+    s_cursor[tid] = 0;
+  }
+  if (tid == 0) s_nbig = 0;
+  __syncthreads();
+  for (int e = tid; e < E; e += T) atomicAdd(&cnt[root[ev[e]]], 1);
+  __syncthreads();
+  const int thr = E / (4 * NW) + 1;  // fewer than 4 * NW <= 32 components can be this large
+  for (int v = tid; v < V; v += T)
+    if (cnt[v] >= thr) s_big[atomicAdd(&s_nbig, 1)] = v;
+  __syncthreads();
+  if (wid == 0) {  // largest first to the least loaded warp; lane w < NW keeps the load of warp w
+    const int nbig = s_nbig;
+    const int my_root = lane < nbig ? s_big[lane] : -1;
+    int my_cnt = lane < nbig ? cnt[my_root] : -1;
+    int load = 0;
+    for (int it = 0; it < nbig; ++it) {
+      int best = (my_cnt << 5) | (31 - lane);  // max count, ties to the lowest lane
+      if (my_cnt < 0) best = -1;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, s));
+      const int src = 31 - (best & 31), c = best >> 5;
+      int least = lane < NW ? ((load << 5) | lane) : 0x7fffffff;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) least = min(least, __shfl_xor_sync(0xffffffffu, least, s));
+      const int w = least & 31;
+      if (lane == w) load += c;
+      if (lane == src) {
+        owner[my_root] = (uint8_t)w;
+        my_cnt = -1;
+      }
+    }
+    // water level for the small components: nobody above max(largest load, ceil(E / NW))
+    int mx = lane < NW ? load : 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    const int target = max(mx, (E + NW - 1) / NW);
+    const int fr = lane < NW ? target - load : 0;
+    const int inc = warp_incl_scan(fr);
+    if (lane < NW) s_free[lane + 1] = inc;
+    if (lane == 0) {
+      s_free[0] = 0;
+      s_target = target;
+    }
+  }
+  __syncthreads();
+  {
+    int carry = 0;
+    for (int v0 = 0; v0 < V; v0 += T) {
+      const int v = v0 + tid;
+      const int c = (v < V) ? cnt[v] : 0;
+      const bool small = c > 0 && c < thr;
+      int total;
+      const int ex = block_excl_scan<T>(small ? c : 0, &total, s_scan);
+      if (small) {
+        const int pos = carry + ex;
+        int w = 0;
+#pragma unroll
+        for (int k = 1; k < NW; ++k) w += (s_free[k] <= pos) ? 1 : 0;  // last warp whose free range starts at or before pos
+        owner[v] = (uint8_t)w;
+      }
+      carry += total;
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += T) {
+    const int c = cnt[v];
+    if (c > 0) atomicAdd(&s_load[owner[v]], c);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < NW; ++w) {
+      s_lbase[w] = run;
+      run += s_load[w];
+    }
+    s_lbase[NW] = run;
+  }
+  __syncthreads();
+  // ---- B. stable partition of the event list by owner warp ---------------------------------------------------
+  for (int e0 = 0; e0 < E; e0 += T) {
+    const int e = e0 + tid;
+    int cid = -1, own = -1 - lane;  // idle lanes match nobody
+    if (e < E) {
+      cid = ev[e];
+      own = owner[root[cid]];
+    }
+    if (lane < NW) s_wcnt[wid][lane] = 0;
+    __syncwarp();
+    const unsigned same = __match_any_sync(0xffffffffu, own);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    if (own >= 0 && rank == 0) s_wcnt[wid][own] = __popc(same);
+    __syncthreads();
+    if (tid < NW) {
+      int run = s_cursor[tid];
+      for (int w = 0; w < NW; ++w) {
+        const int c = s_wcnt[w][tid];
+        s_wcnt[w][tid] = run;
+        run += c;
+      }
+      s_cursor[tid] = run;
+    }
+    __syncthreads();
+    if (own >= 0) lst[s_lbase[own] + s_wcnt[wid][own] + rank] = make_int2(e, cid);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- C. replay ------------------------------------------------------------------------------------------------
+  for (int v = tid; v < V; v += T) {
     parent[v] = v;
     setname[v] = -1;
     first_ev[v] = 0x7fffffff;
     state[v] = 0;
     stable[v] = 0;
   }
-  __syncwarp();
+  for (int w = tid; w < nfw; w += T) flags[w] = 0u;
+  __threadfence_block();
+  __syncthreads();
   auto find = [&](int v) {
     int r = v;
     while (true) {
@@ -1110,111 +1490,135 @@ __global__ void __launch_bounds__(32) k_name_replay(const int64_t* __restrict__ 
     }
     return r;
   };
-  int cluster_name = 4;  // ssc.cpp:300
-  const int32_t* ev = ev_cid + base;
-  const int32_t* nbr = vox_nbr + 27 * base;
-  // Neighbour rows are fetched kLook events ahead with cp.async into a small shared-memory ring, so the L2
-  // latency of a row hides behind the union-find work of the events in between.  A row is only requested
-  // when its voxel is not yet stable (stable never resets): the common no-op events never touch global memory.
-  constexpr int kLook = 8;
-  __shared__ int s_ring[kLook][32];
-  // events are read 32 at a time (one coalesced load per chunk); chA holds the chunk of event e, chB the next one
-  int chA = (lane < E) ? ev[lane] : 0;
-  int chB = (32 + lane < E) ? ev[32 + lane] : 0;
-  auto event_at = [&](int e2, int e_cur) {  // e2 is in the chunk of e_cur or in the next one
-    return ((e2 >> 5) == (e_cur >> 5)) ? __shfl_sync(0xffffffffu, chA, e2 & 31) : __shfl_sync(0xffffffffu, chB, e2 & 31);
-  };
-  auto issue = [&](int e2, int e_cur) {
-    if (e2 < E) {
-      const int W2 = event_at(e2, e_cur);
-      if (!stable[W2] && lane < 27) {
-        unsigned dst = (unsigned)__cvta_generic_to_shared(&s_ring[e2 % kLook][lane]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(nbr + 27 * (size_t)W2 + lane));
+  {
+    const int L = s_load[wid];
+    const int2* my = lst + s_lbase[wid];
+    // Neighbour rows (27 ints, L2 resident) are fetched one chunk of 32 events ahead with cp.async, and only for
+    // voxels that are not yet stable (stable never resets): the common no-op events never touch global memory.
+    auto prefetch = [&](const int2 evn, int buf) {
+      const bool need = evn.y >= 0 && !stable[evn.y];
+      unsigned pm = __ballot_sync(0xffffffffu, need);
+      while (pm) {
+        const int j = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const int Wj = __shfl_sync(0xffffffffu, evn.y, j);
+        if (lane < 27) {
+          unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[buf][j][lane]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(nbr + 27 * (size_t)Wj + lane));
+        }
       }
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-  for (int e2 = 0; e2 < kLook; ++e2) issue(e2, 0);
-  for (int e = 0; e < E; ++e) {
-    if (e > 0 && (e & 31) == 0) {
-      chA = chB;
-      chB = (e + 32 + lane < E) ? ev[e + 32 + lane] : 0;
-    }
-    const int W = __shfl_sync(0xffffffffu, chA, e & 31);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(kLook - 1));
-    __syncwarp();
-    int Vn = (lane < 27) ? s_ring[e % kLook][lane] : -1;
-    const bool was_stable = stable[W];
-    __syncwarp();
-    issue(e + kLook, e);  // reuses the ring slot that was just read
-    if (lane == 0 && first_ev[W] == 0x7fffffff) first_ev[W] = e;
-    if (was_stable) continue;  // warp-uniform
-    const bool exist = Vn >= 0;
-    const int st = exist ? state[Vn] : 0;
-    const bool lab = exist && st != 0;
-    const int r = lab ? find(Vn) : -1;
-    const bool labelled = (state[W] == 2);
-    const int oc0 = labelled ? find(W) : -1;
-    __syncwarp();
-    const unsigned lab_mask = __ballot_sync(0xffffffffu, lab);
-    const unsigned unl_mask = __ballot_sync(0xffffffffu, exist && !lab);
-    if (!labelled && lab_mask == 0u) {  // a new class (:345-351)
-      ++cluster_name;
-      if (lane == 0) {
-        parent[W] = W;
-        setname[W] = cluster_name;
-        state[W] = 2;
-        stable[W] = 1;
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    int2 nxt = (lane < L) ? my[lane] : make_int2(0, -1);
+    prefetch(nxt, 0);
+    for (int c = 0; c * 32 < L; ++c) {
+      const int2 cur = nxt;
+      const int j1 = (c + 1) * 32 + lane;
+      nxt = (j1 < L) ? my[j1] : make_int2(0, -1);
+      prefetch(nxt, (c + 1) & 1);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+      __syncwarp();
+      unsigned pend = __ballot_sync(0xffffffffu, cur.y >= 0 && !stable[cur.y]);
+      while (pend) {
+        const int i = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const int W = __shfl_sync(0xffffffffu, cur.y, i);
+        const int e = __shfl_sync(0xffffffffu, cur.x, i);
+        if (stable[W]) continue;  // became stable inside this chunk (warp-uniform)
+        const int Vn = (lane < 27) ? ring[c & 1][i][lane] : -1;
+        if (lane == 0 && first_ev[W] == 0x7fffffff) first_ev[W] = e;
+        const bool exist = Vn >= 0;
+        const int st = exist ? state[Vn] : 0;
+        const bool lab = exist && st != 0;
+        const int r = lab ? find(Vn) : -1;
+        const bool labelled = (state[W] == 2);
+        const int oc0 = labelled ? find(W) : -1;
+        __syncwarp();
+        const unsigned lab_mask = __ballot_sync(0xffffffffu, lab);
+        const unsigned unl_mask = __ballot_sync(0xffffffffu, exist && !lab);
+        if (!labelled && lab_mask == 0u) {  // a new class (:345-351): named after the creating event, numbered in D
+          if (lane == 0) {
+            atomicOr(&flags[e >> 5], 1u << (e & 31));
+            parent[W] = W;
+            setname[W] = e;
+            state[W] = 2;
+            stable[W] = 1;
+          }
+          __syncwarp();
+          if (exist && Vn != W) {
+            parent[Vn] = W;
+            state[Vn] = 2;
+          }
+          __syncwarp();
+          continue;
+        }
+        // roots met for the first time, in visit order (a root equal to oc0 was "met" before the loop)
+        const unsigned same = __match_any_sync(0xffffffffu, lab ? r : (-2 - lane));
+        const bool first_occ = lab && (r != oc0) && ((same & ((1u << lane) - 1u)) == 0u);
+        const unsigned fo_mask = __ballot_sync(0xffffffffu, first_occ);
+        int f;  // surviving root: the last first-met set (mergeClusters renames oc to nc each time)
+        if (fo_mask) {
+          f = __shfl_sync(0xffffffffu, r, 31 - __clz(fo_mask));
+        } else {
+          f = oc0;
+        }
+        const int p = labelled ? -1 : (__ffs(lab_mask) - 1);  // position where the visitor becomes labelled
+        if (first_occ && r != f) parent[r] = f;
+        if (lane == 0 && labelled && oc0 != f) parent[oc0] = f;
+        __syncwarp();
+        if (lab) state[Vn] = 2;
+        const bool take = exist && !lab && lane > p;  // unlabelled voxels met after the visitor got its label (:338)
+        if (take) {
+          parent[Vn] = f;
+          state[Vn] = 2;
+        }
+        const unsigned skipped = unl_mask & ((p >= 0) ? ((1u << p) - 1u) : 0u);
+        __syncwarp();
+        if (lane == 0) {
+          if (state[W] == 0) {  // only this (first) point of W got the label
+            state[W] = 1;
+            parent[W] = f;
+          }
+          stable[W] = skipped ? 0 : 1;
+        }
+        __syncwarp();
       }
       __syncwarp();
-      if (exist && Vn != W) {
-        parent[Vn] = W;
-        state[Vn] = 2;
-      }
-      __syncwarp();
-      continue;
     }
-    // roots met for the first time, in visit order (a root equal to oc0 was "met" before the loop)
-    const unsigned same = __match_any_sync(0xffffffffu, lab ? r : (-2 - lane));
-    const bool first_occ = lab && (r != oc0) && ((same & ((1u << lane) - 1u)) == 0u);
-    const unsigned fo_mask = __ballot_sync(0xffffffffu, first_occ);
-    int f;  // surviving root: the last first-met set (mergeClusters renames oc to nc each time)
-    if (fo_mask) {
-      f = __shfl_sync(0xffffffffu, r, 31 - __clz(fo_mask));
-    } else {
-      f = oc0;
-    }
-    const int p = labelled ? -1 : (__ffs(lab_mask) - 1);  // position where the visitor becomes labelled
-    if (first_occ && r != f) parent[r] = f;
-    if (lane == 0 && labelled && oc0 != f) parent[oc0] = f;
-    __syncwarp();
-    if (lab) state[Vn] = 2;
-    const bool take = exist && !lab && lane > p;  // unlabelled voxels met after the visitor got its label (:338)
-    if (take) {
-      parent[Vn] = f;
-      state[Vn] = 2;
-    }
-    const unsigned skipped = unl_mask & ((p >= 0) ? ((1u << p) - 1u) : 0u);
-    __syncwarp();
-    if (lane == 0) {
-      if (state[W] == 0) {  // only this (first) point of W got the label
-        state[W] = 1;
-        parent[W] = f;
-      }
-      stable[W] = skipped ? 0 : 1;
-    }
-    __syncwarp();
+    asm volatile("cp.async.wait_group 0;\n" ::);
   }
+  __threadfence_block();
+  __syncthreads();
+  // ---- D. numbers: the k-th creating event (in event order) is name 5 + k (cluster_name starts at 4, :300) ----
+  int n_names;
+  {
+    int carry = 0;
+    for (int w0 = 0; w0 < nfw; w0 += T) {
+      const int w = w0 + tid;
+      const int c = (w < nfw) ? __popc(flags[w]) : 0;
+      int total;
+      const int ex = block_excl_scan<T>(c, &total, s_scan);
+      if (w < nfw) fprefix[w] = carry + ex;
+      carry += total;
+    }
+    n_names = carry;
+  }
+  __syncthreads();
+  const int cluster_name = 4 + n_names;
   // final names + first point (event) of every name, which fixes the insertion order of cluster_pt (:360-375)
   int32_t* nf = name_first + (size_t)b * name_cap;
-  for (int i = lane; i <= cluster_name && i < name_cap; i += 32) nf[i] = 0x7fffffff;
-  __syncwarp();
-  for (int v = lane; v < V; v += 32) {
-    int nm = setname[find(v)];
+  for (int i = tid; i <= cluster_name && i < name_cap; i += T) nf[i] = 0x7fffffff;
+  __syncthreads();
+  for (int v = tid; v < V; v += T) {
+    int r = v;  // read-only walk: other threads resolve voxels of the same component at the same time
+    while (parent[r] != r) r = parent[r];
+    const int ec = setname[r];
+    int nm = -1;
+    if (ec >= 0) nm = 5 + fprefix[ec >> 5] + __popc(flags[ec >> 5] & ((1u << (ec & 31)) - 1u));
     vox_name[base + v] = nm;
     if (nm >= 0 && nm < name_cap) atomicMin(&nf[nm], first_ev[v]);
   }
-  if (lane == 0) scan_counts[b * 8 + 6] = cluster_name;
+  if (tid == 0) scan_counts[b * 8 + 6] = cluster_name;
 }
 
 // ordered compaction of the apri points whose rank inside their voxel is < 3 ("clustering events")
@@ -1332,17 +1736,36 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
   __threadfence();
   const int nh = *reinterpret_cast<volatile int32_t*>(&ctr[0]);
   const int take = min(nh, cap_quads);
-  for (int t = threadIdx.x; t < take; t += blockDim.x) {
-    const int e = hit_list[t];
-    const unsigned long long f = first[e];
-    first[e] = ~0ull;
-    reinterpret_cast<int4*>(out_quads + 4)[t] = make_int4(e / vn, e % vn, (int)(unsigned)(f >> 32), (int)(unsigned)(f & 0xffffffffu));
+  // several independent entries per thread and round: the three dependent accesses (list -> table -> host) overlap
+  constexpr int kEpi = 8;
+  for (int t0 = 0; t0 < take; t0 += 256 * kEpi) {
+    int e[kEpi];
+    unsigned long long f[kEpi];
+#pragma unroll
+    for (int u = 0; u < kEpi; ++u) {
+      const int t = t0 + u * 256 + threadIdx.x;
+      e[u] = (t < take) ? hit_list[t] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kEpi; ++u) f[u] = (e[u] >= 0) ? first[e[u]] : 0ull;
+#pragma unroll
+    for (int u = 0; u < kEpi; ++u) {
+      const int t = t0 + u * 256 + threadIdx.x;
+      if (e[u] >= 0) {
+        first[e[u]] = ~0ull;
+        reinterpret_cast<int4*>(out_quads + 4)[t] =
+            make_int4(e[u] / vn, e[u] % vn, (int)(unsigned)(f[u] >> 32), (int)(unsigned)(f[u] & 0xffffffffu));
+      }
+    }
   }
+  __threadfence_system();  // the quads must have reached host memory before the host sees the count
   __syncthreads();
   if (threadIdx.x == 0) {
-    out_quads[0] = nh;  // > cap_quads tells the host that the table overflowed
     ctr[0] = 0;
     ctr[1] = 0;
+    out_quads[1] = 0;
+    // the host polls this word (it stores -1 before the launch); > cap_quads tells it that the table overflowed
+    *reinterpret_cast<volatile int32_t*>(out_quads) = nh;
   }
 }
 
@@ -1361,28 +1784,47 @@ __global__ void __launch_bounds__(256) k_final_labels(const int64_t* __restrict_
   }
 }
 
-// static submap: every non-dynamic point of the frames of a batch moved to the map frame
-// (transformCloud arithmetic with the frame's pose), appended with warp-aggregated atomics
+// static submap: every non-dynamic point of the frames of a batch moved to the map frame (transformCloud arithmetic
+// with the frame's pose).  A CTA owns a contiguous chunk of a scan and every warp a contiguous part of it: the static
+// points are counted first (1 B / point), the CTA reserves its output range with ONE atomic on the global counter,
+// and the second pass writes with ballot / popcount ranks (no per-warp atomics on a single address).
 __global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, const uint8_t* __restrict__ cls,
                                                 const int64_t* __restrict__ off, const float* __restrict__ Ts, int first_scan,
                                                 float4* __restrict__ out, unsigned long long* __restrict__ counter, long long cap) {
+  __shared__ int s_wcnt[8];
+  __shared__ unsigned long long s_base;
   const int b = first_scan + blockIdx.y;
   const int64_t base = off[b];
   const int n = (int)(off[b + 1] - base);
   float t[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) t[i] = Ts[blockIdx.y * 12 + i];
-  const int lane = threadIdx.x & 31;
-  for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += gridDim.x * blockDim.x) {
-    int i = i0 + lane;
-    bool keep = (i < n) && cls[base + i] != SCVOD_PT_DYNAMIC;
-    unsigned mask = __ballot_sync(0xffffffffu, keep);
-    if (!mask) continue;
-    unsigned long long basepos = 0;
-    if (lane == 0) basepos = atomicAdd(counter, (unsigned long long)__popc(mask));
-    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per_warp = (((n + gridDim.x * 8 - 1) / (gridDim.x * 8)) + 31) & ~31;  // multiple of 32: aligned 1-byte loads
+  const int i0 = min(n, (blockIdx.x * 8 + wid) * per_warp), i1 = min(n, i0 + per_warp);
+  int cnt = 0;
+  for (int i = i0 + lane; i < i1; i += 32) cnt += (cls[base + i] != SCVOD_PT_DYNAMIC) ? 1 : 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+  if (lane == 0) s_wcnt[wid] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < 8; ++w) {
+      const int c = s_wcnt[w];
+      s_wcnt[w] = run;
+      run += c;
+    }
+    s_base = run ? atomicAdd(counter, (unsigned long long)run) : 0ull;
+  }
+  __syncthreads();
+  long long pos0 = (long long)s_base + s_wcnt[wid];
+  for (int j = i0; j < i1; j += 32) {
+    const int i = j + lane;
+    const bool keep = (i < i1) && cls[base + i] != SCVOD_PT_DYNAMIC;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
     if (keep) {
-      long long pos = (long long)basepos + __popc(mask & ((1u << lane) - 1));
+      const long long pos = pos0 + __popc(mask & ((1u << lane) - 1));
       if (pos < cap) {
         float4 p = __ldg(&pts[base + i]);
         float4 q;
@@ -1393,6 +1835,7 @@ __global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, 
         out[pos] = q;
       }
     }
+    pos0 += __popc(mask);
   }
 }
 
@@ -1590,9 +2033,10 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   BinParams bp = make_bin_params(hp);
   int launches = 0;
   cudaMemsetAsync(d.patch_cnt, 0, sizeof(int32_t) * (size_t)nscans * kNumPatches, st);
+  cudaMemsetAsync(d.sort_ctr, 0, sizeof(int32_t) * 8, st);
   dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
   { TIMED("k_patch_assign", TSTREAM); k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, d.patch_cnt, d.cls); }
-  { TIMED("k_patch_scan", TSTREAM); k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur); }
+  { TIMED("k_patch_scan", TSTREAM); k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur, d.sort_ctr, d.sort_list, d.cap_scans * kNumPatches); }
   { TIMED("k_patch_scatter", TSTREAM); k_patch_scatter<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_of, d.patch_off, d.patch_cur, d.bucket_kv); }
   FitArgs fa;
   fa.pts = d.pts;
@@ -1612,44 +2056,30 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   fa.err = d.scan_counts + (size_t)d.cap_scans * 8;  // one extra int past the per-scan counters
   fa.gc = gc;
   fa.bp = bp;
-  constexpr int kT0 = 1024, kT1 = 4096, kT2 = 16384;
   static std::once_flag sort_once;
   std::call_once(sort_once, [] {
-    cudaFuncSetAttribute(k_patch_sort<kT1, kT0, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1 * 8);
-    cudaFuncSetAttribute(k_patch_sort<kT2, kT1, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2 * 8);
+    cudaFuncSetAttribute(k_patch_sort_list<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSortT1 * 8);
   });
   dim3 gfit(kNumPatches, nscans);
-  { TIMED("k_patch_sort_1k", TSTREAM); k_patch_sort<kT0, 0, 128, false><<<gfit, 128, kT0 * 8, st>>>(fa); }
+  { TIMED("k_patch_sort_1k", TSTREAM); k_patch_sort<128><<<gfit, 128, kSortT0 * 8, st>>>(fa); }
   launches += 1;
-  if (max_scan_points > kT0) {
-    { TIMED("k_patch_sort_4k", TSTREAM); k_patch_sort<kT1, kT0, 256, false><<<gfit, 256, kT1 * 8, st>>>(fa); }
+  const int list_cap = d.cap_scans * kNumPatches;
+  if (max_scan_points > kSortT0) {  // persistent CTAs over the worklists: three 72 KB CTAs per SM
+    { TIMED("k_patch_sort_4k", TSTREAM); k_patch_sort_list<256, false><<<num_sms() * 3, 256, 2 * kSortT1 * 8, st>>>(fa, d.sort_list, d.sort_ctr, kSortT1); }
     launches += 1;
   }
-  if (max_scan_points > kT1) {
-    { TIMED("k_patch_sort_16k", TSTREAM); k_patch_sort<kT2, kT1, 512, false><<<gfit, 512, kT2 * 8, st>>>(fa); }
+  if (max_scan_points > kSortT1) {
+    { TIMED("k_patch_sort_16k", TSTREAM); k_patch_sort_list<512, true><<<num_sms() * 2, 512, 0, st>>>(fa, d.sort_list + list_cap, d.sort_ctr + 2, 0); }
     launches += 1;
   }
-  if (max_scan_points > kT2) {  // overflow tier: sorted in place in global memory
-    { TIMED("k_patch_sort_overflow", TSTREAM); k_patch_sort<0x3fffffff, kT2, 512, true><<<gfit, 512, 0, st>>>(fa); }
+  if (max_scan_points > kSortT2) {
+    { TIMED("k_patch_sort_overflow", TSTREAM); k_patch_sort_list<512, true><<<num_sms() * 2, 512, 0, st>>>(fa, d.sort_list + 2 * (size_t)list_cap, d.sort_ctr + 4, 0); }
     launches += 1;
   }
   {
-    // dynamic shared memory is requested only to cap the residency at kChainCtasPerSm CTAs per SM (see the kernel)
-    static int chain_pad = 0;
-    static std::once_flag chain_once;  // several host threads (one context each) may get here at the same time
-    std::call_once(chain_once, [] {
-      int dev = 0, smem_sm = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-      cudaFuncAttributes fattr;
-      cudaFuncGetAttributes(&fattr, k_patch_chain);
-      int pad = smem_sm / kChainCtasPerSm - (int)fattr.sharedSizeBytes - 2048;
-      if (pad < 0) pad = 0;
-      cudaFuncSetAttribute(k_patch_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-      chain_pad = pad;
-    });
+    // persistent: kChainCtasPerSm CTAs of kChainWarps warps per SM (the chain is issue/latency bound, see the kernel)
     TIMED("k_patch_chain", TSTREAM);
-    k_patch_chain<<<(kNumPatches * nscans + kChainWarps - 1) / kChainWarps, kChainWarps * 32, chain_pad, st>>>(fa, nscans);
+    k_patch_chain<<<num_sms() * kChainCtasPerSm, kChainWarps * 32, 0, st>>>(fa, nscans, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches);
   }
   { TIMED("k_patch_rank", TSTREAM); k_patch_rank<256><<<gfit, 256, 0, st>>>(fa); }
   launches += 2;
@@ -1683,7 +2113,8 @@ int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int max_s
   { TIMED("k_vox_nbr", TSTREAM); k_vox_nbr<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_nbr, d.vox_root); }
   { TIMED("k_ccl_union", TSTREAM); k_ccl_union<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_nbr, d.vox_root); }
   { TIMED("k_ccl_flatten", TSTREAM); k_ccl_flatten<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_root); }
-  { TIMED("k_similar_edges", TSTREAM); k_similar_edges<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_av, d.vox_cov, d.vox_root,
+  dim3 gw(grid_x_for(nscans, max_scan_points / 4 + 1, 8), nscans);  // one warp per voxel, 8 warps per CTA
+  { TIMED("k_similar_edges", TSTREAM); k_similar_edges<<<gw, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_av, d.vox_cov, d.vox_root,
                                       hp.p.search_c, hp.p.intensity_cov, hp.p.intensity_diff,
                                       reinterpret_cast<unsigned long long*>(d.edge_hash), d.hash_cap, d.edge_buf, d.edge_cap); }
   { TIMED("k_events", TSTREAM); k_events<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.apri_rank, d.ev_cid); }
@@ -1731,15 +2162,23 @@ int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, con
   return 1;
 }
 
-int launch_name_replay(BatchDev& d, int nscans, int max_vox, int32_t* vox_name, int32_t* name_first, int name_cap, void* stream_) {
+int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, bool force_global, int32_t* vox_name, int32_t* name_first, int name_cap,
+                       void* stream_) {
   if (nscans <= 0) return 0;
-  const size_t smem = (size_t)max_vox * 14 + 16;
+  constexpr int NW = kReplayWarps;
+  const size_t ring = sizeof(int) * NW * 2 * kReplayRows * 32;
+  const size_t nfw = ((size_t)max_events + 31) / 32;
+  const size_t smem = ring + (size_t)max_vox * 14 + nfw * 8 + 16;
   static std::once_flag replay_once;
-  std::call_once(replay_once, [] { cudaFuncSetAttribute(k_name_replay<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-  if (smem <= 220 * 1024) {
-    { TIMED("k_name_replay", TSTREAM); k_name_replay<false><<<nscans, 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_nbr, nullptr, nullptr, nullptr, nullptr, vox_name, name_first, name_cap); }
-  } else {  // very dense scans: union-find state in (L2-resident) global scratch
-    { TIMED("k_name_replay_global", TSTREAM); k_name_replay<true><<<nscans, 32, 0, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_nbr, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, vox_name, name_first, name_cap); }
+  std::call_once(replay_once, [ring] {
+    cudaFuncSetAttribute(k_name_replay<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_name_replay<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+  });
+  int2* ev_list = reinterpret_cast<int2*>(d.bucket_kv);  // the ground stage is done with its (key, index) buckets
+  if (smem <= 220 * 1024 && !force_global) {
+    { TIMED("k_name_replay", TSTREAM); k_name_replay<NW, false><<<nscans, NW * 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, nullptr, nullptr, nullptr, nullptr, nullptr, vox_name, name_first, name_cap); }
+  } else {  // very dense scans: union-find state in (L2-resident) global scratch that the earlier stages are done with
+    { TIMED("k_name_replay_global", TSTREAM); k_name_replay<NW, true><<<nscans, NW * 32, ring, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, d.slot_pos, vox_name, name_first, name_cap); }
   }
   return 1;
 }

@@ -98,6 +98,37 @@ def test_ground_ragged_inputs(ssc, oracle, pkg):
         assert np.array_equal(g, og) and np.array_equal(ng, ong)
 
 
+def test_ground_sort_with_z_ties_is_deterministic(pkg):
+    """std::sort is unstable, so the reference's order of equal-z points is implementation defined; here it is
+    defined as (z, input index).  Patches of every sort tier (<= 1024, <= 4096, above) with many z ties: the result
+    must be reproducible, a partition of the kept points, and ascending in (z, index) inside each list of a patch."""
+    rng = np.random.default_rng(7)
+    parts = []
+    for n, ang in ((700, 0.1), (3000, 0.5), (9000, 0.9)):  # three zone-0 patches (r in [2.7, 7.5), sectors 0, 1, 2)
+        r = rng.uniform(3.0, 7.0, n)
+        a = rng.uniform(ang - 0.05, ang + 0.05, n)
+        z = -1.73 + np.round(rng.normal(0, 0.02, n), 2)  # quantised to 1 cm: lots of ties
+        parts.append(np.stack([r * np.cos(a), r * np.sin(a), z, np.full(n, 20.0)], 1))
+    cloud = np.concatenate(parts).astype(np.float32)
+    cloud = cloud[rng.permutation(len(cloud))]
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=len(cloud), max_batch=1)
+    g1, ng1 = s.extractGroudByPatchWork(cloud)
+    for _ in range(3):
+        g2, ng2 = s.extractGroudByPatchWork(cloud)
+        assert np.array_equal(g1, g2) and np.array_equal(ng1, ng2)
+    both = np.concatenate([g1, ng1])
+    assert len(np.unique(both)) == len(both) == len(cloud)
+    # the ground list is patch-major; inside a patch it follows the sorted order
+    ang = np.arctan2(cloud[:, 1].astype(np.float64), cloud[:, 0].astype(np.float64))
+    sector = np.minimum((ang / (2 * np.pi / 16)).astype(int), 15)
+    for lst in (g1, ng1):
+        for sec in np.unique(sector[lst]):
+            idx = lst[sector[lst] == sec]
+            zz = cloud[idx, 2]
+            assert np.all((np.diff(zz) > 0) | ((np.diff(zz) == 0) & (np.diff(idx) > 0)))
+    s.close()
+
+
 # ---- whole path -------------------------------------------------------------------------------------
 def compare_frames(ssc, orc, nframes, pkg):
     for f in range(nframes):
@@ -141,6 +172,18 @@ def test_pipeline_stage_by_stage_kitti(pkg, ssc, oracle):
         for k in ("name", "type", "state", "npts", "nvox"):
             assert np.array_equal(cg[k], co[k]), k
     assert ndyn > 0  # the sequence does contain moving cars
+
+
+def test_name_replay_global_memory_variant(pkg, oracle):
+    """Very dense scans keep the union-find state of k_name_replay in global memory: same names, same clusters."""
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=4)
+    s.set_option("replay_global", 1)
+    scans, _ = zip(*[pkg.synth_scan(conftest.SEED + 5, k) for k in range(3)])
+    s.process(scans)
+    for sc in scans:
+        oracle.push_scan(sc)
+    compare_frames(s, oracle, len(scans), pkg)
+    s.close()
 
 
 def test_long_sequence_labels(pkg, oracle):
@@ -241,6 +284,21 @@ def test_full_size_batch_properties(pkg):
     cnt = s.static_submap_device(0, n, poses, out.data_ptr(), total)
     assert cnt == sum(int((l != pkg.PT_DYNAMIC).sum()) for l in labels)
     assert torch.isfinite(out[:cnt]).all()
+    # ... moved to the map frame with transformCloud's arithmetic (utility.h:394-406: left to right, float, no FMA);
+    # the submap is a concatenation without a defined order, so compare as multisets
+    exp = []
+    for f in range(n):
+        T = pkg.pose_matrix(poses[f]).astype(np.float32)
+        p = scans[f][labels[f] != pkg.PT_DYNAMIC].astype(np.float32)
+        q = np.empty_like(p)
+        for r in range(3):
+            q[:, r] = ((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3]
+        q[:, 3] = p[:, 3]
+        exp.append(q)
+    exp = np.concatenate(exp).view(np.uint32)
+    got = out[:cnt].cpu().numpy().view(np.uint32)
+    key = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(exp), key(got))
     s.close()
     t.close()
 
