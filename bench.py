@@ -35,7 +35,10 @@ RINGS, COLS = 64, 1800
 SEED = 0x5C0D0000
 # algorithmic (compulsory) bytes per unit for the stage each kernel dominates
 ALGO_BYTES = {
-    "k_patch_fit": ("ground stage (P1-P6): 32 B per input point (16N read + 16N written in reference order)", 32.0, "points"),
+    "k_patch_chain": ("ground stage (P1-P6): 32 B per input point (16N read + 16N written in reference order)", 32.0, "points"),
+    "k_patch_sort_4k": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
+    "k_patch_sort_1k": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
+    "k_name_replay": ("cluster stage (C1-C2): 8 B per voxel read + 4 B per voxel + 4 B per apri point written", 16.0, "voxels_plus_apri"),
     "k_patch_assign": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
     "k_patch_scatter": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
     "k_emit": ("ground stage (P1-P6): 32 B per input point", 32.0, "points"),
@@ -342,10 +345,11 @@ def main():
         # dominant kernel by total device time inside the timed region
         dom = max(rep.items(), key=lambda kv: kv[1][0])
         dom_name, (dom_ms, dom_cnt) = dom
-        key = "k_patch_fit" if dom_name.startswith("k_patch_fit") else dom_name
+        key = dom_name
         desc, bytes_per_unit, unit_kind = ALGO_BYTES.get(key, ("ground stage, 32 B per input point", 32.0, "points"))
         w0 = workers[0].ssc
-        per_kind = {"points": w0.stat("points"), "apri": w0.stat("apri_points"), "track_points": w0.stat("track_points")}
+        per_kind = {"points": w0.stat("points"), "apri": w0.stat("apri_points"), "track_points": w0.stat("track_points"),
+                    "voxels_plus_apri": (12 * w0.stat("voxels") + 4 * w0.stat("apri_points")) / 16.0}
         steps_seen = max(1, w0.stat("scans") // S)
         units_per_launch = per_kind[unit_kind] / steps_seen * (args.steps / dom_cnt)  # units handled by one launch, on average
         achieved = bytes_per_unit * units_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e9

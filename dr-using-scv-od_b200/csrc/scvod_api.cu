@@ -201,6 +201,15 @@ struct scvod_ctx {
   PinBuf<int32_t> h_treq, h_triples;
   DevBuf<float4> d_tout[2];
   int tout_cur = 0;  // d_tout[tout_cur] holds the carried clouds of the frame that is the next frame_pre_
+  // host scratch of track_pair, kept across pairs so that the steady state allocates nothing
+  struct LabelAcc {
+    int lab = -1;
+    uint64_t min_key = 0;
+    std::vector<int> vox;
+  };
+  std::vector<int> hit_start, hit_cur, hit_vox, label_order;
+  std::vector<uint64_t> hit_key;
+  std::vector<LabelAcc> label_accs;
   // label refresh staging
   DevBuf<int32_t> d_vcls;
   PinBuf<int32_t> h_vcls;
@@ -646,8 +655,8 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     add(w.edge_buf + (size_t)s * w.edge_cap * 2, o_edge + gbase[s] * 2, G * 2);
   }
   add(w.scan_counts, o_max, nscans * 8);  // re-read the counters: slot 6 now holds max_name
-  CU(cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, sizeof(PackDesc) * nd, cudaMemcpyHostToDevice, st));
-  c->launches += launch_pack(c->d_desc.p, nd, max_desc_n, c->d_pack.p, st);
+  // k_pack reads its descriptors straight from the pinned table (no copy-engine hop, see k_upload_words)
+  c->launches += launch_pack(c->h_desc.p, nd, max_desc_n, c->d_pack.p, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_pack.p, c->d_pack.p, sizeof(int32_t) * pack_ints, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -778,9 +787,10 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
   const int ncl = (int)cars.size();
   const int vn = next.n_vox;
   std::vector<size_t> cstart(cars.size() + 1, 0);
-  // per cluster: (first-occurrence key, hit voxel).  The cloud of a cluster is [part 0][part 1]...[carried 0]...
-  // (ssc.cpp:380,617,1382) with ascending apri index inside a part, which is what the 64-bit key encodes.
-  std::vector<std::vector<std::pair<uint64_t, int>>> hits(cars.size());
+  // per cluster: (first-occurrence key, hit voxel), grouped by cluster in c->hit_start / c->hit_key / c->hit_vox.  The cloud
+  // of a cluster is [part 0][part 1]...[carried 0]... (ssc.cpp:380,617,1382) with ascending apri index inside a part,
+  // which is what the 64-bit key encodes.
+  c->hit_start.assign(cars.size() + 1, 0);
   const int in_buf = c->tout_cur, out_buf = 1 - c->tout_cur;
   {
     PROF("  track: gpu round trip");
@@ -840,7 +850,7 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
       std::atomic_thread_fence(std::memory_order_release);
       PROF("    track: enqueue+wait+read");
-      CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4), cudaMemcpyHostToDevice, c->stream));
+      c->launches += launch_upload_words(c->h_treq.p, c->d_treq.p, (long long)(si * 4), c->stream);
       c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                   reinterpret_cast<const int4*>(c->d_treq.p), (int)si, (int)K, T,
                                   pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
@@ -881,11 +891,20 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
         cudaStreamSynchronize(c->stream);
         return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
       }
+      // counting sort of the quads by cluster (no order inside a cluster: the decisions only need, per next-frame
+      // label, the smallest key and the set of hit voxels)
+      const int32_t* quads = c->h_triples.p + 4;
+      for (int t = 0; t < nt; ++t) c->hit_start[quads[4 * t] + 1]++;
+      for (size_t i = 0; i < cars.size(); ++i) c->hit_start[i + 1] += c->hit_start[i];
+      c->hit_key.resize(nt);
+      c->hit_vox.resize(nt);
+      c->hit_cur.assign(c->hit_start.begin(), c->hit_start.end() - 1);
       for (int t = 0; t < nt; ++t) {
-        const int32_t* q = c->h_triples.p + 4 + 4 * t;
-        hits[q[0]].push_back(std::make_pair(((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3], q[1]));
+        const int32_t* q = quads + 4 * t;
+        const int pos = c->hit_cur[q[0]]++;
+        c->hit_key[pos] = ((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3];
+        c->hit_vox[pos] = q[1];
       }
-      for (auto& h : hits) std::sort(h.begin(), h.end());  // order of first occurrence along the cloud
     }
   }
 
@@ -899,21 +918,39 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       cc.track_id = c->track_name;
       c->track_name++;
     }
-    std::unordered_map<int, std::vector<int>> remap_name;  // label -> hit voxels (ssc.cpp:1277-1317)
-    for (auto& h : hits[ci]) {
-      const int v = h.second;
-      int lab = nlabel[v];
-      if (lab == -1) continue;
-      auto l_find = remap_name.find(lab);
-      if (l_find == remap_name.end()) {
-        std::vector<int> vec;
-        vec.emplace_back(v);
-        remap_name.insert(std::make_pair(lab, vec));
-      } else {
-        l_find->second.emplace_back(v);
+    // label -> hit voxels (ssc.cpp:1277-1317).  The reference inserts a label when the first point that hits one of its
+    // voxels comes by, so the insertion order (which fixes the iteration order of the unordered_map) is the order of the
+    // labels' smallest keys; the voxel lists are sorted afterwards (sampleVec), so their arrival order is irrelevant.
+    std::unordered_map<int, std::vector<int>> remap_name;
+    {
+      auto& accs = c->label_accs;  // few labels per cluster: linear search, vectors reused across clusters and pairs
+      size_t na = 0;
+      for (int t = c->hit_start[ci]; t < c->hit_start[ci + 1]; ++t) {
+        const int v = c->hit_vox[t];
+        const int lab = nlabel[v];
+        if (lab == -1) continue;
+        size_t k = 0;
+        while (k < na && accs[k].lab != lab) ++k;
+        if (k == na) {
+          if (accs.size() <= na) accs.emplace_back();
+          accs[na].lab = lab;
+          accs[na].min_key = c->hit_key[t];
+          accs[na].vox.clear();
+          ++na;
+        } else if (c->hit_key[t] < accs[k].min_key) {
+          accs[k].min_key = c->hit_key[t];
+        }
+        accs[k].vox.push_back(v);
+      }
+      c->label_order.resize(na);
+      for (size_t k = 0; k < na; ++k) c->label_order[k] = (int)k;
+      std::sort(c->label_order.begin(), c->label_order.end(), [&](int x, int y) { return accs[x].min_key < accs[y].min_key; });
+      for (size_t k = 0; k < na; ++k) {
+        auto& acc = accs[c->label_order[k]];
+        std::sort(acc.vox.begin(), acc.vox.end());  // sampleVec: already unique
+        remap_name.insert(std::make_pair(acc.lab, acc.vox));
       }
     }
-    for (auto& re : remap_name) std::sort(re.second.begin(), re.second.end());  // sampleVec: already unique
     if (remap_name.size() == 0) {
       cc.state = 1;
     } else if (remap_name.size() == 1) {
@@ -1026,7 +1063,7 @@ static int refresh_batch_labels(scvod_ctx* c, int batch) {
     }
     pos += (fr->n_vox + 3) & ~3;
   }
-  CU(cudaMemcpyAsync(c->d_vcls.p, c->h_vcls.p, sizeof(int32_t) * words, cudaMemcpyHostToDevice, c->stream));
+  c->launches += launch_upload_words(c->h_vcls.p, c->d_vcls.p, (long long)words, c->stream);
   c->launches += launch_final_labels(pb.off_dev.p, pb.scan_counts_dev.p, pb.nscans, pb.max_n, pb.apri_src.p, pb.apri_cid.p, c->d_vcls.p,
                                      reinterpret_cast<const uint8_t*>(c->d_vcls.p + pb.nscans), pb.cls.p, c->stream);
   CU(cudaGetLastError());
@@ -1089,7 +1126,7 @@ extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float
   CU(c->h_Ts.alloc(std::max(1, nf) * 12));
   CU(c->d_Ts.alloc(std::max(1, nf) * 12));
   for (int f = f0; f < f1; ++f) pose_matrix(poses6 + 6 * f, c->h_Ts.p + 12 * (f - f0));
-  if (nf > 0) CU(cudaMemcpyAsync(c->d_Ts.p, c->h_Ts.p, sizeof(float) * 12 * nf, cudaMemcpyHostToDevice, c->stream));
+  if (nf > 0) c->launches += launch_upload_words(c->h_Ts.p, c->d_Ts.p, 12LL * nf, c->stream);
   int f = f0;
   while (f < f1) {
     FrameHost& fr = c->frames[f];

@@ -14,7 +14,9 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -341,7 +343,7 @@ __device__ void dev_svd3(const float A[3][3], float U[3][3], float sv[3]) {
 //                      strictly sequentially, one lane per accumulator; the chain is latency bound, hence one
 //                      warp per patch, many patches per SM, points streamed through a small cp.async ring
 //                      instead of a whole-patch shared-memory tile   (patchwork.h:235-268, 217-232, 463-504)
-//   G4c k_patch_rank   CTA per (patch, scan): final ground test, gating outcome, curved-voxel binning of the
+//   G4c k_patch_rank_* warp (<= 1024 points) or CTA (worklists) per (patch, scan): final ground test, gating outcome, curved-voxel binning of the
 //                      nonground points (ssc.cpp:158-172,185-188) and ordered ranks     (patchwork.h:331-384)
 // ------------------------------------------------------------------------------------------------
 struct FitArgs {
@@ -660,14 +662,11 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
   float n0 = 0.f, n1 = 0.f, n2 = 0.f, th = 0.f;
   float st_meanx = 0.f, st_meany = 0.f, st_meanz = 0.f, st_sv0 = 0.f, st_sv1 = 0.f, st_sv2 = 0.f, st_d = 0.f;
   const int nstages = (n + 31) >> 5;
-  auto issue = [&](int st) {
-    if (st < nstages) {
-      const int j = st * 32 + lane;
-      if (j < n) {
-        unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[st % kChainStages][lane]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(S + j));
-      }
-    }
+  auto issue = [&](int st) {  // branch-free: past the end of the patch the copy degenerates to a zero fill (src-size 0)
+    const int j = st * 32 + lane;
+    const bool live = j < n;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[st % kChainStages][lane]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(S + (live ? j : 0)), "r"(live ? 16 : 0));
     asm volatile("cp.async.commit_group;\n" ::);
   };
   // Lane L < 9 accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix (xx xy xz yy yz zz x y z) STRICTLY in
@@ -680,10 +679,10 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
   for (int it = 0; it < 3; ++it) {
     float acc = 0.f;
     int cnt = 0;
-    for (int st = 0; st < kChainStages; ++st) issue(st);
-    for (int st = 0; st < nstages; ++st) {
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));
-      __syncwarp();
+    // Software pipeline inside the warp: the products of stage st+1 are computed (and stored to the other half of
+    // s_prod) in the same straight-line block as the column walk of stage st, so their issue slots and shared-memory
+    // latencies hide in the 4-cycle bubbles of the dependent FADD chain.  One __syncwarp per stage.
+    auto produce = [&](int st) {  // stage st -> s_prod[st & 1]; a stage past the end contributes -0.0f everywhere
       const bool live = st * 32 + lane < n;
       const float4 q = live ? ring[st % kChainStages][lane] : make_float4(0.f, 0.f, 0.f, 0.f);
       bool in;
@@ -704,11 +703,20 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
       pr[6] = in ? q.x : -0.0f;
       pr[7] = in ? q.y : -0.0f;
       pr[8] = in ? q.z : -0.0f;
-      __syncwarp();
-      issue(st + kChainStages);  // refills the ring slot that was just consumed
+    };
+    for (int st = 0; st < kChainStages; ++st) issue(st);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));
+    produce(0);
+    issue(kChainStages);  // every lane refills the ring element it has just read itself
+    __syncwarp();
+    for (int st = 0; st < nstages; ++st) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));  // stage st + 1 has landed
+      produce(st + 1);
+      issue(st + 1 + kChainStages);
       const float* pc = s_prod[wid][st & 1] + col;
 #pragma unroll
       for (int t = 0; t < 32; ++t) acc = da(acc, pc[t * 9]);
+      __syncwarp();
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
     float accu[9];
@@ -785,12 +793,10 @@ constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md
 // slot_pos encoding: role << 30 | in-ground-set << 29 | rank inside its class (ground set / complement);
 // slot_apos: rank among the gate-passing points of the same class, or -1.  k_emit turns them into positions with
 // the per-patch totals of patch_out (a rejected patch emits [ground set][complement] into cloud_nonground).
+// One patch by a group of THREADS threads: a warp (THREADS == 32, the many patches up to 1024 points, no block barrier)
+// or a whole CTA (the long patches on the sort worklists).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_patch_rank(FitArgs a) {
-  __shared__ int s_scan[THREADS / 32 + 1];
-  const int p = blockIdx.x, b = blockIdx.y;
-  const int n = a.patch_cnt[b * kNumPatches + p];
-  if (n <= kMinPatchPts) return;
+__device__ __forceinline__ void rank_one_patch(const FitArgs& a, int p, int b, int n, int tid, int* s_scan) {
   const int64_t base = a.off[b];
   const int slot0 = a.patch_off[b * (kNumPatches + 1) + p];
   const float4* __restrict__ S = a.sorted_xyz + base + slot0;
@@ -799,8 +805,7 @@ __global__ void __launch_bounds__(THREADS) k_patch_rank(FitArgs a) {
   const float th = (float)__dsub_rn(0.1, (double)rec[9]);
   const int decision = (int)rec[10];
   const bool rejected = (decision == 1 || decision == 2);
-  const int tid = threadIdx.x;
-  int cG = 0, cGP = 0, cNP = 0, cQ = 0;  // running totals (block uniform)
+  int cG = 0, cGP = 0, cNP = 0, cQ = 0;  // running totals (group uniform)
   for (int j0 = 0; j0 < n; j0 += THREADS) {
     const int j = j0 + tid;
     const bool valid = j < n;
@@ -822,9 +827,16 @@ __global__ void __launch_bounds__(THREADS) k_patch_rank(FitArgs a) {
     const bool g = f & F_G, ps = f & F_PASS;
     // chunk counts are <= THREADS <= 512: three 10-bit fields in one scan
     const int packed = (g ? 1 : 0) | ((g && ps) ? (1 << 10) : 0) | ((!g && ps) ? (1 << 20) : 0);
-    int total;
-    const int ex = block_excl_scan<THREADS>(packed, &total, s_scan);
-    const int nq = __syncthreads_count((f & F_QUIRK) ? 1 : 0);
+    int total, ex, nq;
+    if (THREADS == 32) {
+      const int inc = warp_incl_scan(packed);
+      total = __shfl_sync(0xffffffffu, inc, 31);
+      ex = inc - packed;
+      nq = __popc(__ballot_sync(0xffffffffu, (f & F_QUIRK) != 0));
+    } else {
+      ex = block_excl_scan<(THREADS == 32 ? 64 : THREADS)>(packed, &total, s_scan);
+      nq = __syncthreads_count((f & F_QUIRK) ? 1 : 0);
+    }
     if (valid) {
       const int rG = cG + (ex & 1023), rGP = cGP + ((ex >> 10) & 1023), rNP = cNP + ((ex >> 20) & 1023);
       const int rN = j - rG;  // complement points before j
@@ -854,6 +866,38 @@ __global__ void __launch_bounds__(THREADS) k_patch_rank(FitArgs a) {
     pout[5] = cGP;
     pout[6] = rejected ? 1 : 0;
     pout[7] = 0;
+  }
+}
+
+constexpr int kRankWarps = 4;  // patches per CTA of k_patch_rank_small
+
+// patches up to 1024 points: one warp each
+__global__ void __launch_bounds__(kRankWarps * 32) k_patch_rank_small(FitArgs a) {
+  const int p = blockIdx.x * kRankWarps + (threadIdx.x >> 5), b = blockIdx.y;
+  if (p >= kNumPatches) return;
+  const int n = a.patch_cnt[b * kNumPatches + p];
+  if (n <= kMinPatchPts || n > kSortT0) return;
+  rank_one_patch<32>(a, p, b, n, threadIdx.x & 31, nullptr);
+}
+
+// patches above 1024 points (the three sort worklists): persistent CTAs
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_patch_rank_list(FitArgs a, const int32_t* __restrict__ sort_list, int32_t* __restrict__ sort_ctr,
+                                                             int list_cap) {
+  __shared__ int s_scan[THREADS / 32 + 1];
+  __shared__ int s_item;
+  const int c2 = sort_ctr[4], c1 = sort_ctr[2], c0 = sort_ctr[0];
+  const int n_listed = c2 + c1 + c0;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(&sort_ctr[7], 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if (item >= n_listed) break;
+    const int g = (item < c2) ? sort_list[2 * (size_t)list_cap + item] : (item < c2 + c1) ? sort_list[(size_t)list_cap + item - c2] : sort_list[item - c2 - c1];
+    const int b = g / kNumPatches, p = g - b * kNumPatches;
+    rank_one_patch<THREADS>(a, p, b, a.patch_cnt[g], threadIdx.x, s_scan);
+    __syncthreads();
   }
 }
 
@@ -1041,13 +1085,11 @@ constexpr int kVoxStage = 512;  // intensities staged in shared memory per warp
 __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
                                                    const int32_t* __restrict__ vox_cnt, const int32_t* __restrict__ vox_off,
                                                    const int32_t* __restrict__ vox_pts_tmp, const float4* __restrict__ apri_xyzi,
-                                                   BinParams bp, scvod_params sp, int32_t* __restrict__ vox_pts,
-                                                   int32_t* __restrict__ apri_rank, float* __restrict__ vox_av,
-                                                   float* __restrict__ vox_cov, float* __restrict__ vox_center,
-                                                   int32_t* __restrict__ vox_tri, float* __restrict__ vox_bbox) {
+                                                   int32_t* __restrict__ vox_pts, int32_t* __restrict__ apri_rank,
+                                                   float* __restrict__ vox_av, float* __restrict__ vox_cov,
+                                                   float* __restrict__ vox_bbox) {
   __shared__ float s_val[8][kVoxStage];
   __shared__ int s_seg[8][kVoxStage];
-  __shared__ float4 s_first[8];
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int V = scan_counts[b * 8 + 3];
@@ -1073,7 +1115,6 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
       apri_rank[base + me] = r;
       float4 q = __ldg(&apri_xyzi[base + me]);
       if (staged) sv[r] = q.w;
-      if (r == 0) s_first[wid] = q;
       lo[0] = fminf(lo[0], q.x);
       lo[1] = fminf(lo[1], q.y);
       lo[2] = fminf(lo[2], q.z);
@@ -1111,17 +1152,6 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
     if (lane == 0) {
       vox_av[base + v] = av;
       vox_cov[base + v] = cov;
-      const float4 q0 = s_first[wid];
-      BinResult r = dev_bin_point(q0.x, q0.y, q0.z, bp);
-      vox_tri[3 * (base + v) + 0] = r.ri;
-      vox_tri[3 * (base + v) + 1] = r.si;
-      vox_tri[3 * (base + v) + 2] = r.ei;
-      float range_center = da(dm((float)((r.ri * 2 + 1) / 2), sp.range_res), sp.min_dis);
-      float sector_center = da(dev_deg2rad_f(dm((float)((r.si * 2 + 1) / 2), sp.sector_res)), sp.min_angle);
-      float azimuth_center = da(dev_deg2rad_f(dm((float)((r.ei * 2 + 1) / 2), sp.azimuth_res)), dev_deg2rad_f(sp.min_azimuth));
-      vox_center[3 * (base + v) + 0] = dm(range_center, cosf(sector_center));
-      vox_center[3 * (base + v) + 1] = dm(range_center, sinf(sector_center));
-      vox_center[3 * (base + v) + 2] = dm(range_center, tanf(azimuth_center));
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         vox_bbox[6 * (base + v) + d] = lo[d];
@@ -1129,6 +1159,30 @@ __global__ void __launch_bounds__(256) k_vox_stats(const int64_t* __restrict__ o
       }
     }
     __syncwarp();
+  }
+}
+
+// index triple of the first inserted point of every voxel (ssc.cpp:268-270) and the voxel "centre" (:271-277): one
+// thread per voxel (the binning and the three libm calls are scalar work; a warp per voxel would waste 31 lanes on them)
+__global__ void __launch_bounds__(256) k_vox_center(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                    const int32_t* __restrict__ vox_off, const int32_t* __restrict__ vox_pts,
+                                                    const float4* __restrict__ apri_xyzi, BinParams bp, scvod_params sp,
+                                                    float* __restrict__ vox_center, int32_t* __restrict__ vox_tri) {
+  const int b = blockIdx.y;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    const float4 q0 = __ldg(&apri_xyzi[base + vox_pts[base + vox_off[base + v]]]);
+    BinResult r = dev_bin_point(q0.x, q0.y, q0.z, bp);
+    vox_tri[3 * (base + v) + 0] = r.ri;
+    vox_tri[3 * (base + v) + 1] = r.si;
+    vox_tri[3 * (base + v) + 2] = r.ei;
+    float range_center = da(dm((float)((r.ri * 2 + 1) / 2), sp.range_res), sp.min_dis);
+    float sector_center = da(dev_deg2rad_f(dm((float)((r.si * 2 + 1) / 2), sp.sector_res)), sp.min_angle);
+    float azimuth_center = da(dev_deg2rad_f(dm((float)((r.ei * 2 + 1) / 2), sp.azimuth_res)), dev_deg2rad_f(sp.min_azimuth));
+    vox_center[3 * (base + v) + 0] = dm(range_center, cosf(sector_center));
+    vox_center[3 * (base + v) + 1] = dm(range_center, sinf(sector_center));
+    vox_center[3 * (base + v) + 2] = dm(range_center, tanf(azimuth_center));
   }
 }
 
@@ -1553,9 +1607,20 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
           continue;
         }
         // roots met for the first time, in visit order (a root equal to oc0 was "met" before the loop)
-        const unsigned same = __match_any_sync(0xffffffffu, lab ? r : (-2 - lane));
-        const bool first_occ = lab && (r != oc0) && ((same & ((1u << lane) - 1u)) == 0u);
-        const unsigned fo_mask = __ballot_sync(0xffffffffu, first_occ);
+        bool first_occ;
+        unsigned fo_mask;
+        {
+          const int lane0 = __ffs(lab_mask) - 1;  // lab_mask != 0 here: a labelled W is its own (labelled) neighbour
+          const int r0 = __shfl_sync(0xffffffffu, r, lane0);
+          if (__ballot_sync(0xffffffffu, lab && r != r0) == 0u) {  // the usual case: every labelled neighbour is in one set
+            first_occ = (lane == lane0) && (r0 != oc0);
+            fo_mask = (r0 != oc0) ? (1u << lane0) : 0u;
+          } else {
+            const unsigned same = __match_any_sync(0xffffffffu, lab ? r : (-2 - lane));
+            first_occ = lab && (r != oc0) && ((same & ((1u << lane) - 1u)) == 0u);
+            fo_mask = __ballot_sync(0xffffffffu, first_occ);
+          }
+        }
         int f;  // surviving root: the last first-met set (mergeClusters renames oc to nc each time)
         if (fo_mask) {
           f = __shfl_sync(0xffffffffu, r, 31 - __clz(fo_mask));
@@ -1839,6 +1904,13 @@ __global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, 
   }
 }
 
+// Small host -> device uploads (tracking segments, per-voxel classes, poses) done by SMs reading pinned host memory:
+// a cudaMemcpyAsync would queue on the copy engine behind the bulk scan uploads of the other contexts of this GPU,
+// which stalls the latency-critical tracking chain for milliseconds.
+__global__ void __launch_bounds__(256) k_upload_words(const int32_t* __restrict__ src_host, int32_t* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
 // gather of the per-scan voxel tables into one packed buffer (one D2H instead of hundreds)
 __global__ void __launch_bounds__(256) k_pack(const PackDesc* __restrict__ descs, int32_t* __restrict__ out) {
   const PackDesc d = descs[blockIdx.y];
@@ -2078,10 +2150,15 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   }
   {
     // persistent: kChainCtasPerSm CTAs of kChainWarps warps per SM (the chain is issue/latency bound, see the kernel)
+    static const int ctas_per_sm = getenv("SCVOD_CHAIN_CTAS") ? std::max(1, atoi(getenv("SCVOD_CHAIN_CTAS"))) : kChainCtasPerSm;  // tuning hook
     TIMED("k_patch_chain", TSTREAM);
-    k_patch_chain<<<num_sms() * kChainCtasPerSm, kChainWarps * 32, 0, st>>>(fa, nscans, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches);
+    k_patch_chain<<<num_sms() * ctas_per_sm, kChainWarps * 32, 0, st>>>(fa, nscans, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches);
   }
-  { TIMED("k_patch_rank", TSTREAM); k_patch_rank<256><<<gfit, 256, 0, st>>>(fa); }
+  { TIMED("k_patch_rank_small", TSTREAM); k_patch_rank_small<<<dim3((kNumPatches + kRankWarps - 1) / kRankWarps, nscans), kRankWarps * 32, 0, st>>>(fa); }
+  if (max_scan_points > kSortT0) {
+    { TIMED("k_patch_rank_list", TSTREAM); k_patch_rank_list<256><<<num_sms() * 4, 256, 0, st>>>(fa, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches); }
+    launches += 1;
+  }
   launches += 2;
   { TIMED("k_patch_out_scan", TSTREAM); k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts); }
   { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
@@ -2101,9 +2178,11 @@ int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int max_sca
   { TIMED("k_vox_offsets", TSTREAM); k_vox_offsets<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_cur); }
   { TIMED("k_vox_fill", TSTREAM); k_vox_fill<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.vox_off, d.vox_cur, d.vox_pts_tmp); }
   dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 8), nscans);  // one warp per voxel, 8 warps per CTA
-  { TIMED("k_vox_stats", TSTREAM); k_vox_stats<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_pts_tmp, d.apri_xyzi, bp, hp.p, d.vox_pts,
-                                  d.apri_rank, d.vox_av, d.vox_cov, d.vox_center, d.vox_tri, d.vox_bbox); }
-  return 6;
+  { TIMED("k_vox_stats", TSTREAM); k_vox_stats<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_pts_tmp, d.apri_xyzi, d.vox_pts,
+                                  d.apri_rank, d.vox_av, d.vox_cov, d.vox_bbox); }
+  dim3 gc(grid_x_for(nscans, max_scan_points / 4 + 1, 256), nscans);
+  { TIMED("k_vox_center", TSTREAM); k_vox_center<<<gc, 256, 0, st>>>(d.off, d.scan_counts, d.vox_off, d.vox_pts, d.apri_xyzi, bp, hp.p, d.vox_center, d.vox_tri); }
+  return 7;
 }
 
 int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int max_scan_points, void* stream_) {
@@ -2180,6 +2259,14 @@ int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, boo
   } else {  // very dense scans: union-find state in (L2-resident) global scratch that the earlier stages are done with
     { TIMED("k_name_replay_global", TSTREAM); k_name_replay<NW, true><<<nscans, NW * 32, ring, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, d.slot_pos, vox_name, name_first, name_cap); }
   }
+  return 1;
+}
+
+int launch_upload_words(const void* src_pinned_host, void* dst_dev, long long nwords, void* stream_) {
+  if (nwords <= 0) return 0;
+  long long blocks = (nwords + 1023) / 1024;
+  if (blocks > 64) blocks = 64;
+  { TIMED("k_upload_words", TSTREAM); k_upload_words<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const int32_t*)src_pinned_host, (int32_t*)dst_dev, nwords); }
   return 1;
 }
 
