@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """bench.py — scans/s of the full SCV-OD dynamic-removal path (BASELINE.json metric) on N B200s.
 
-One "step" = one pass of the hot path over one batch of S synthetic 64x1800 scans (a sequence chunk):
+One "step" = one pass of the hot path over one batch of synthetic 64x1800 scans per GPU: W independent sequence chunks
+of S scans each (W workers per GPU, one chunk per worker and step; default 16 x 64 = 1024 scans), every chunk going through
 PatchWork ground fit -> curved-voxel binning -> occupancy descriptor -> clustering/classification ->
 tracking diff over the chunk -> per-point classes -> static submap (+ one NCCL all-gather of the per-GPU
-submaps when N > 1).  Scans shard across ranks (one process per GPU, independent chunks, weak scaling).
+submaps per chunk when N > 1).  Scans shard across ranks (one process per GPU, independent chunks, weak scaling).
 
   value : inputs already resident in HBM (scvod_push_scans_dev), labels stay on the device
   e2e   : same work through the host-buffer C-ABI call a reference maintainer would bind
@@ -15,6 +16,11 @@ submaps when N > 1).  Scans shard across ranks (one process per GPU, independent
 """
 import argparse
 import ctypes
+import os
+
+# Independent sequence chunks run on up to 16 streams per GPU; with the default of 8 hardware work queues, streams that share a
+# queue serialise behind each other's bulk copies.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import json
 import os
 import subprocess
@@ -88,7 +94,10 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        deadline = time.time() + 1.0
+        while not self.lines and time.time() < deadline:  # a very short timed region: wait for the first sample
+            time.sleep(0.02)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -114,6 +123,24 @@ def measured_peak():
         return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel`, averaged over its launches in the
+    committed `ncu --set full` capture of the same 64-scan workload (profiles/r01_ncu_full_summary.csv); None if absent."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:]
+                if r[ik].replace("void ", "").split("(")[0].split("<")[0].strip() == kernel]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
 
 
 def cpu_baseline(pkg, params, scans, poses, nthreads, max_scans):
@@ -170,7 +197,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--scans-per-step", type=int, default=64)
+    ap.add_argument("--scans-per-step", type=int, default=64, help="scans per sequence chunk; a step is one chunk per worker")
     ap.add_argument("--pool", type=int, default=3, help="distinct input batches rotated through (pool > L2)")
     ap.add_argument("--workers", type=int, default=0, help="independent sequence chunks processed side by side per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans for the cpu_baseline leg (0 = auto)")
@@ -223,13 +250,17 @@ def main():
             self.submap = torch.empty((max_pts, 4), dtype=torch.float32, device=dev)
             self.submap_free = threading.Event()
             self.submap_free.set()
+            self.count = 0
 
     workers = [Worker(w) for w in range(W)]
     par = entry._load_parallel()
     gatherer = par.SubmapGatherer(max_pts, dev) if world > 1 else None  # one NCCL all-gather of the static submaps per step
 
     def step(wk, i, host_io):
-        b = batches[i % len(batches)]
+        # every worker cycles through the whole pool (so its buffers reach their steady-state sizes during warm-up) and
+        # neighbouring workers are on different batches at any time
+        wk.count += 1
+        b = batches[(wk.wid + wk.count) % len(batches)]
         ssc = wk.ssc
         ssc.reset()
         if host_io:
@@ -294,7 +325,7 @@ def main():
             raise errors[0]
 
     def timed(host_io, with_kernel_timing):
-        run_steps(0, max(args.warmup, W * len(batches)), host_io)  # every worker sees every pool batch once: buffers reach steady state
+        run_steps(0, W * max(args.warmup, len(batches)), host_io)  # every worker sees every pool batch once: buffers reach steady state
         barrier()
         if with_kernel_timing:
             pkg.kernel_timing(True)
@@ -305,7 +336,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        run_steps(1000, args.steps, host_io)
+        run_steps(1000 * W, args.steps * W, host_io)
         for wk in workers:
             torch.cuda.current_stream().wait_stream(wk.stream)
         e1.record()
@@ -338,8 +369,8 @@ def main():
         dist.barrier()
 
     if rank == 0:
-        value = world * S * args.steps / secs_dev
-        e2e_value = world * S * args.steps / secs_e2e
+        value = world * W * S * args.steps / secs_dev
+        e2e_value = world * W * S * args.steps / secs_e2e
         avg_pts = float(np.mean([b["npts"] for b in batches])) / S
         peak, peak_src = measured_peak()
         # dominant kernel by total device time inside the timed region
@@ -355,10 +386,11 @@ def main():
         achieved = bytes_per_unit * units_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e9
         total_kernel_ms = sum(v[0] for v in rep.values())
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes": desc, "avg_launch_ms": dom_ms / dom_cnt,
+                    "traffic": ncu_traffic(dom_name), "traffic_source": "profiles/r01_ncu_full_summary.csv (ncu --set full, bytes per launch)",
+                    "peak_source": peak_src, "algorithmic_bytes": desc, "avg_launch_ms": dom_ms / dom_cnt,
                     "kernel_share_of_gpu_time": dom_ms / total_kernel_ms,
-                    "measured": f"CUDA events on the launching stream, dedicated single-worker pass of {args.steps} steps inside bench.py",
-                    "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0])}}
+                    "measured": f"CUDA events on the launching stream, dedicated single-worker pass of {args.steps} chunks inside bench.py",
+                    "kernels_ms_per_chunk": {k: round(v[0] / args.steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][0])}}
         ncores = os.cpu_count() or 1
         b0 = batches[0]
         nsample = args.cpu_sample or max(16, min(S, 4 * ncores))
@@ -368,13 +400,13 @@ def main():
             "ms_per_step": 1000.0 * secs_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "configs[1]: SemanticKITTI-shape stream (config/semantickitti.yaml), full PatchWork+SSC+tracking labelling",
-                       "scans_per_step": S, "points_per_scan": avg_pts, "rings": RINGS, "cols": COLS,
+                       "scans_per_step": W * S, "chunks_per_step": W, "scans_per_chunk": S, "points_per_scan": avg_pts, "rings": RINGS, "cols": COLS,
                        "l2": f"inputs rotate over a pool of {args.pool} batches ({args.pool * b0['npts'] * 16 / 1e6:.0f} MB) larger than the 126 MB L2; "
                              "per-step workspace (>1 GB) is rewritten every step",
                        "workers_per_gpu": W,
                        "sharding": ("scan-sharded: independent sequence chunks per rank and per worker; one NCCL all-gather of static submaps per step"
                                     if world > 1 else "single GPU; independent sequence chunks per worker")},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b0["npts"] * 16 + (S + 1) * 8), "d2h_bytes_per_step": int(b0["npts"]),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(W * (b0["npts"] * 16 + (S + 1) * 8)), "d2h_bytes_per_step": int(W * b0["npts"]),
                     "ms_per_step": 1000.0 * secs_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline,

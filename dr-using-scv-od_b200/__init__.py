@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libscvod_b200.so")
 
 # enum scvod_point_class (include/scvod.h)
 PT_DROPPED_LOW, PT_DROPPED_RANGE, PT_DROPPED_SPARSE, PT_GROUND, PT_GATED_OUT, PT_UNCLUSTERED, PT_STATIC, PT_DYNAMIC = range(8)
+INIT_FRAME = -1  # SCVOD_INIT_FRAME: the frame produced by SSC.intialization
 
 
 class Params(ctypes.Structure):
@@ -67,7 +68,7 @@ EXPORTS = (
     "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
     "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
     "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
-    "scvod_gicp_normals", "scvod_pose_matrix",
+    "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization",
 )
 
 _lib = None
@@ -269,6 +270,15 @@ class SSC:
     def tracking(self, poses: np.ndarray):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
         _check(self._lib.scvod_track(self._ctx, _ptr(poses), len(poses)))
+
+    def intialization(self, poses: np.ndarray) -> int:
+        """SSC::intialization (reference src/ssc.cpp:1148-1248, spelling as in the reference): fuses the clusters of the base frame
+        (the last frame with the fewest clusters) that clusters of the other frames bridge.  Returns the base frame's index; read
+        the initialised frame with frame index INIT_FRAME."""
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        out = ctypes.c_int32(-1)
+        _check(self._lib.scvod_initialization(self._ctx, _ptr(poses), len(poses), ctypes.byref(out)))
+        return int(out.value)
 
     def segDF(self, clouds: Sequence[np.ndarray], poses: np.ndarray) -> List[np.ndarray]:
         f0 = self.num_frames

@@ -120,6 +120,24 @@ inline bool name_in(const std::vector<int>& v, int n) { return std::find(v.begin
 
 }  // namespace
 
+// recognize (ssc.cpp:834-895; features :723-751): car <=> footprint < car_square, min z < min_z, max z < max_z
+void recognize_clusters(const scvod_params& p, FrameClusters& out) {
+  for (auto& c : out.cluster_set) {
+    HCluster& cl = c.second;
+    double diff_x = cl.bb_max[0] - cl.bb_min[0];
+    double diff_y = cl.bb_max[1] - cl.bb_min[1];
+    double square = diff_x * diff_y;
+    double f6 = cl.bb_max[2], f9 = cl.bb_min[2];
+    if (square > p.car_square) {
+      cl.type = p.tree;  // building/tree split (regionGrowing, :797-832) does not feed labels; see DESIGN.md
+    } else if (f9 < p.min_z && square < p.car_square && f6 < p.max_z) {
+      cl.type = p.car;
+    } else {
+      cl.type = p.tree;
+    }
+  }
+}
+
 bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClusters& out, bool keep_stages) {
 #ifdef SEG_PROF
   double tp_last = now_us();
@@ -287,21 +305,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   if (keep_stages) out.vox_name_stage[2] = vox_label;
 
   TP(3);
-  // ---- recognize (ssc.cpp:834-895; features :723-751) ------------------------------------------------
-  for (auto& c : out.cluster_set) {
-    HCluster& cl = c.second;
-    double diff_x = cl.bb_max[0] - cl.bb_min[0];
-    double diff_y = cl.bb_max[1] - cl.bb_min[1];
-    double square = diff_x * diff_y;
-    double f6 = cl.bb_max[2], f9 = cl.bb_min[2];
-    if (square > p.car_square) {
-      cl.type = p.tree;  // building/tree split (regionGrowing, :797-832) does not feed labels; see DESIGN.md
-    } else if (f9 < p.min_z && square < p.car_square && f6 < p.max_z) {
-      cl.type = p.car;
-    } else {
-      cl.type = p.tree;
-    }
-  }
+  recognize_clusters(p, out);
   TP(4);
   return true;
 }

@@ -62,6 +62,9 @@ struct FrameClusters {
 // Returns false when the replayed partition disagrees with the GPU components (internal error).
 bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClusters& out, bool keep_stages);
 
+// recognize (ssc.cpp:834-895) alone: cluster types from the bounding boxes stored in the clusters
+void recognize_clusters(const scvod_params& p, FrameClusters& out);
+
 // trans_next.inverse() * trans_pre (ssc.cpp:1255-1257) — 12 floats, row-major 3x4
 void relative_pose(const float pose_next[6], const float pose_pre[6], float T[12]);
 // pcl::getTransformation(x,y,z,roll,pitch,yaw) as 12 floats

@@ -221,6 +221,9 @@ struct scvod_ctx {
   std::vector<std::unique_ptr<PersistBatch>> batch_pool;  // released batches kept for reuse (no cudaMalloc in steady state)
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
+  FrameClusters init_fc;  // frame_based after scvod_initialization (read with frame index SCVOD_INIT_FRAME)
+  int init_base = -1;
+  bool have_init = false;
   int track_name = 0;  // SSC::name (ssc.h:49)
   int64_t stat_track_points = 0, stat_track_pairs = 0, stat_scans = 0, stat_points = 0, stat_apri = 0, stat_voxels = 0;
   void* gicp = nullptr;  // GICP state (scvod_gicp.cu)
@@ -655,8 +658,8 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     add(w.edge_buf + (size_t)s * w.edge_cap * 2, o_edge + gbase[s] * 2, G * 2);
   }
   add(w.scan_counts, o_max, nscans * 8);  // re-read the counters: slot 6 now holds max_name
-  // k_pack reads its descriptors straight from the pinned table (no copy-engine hop, see k_upload_words)
-  c->launches += launch_pack(c->h_desc.p, nd, max_desc_n, c->d_pack.p, st);
+  CU(cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, sizeof(PackDesc) * nd, cudaMemcpyHostToDevice, st));
+  c->launches += launch_pack(c->d_desc.p, nd, max_desc_n, c->d_pack.p, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_pack.p, c->d_pack.p, sizeof(int32_t) * pack_ints, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -764,29 +767,25 @@ extern "C" int scvod_reset_frames(scvod_ctx* c) {
   c->tracked = 0;
   c->track_name = 0;
   c->tout_cur = 0;
+  c->have_init = false;
+  c->init_base = -1;
   return SCVOD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // tracking (SSC::tracking, reference src/ssc.cpp:1250-1426)
 // ---------------------------------------------------------------------------------------------
-static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float* pose_pre, const float* pose_next) {
-  PROF("track_pair total");
-  const scvod_params& P = c->hp.p;
-  float T[12];
-  relative_pose(pose_next, pose_pre, T);
-  // car clusters of frame_pre_ in cluster_set order (ssc.cpp:1261-1264)
-  std::vector<HCluster*> cars;
+// Re-binning of the clouds of `cars` (clusters of frame `pre`) into the curved-voxel grid of frame `next` after the rigid
+// transform T (transformCloud + ssc.cpp:1275-1315 / :1180-1205): one k_track launch for all clusters.  On return the distinct
+// (cluster, hit voxel) pairs with their first-occurrence keys are grouped by cluster in c->hit_start / hit_key / hit_vox,
+// cstart holds the offset of every cluster's transformed cloud in c->d_tout[1 - c->tout_cur].
+static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float T[12], const std::vector<HCluster*>& cars,
+                         std::vector<size_t>& cstart) {
   size_t n_seg = 0;
-  {
-    PROF("  track: prepare");
-    for (auto& cs : pre.fc.cluster_set)
-      if (cs.second.type == P.car) cars.push_back(&cs.second);
-    for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size();
-  }
+  for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size();
   const int ncl = (int)cars.size();
   const int vn = next.n_vox;
-  std::vector<size_t> cstart(cars.size() + 1, 0);
+  cstart.assign(cars.size() + 1, 0);
   // per cluster: (first-occurrence key, hit voxel), grouped by cluster in c->hit_start / c->hit_key / c->hit_vox.  The cloud
   // of a cluster is [part 0][part 1]...[carried 0]... (ssc.cpp:380,617,1382) with ascending apri index inside a part,
   // which is what the 64-bit key encodes.
@@ -850,7 +849,7 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
       std::atomic_thread_fence(std::memory_order_release);
       PROF("    track: enqueue+wait+read");
-      c->launches += launch_upload_words(c->h_treq.p, c->d_treq.p, (long long)(si * 4), c->stream);
+      CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4), cudaMemcpyHostToDevice, c->stream));
       c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                   reinterpret_cast<const int4*>(c->d_treq.p), (int)si, (int)K, T,
                                   pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
@@ -907,6 +906,61 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       }
     }
   }
+  return SCVOD_OK;
+}
+
+// label -> hit voxels of cluster ci (ssc.cpp:1277-1317 / :1180-1205) from the grouped hits of diff_clusters.  The reference inserts a
+// label when the first point that hits one of its voxels comes by, so the insertion order (which fixes the iteration order of the
+// unordered_map) is the order of the labels' smallest keys; the voxel lists are sorted afterwards (sampleVec), so their arrival
+// order is irrelevant.
+static void build_remap(scvod_ctx* c, size_t ci, const std::vector<int>& nlabel, std::unordered_map<int, std::vector<int>>& remap_name) {
+  auto& accs = c->label_accs;  // few labels per cluster: linear search, vectors reused across clusters and pairs
+  size_t na = 0;
+  for (int t = c->hit_start[ci]; t < c->hit_start[ci + 1]; ++t) {
+    const int v = c->hit_vox[t];
+    const int lab = nlabel[v];
+    if (lab == -1) continue;
+    size_t k = 0;
+    while (k < na && accs[k].lab != lab) ++k;
+    if (k == na) {
+      if (accs.size() <= na) accs.emplace_back();
+      accs[na].lab = lab;
+      accs[na].min_key = c->hit_key[t];
+      accs[na].vox.clear();
+      ++na;
+    } else if (c->hit_key[t] < accs[k].min_key) {
+      accs[k].min_key = c->hit_key[t];
+    }
+    accs[k].vox.push_back(v);
+  }
+  c->label_order.resize(na);
+  for (size_t k = 0; k < na; ++k) c->label_order[k] = (int)k;
+  std::sort(c->label_order.begin(), c->label_order.end(), [&](int x, int y) { return accs[x].min_key < accs[y].min_key; });
+  for (size_t k = 0; k < na; ++k) {
+    auto& acc = accs[c->label_order[k]];
+    std::sort(acc.vox.begin(), acc.vox.end());  // sampleVec: already unique
+    remap_name.insert(std::make_pair(acc.lab, acc.vox));
+  }
+}
+
+static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float* pose_pre, const float* pose_next) {
+  PROF("track_pair total");
+  const scvod_params& P = c->hp.p;
+  float T[12];
+  relative_pose(pose_next, pose_pre, T);
+  // car clusters of frame_pre_ in cluster_set order (ssc.cpp:1261-1264)
+  std::vector<HCluster*> cars;
+  {
+    PROF("  track: prepare");
+    for (auto& cs : pre.fc.cluster_set)
+      if (cs.second.type == P.car) cars.push_back(&cs.second);
+  }
+  std::vector<size_t> cstart;
+  const int out_buf = 1 - c->tout_cur;
+  {
+    int rc = diff_clusters(c, pre, next, T, cars, cstart);
+    if (rc) return rc;
+  }
 
   PROF("  track: host decisions");
   std::vector<int>& nlabel = next.fc.vox_label;
@@ -918,39 +972,8 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
       cc.track_id = c->track_name;
       c->track_name++;
     }
-    // label -> hit voxels (ssc.cpp:1277-1317).  The reference inserts a label when the first point that hits one of its
-    // voxels comes by, so the insertion order (which fixes the iteration order of the unordered_map) is the order of the
-    // labels' smallest keys; the voxel lists are sorted afterwards (sampleVec), so their arrival order is irrelevant.
     std::unordered_map<int, std::vector<int>> remap_name;
-    {
-      auto& accs = c->label_accs;  // few labels per cluster: linear search, vectors reused across clusters and pairs
-      size_t na = 0;
-      for (int t = c->hit_start[ci]; t < c->hit_start[ci + 1]; ++t) {
-        const int v = c->hit_vox[t];
-        const int lab = nlabel[v];
-        if (lab == -1) continue;
-        size_t k = 0;
-        while (k < na && accs[k].lab != lab) ++k;
-        if (k == na) {
-          if (accs.size() <= na) accs.emplace_back();
-          accs[na].lab = lab;
-          accs[na].min_key = c->hit_key[t];
-          accs[na].vox.clear();
-          ++na;
-        } else if (c->hit_key[t] < accs[k].min_key) {
-          accs[k].min_key = c->hit_key[t];
-        }
-        accs[k].vox.push_back(v);
-      }
-      c->label_order.resize(na);
-      for (size_t k = 0; k < na; ++k) c->label_order[k] = (int)k;
-      std::sort(c->label_order.begin(), c->label_order.end(), [&](int x, int y) { return accs[x].min_key < accs[y].min_key; });
-      for (size_t k = 0; k < na; ++k) {
-        auto& acc = accs[c->label_order[k]];
-        std::sort(acc.vox.begin(), acc.vox.end());  // sampleVec: already unique
-        remap_name.insert(std::make_pair(acc.lab, acc.vox));
-      }
-    }
+    build_remap(c, ci, nlabel, remap_name);
     if (remap_name.size() == 0) {
       cc.state = 1;
     } else if (remap_name.size() == 1) {
@@ -1035,6 +1058,75 @@ extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// initialization (SSC::intialization, reference src/ssc.cpp:1148-1248)
+// ---------------------------------------------------------------------------------------------
+extern "C" int scvod_initialization(scvod_ctx* c, const float* poses6, int nposes, int32_t* id_based_out) {
+  if (!c || !poses6 || !id_based_out) return fail(SCVOD_ERR_ARG, "null argument");
+  if (c->tracked > 0) return fail(SCVOD_ERR_STATE, "scvod_initialization works on untracked frames: call it before scvod_track");
+  CU(cudaSetDevice(c->device));
+  const int nf = std::min<int>((int)c->frames.size(), nposes);
+  if (nf <= 0) return fail(SCVOD_ERR_STATE, "no frames");
+  const scvod_params& P = c->hp.p;
+  int max_num = 999999, id_based = 0;  // the LAST frame with the fewest clusters (<=, ssc.cpp:1153-1158)
+  for (int i = 0; i < nf; ++i) {
+    if ((int)c->frames[i].fc.cluster_set.size() <= max_num) {
+      max_num = (int)c->frames[i].fc.cluster_set.size();
+      id_based = i;
+    }
+  }
+  FrameHost& base = c->frames[id_based];
+  c->init_fc = base.fc;  // Frame frame_based = frames_[id_based]: same container copy as the reference
+  c->init_base = id_based;
+  FrameClusters& fb = c->init_fc;
+  std::vector<size_t> cstart;
+  for (int i = 0; i < nf; ++i) {
+    if (i == id_based) continue;
+    FrameHost& fi = c->frames[i];
+    float T[12];
+    relative_pose(poses6 + 6 * id_based, poses6 + 6 * i, T);  // trans_based.inverse() * trans_i (:1172)
+    std::vector<HCluster*> all;  // every cluster of frame i, in cluster_set order (:1180)
+    for (auto& cs : fi.fc.cluster_set) all.push_back(&cs.second);
+    int rc = diff_clusters(c, fi, base, T, all, cstart);
+    if (rc) return rc;
+    for (size_t ci = 0; ci < all.size(); ++ci) {
+      std::unordered_map<int, std::vector<int>> remap_name;
+      build_remap(c, ci, fb.vox_label, remap_name);
+      if (remap_name.size() <= 1) continue;
+      HCluster fusion;  // name stays -1 when no label passes the occupancy test (utility.h:154)
+      for (int d = 0; d < 3; ++d) {
+        fusion.bb_min[d] = 3.402823466e38f;
+        fusion.bb_max[d] = -3.402823466e38f;
+      }
+      std::vector<int> erase_id;
+      for (auto& re : remap_name) {
+        HCluster& src = fb.cluster_set[re.first];
+        if (((float)re.second.size() / (float)src.occupy_voxels.size()) >= P.occupancy) {
+          erase_id.emplace_back(re.first);
+          fusion.name = re.first;
+          const int basev = (int)fusion.occupy_voxels.size();
+          fusion.occupy_voxels.insert(fusion.occupy_voxels.end(), src.occupy_voxels.begin(), src.occupy_voxels.end());
+          for (int pe : src.part_end) fusion.part_end.push_back(basev + pe);
+          fusion.npts += src.npts;
+          for (int d = 0; d < 3; ++d) {  // bounding box of the concatenated clouds (getMinMax3D is exact)
+            fusion.bb_min[d] = std::min(fusion.bb_min[d], src.bb_min[d]);
+            fusion.bb_max[d] = std::max(fusion.bb_max[d], src.bb_max[d]);
+          }
+        }
+      }
+      for (int e : erase_id) fb.cluster_set.erase(e);
+      const int fname = fusion.name;
+      const std::vector<int> fvox = fusion.occupy_voxels;
+      fb.cluster_set.insert(std::make_pair(fname, std::move(fusion)));
+      for (int v : fvox) fb.vox_label[v] = fname;
+    }
+  }
+  recognize_clusters(P, fb);  // recognize(frame_based), :1241
+  c->have_init = true;
+  *id_based_out = id_based;
+  return SCVOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // labels
 // ---------------------------------------------------------------------------------------------
 // per-voxel classes of every frame of a batch (decided on the host) -> per-point classes on the device
@@ -1063,7 +1155,7 @@ static int refresh_batch_labels(scvod_ctx* c, int batch) {
     }
     pos += (fr->n_vox + 3) & ~3;
   }
-  c->launches += launch_upload_words(c->h_vcls.p, c->d_vcls.p, (long long)words, c->stream);
+  CU(cudaMemcpyAsync(c->d_vcls.p, c->h_vcls.p, sizeof(int32_t) * words, cudaMemcpyHostToDevice, c->stream));
   c->launches += launch_final_labels(pb.off_dev.p, pb.scan_counts_dev.p, pb.nscans, pb.max_n, pb.apri_src.p, pb.apri_cid.p, c->d_vcls.p,
                                      reinterpret_cast<const uint8_t*>(c->d_vcls.p + pb.nscans), pb.cls.p, c->stream);
   CU(cudaGetLastError());
@@ -1126,7 +1218,7 @@ extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float
   CU(c->h_Ts.alloc(std::max(1, nf) * 12));
   CU(c->d_Ts.alloc(std::max(1, nf) * 12));
   for (int f = f0; f < f1; ++f) pose_matrix(poses6 + 6 * f, c->h_Ts.p + 12 * (f - f0));
-  if (nf > 0) c->launches += launch_upload_words(c->h_Ts.p, c->d_Ts.p, 12LL * nf, c->stream);
+  if (nf > 0) CU(cudaMemcpyAsync(c->d_Ts.p, c->h_Ts.p, sizeof(float) * 12 * nf, cudaMemcpyHostToDevice, c->stream));
   int f = f0;
   while (f < f1) {
     FrameHost& fr = c->frames[f];
@@ -1156,6 +1248,14 @@ extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float
   FrameHost& fr = c->frames[frame];                                                                      \
   PersistBatch& pb = *c->batches[fr.batch];                                                              \
   (void)pb;
+// the same, but SCVOD_INIT_FRAME selects the frame produced by scvod_initialization: per-point / per-voxel data of its
+// base frame, clusters and voxel labels of the initialised copy (fcl)
+#define FRAME_OR_INIT_OR_FAIL()                                                                                          \
+  if (c && frame == SCVOD_INIT_FRAME && !c->have_init) return fail(SCVOD_ERR_STATE, "scvod_initialization has not run"); \
+  const bool is_init__ = c && frame == SCVOD_INIT_FRAME;                                                                 \
+  if (is_init__) frame = c->init_base;                                                                                   \
+  FRAME_OR_FAIL();                                                                                                       \
+  FrameClusters& fcl = is_init__ ? c->init_fc : fr.fc;
 
 template <typename T>
 static int d2h(scvod_ctx* c, T* dst, const T* src, size_t n) {
@@ -1165,16 +1265,16 @@ static int d2h(scvod_ctx* c, T* dst, const T* src, size_t n) {
 }
 
 extern "C" int scvod_frame_counts(scvod_ctx* c, int frame, int32_t counts[9]) {
-  FRAME_OR_FAIL();
+  FRAME_OR_INIT_OR_FAIL();
   counts[0] = fr.n_in;
   counts[1] = fr.n_ground;
   counts[2] = fr.n_ng;
   counts[3] = fr.n_apri;
   counts[4] = fr.n_vox;
-  counts[5] = fr.fc.n_clusters[0];
-  counts[6] = fr.fc.n_clusters[1];
-  counts[7] = fr.fc.n_clusters[2];
-  counts[8] = (int)fr.fc.cluster_set.size();
+  counts[5] = fcl.n_clusters[0];
+  counts[6] = fcl.n_clusters[1];
+  counts[7] = fcl.n_clusters[2];
+  counts[8] = (int)fcl.cluster_set.size();
   return SCVOD_OK;
 }
 
@@ -1200,7 +1300,7 @@ extern "C" int scvod_frame_apri(scvod_ctx* c, int frame, int32_t* src, int32_t* 
 
 extern "C" int scvod_frame_voxels(scvod_ctx* c, int frame, int32_t* voxel_idx, int32_t* count, float* av, float* cov, float* center,
                                   int32_t* tri, int32_t* label) {
-  FRAME_OR_FAIL();
+  FRAME_OR_INIT_OR_FAIL();
   int rc = 0;
   rc |= d2h(c, voxel_idx, pb.vox_vid.p + fr.base, fr.n_vox);
   rc |= d2h(c, count, pb.vox_cnt.p + fr.base, fr.n_vox);
@@ -1210,7 +1310,7 @@ extern "C" int scvod_frame_voxels(scvod_ctx* c, int frame, int32_t* voxel_idx, i
   rc |= d2h(c, tri, pb.vox_tri.p + 3 * fr.base, (size_t)fr.n_vox * 3);
   if (rc) return SCVOD_ERR_CUDA;
   CU(cudaStreamSynchronize(c->stream));
-  if (label) std::memcpy(label, fr.fc.vox_label.data(), sizeof(int32_t) * fr.n_vox);
+  if (label) std::memcpy(label, fcl.vox_label.data(), sizeof(int32_t) * fr.n_vox);
   return SCVOD_OK;
 }
 
@@ -1228,9 +1328,9 @@ extern "C" int scvod_frame_point_cluster(scvod_ctx* c, int frame, int stage, int
 
 extern "C" int scvod_frame_clusters(scvod_ctx* c, int frame, int cap, int32_t* name, int32_t* type, int32_t* state, int32_t* npts,
                                     int32_t* nvox, float* bbox) {
-  FRAME_OR_FAIL();
+  FRAME_OR_INIT_OR_FAIL();
   int i = 0;
-  for (auto& cs : fr.fc.cluster_set) {
+  for (auto& cs : fcl.cluster_set) {
     if (i >= cap) break;
     if (name) name[i] = cs.first;
     if (type) type[i] = cs.second.type;
@@ -1244,7 +1344,7 @@ extern "C" int scvod_frame_clusters(scvod_ctx* c, int frame, int cap, int32_t* n
       }
     ++i;
   }
-  return (int)fr.fc.cluster_set.size();
+  return (int)fcl.cluster_set.size();
 }
 
 // ---------------------------------------------------------------------------------------------

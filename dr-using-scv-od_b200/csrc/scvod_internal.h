@@ -110,8 +110,6 @@ int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, con
 // name_first is [nscans][name_cap]
 int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, bool force_global, int32_t* vox_name, int32_t* name_first, int name_cap,
                        void* stream);
-// 32-bit words from pinned (device-accessible) host memory to device memory, by a kernel instead of the copy engine
-int launch_upload_words(const void* src_pinned_host, void* dst_dev, long long nwords, void* stream);
 int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
 

@@ -595,13 +595,78 @@ __global__ void __launch_bounds__(THREADS) k_patch_sort_list(FitArgs a, const in
   }
 }
 
-constexpr int kChainWarps = 4;    // warps (= patches) per CTA of k_patch_chain
-constexpr int kChainStages = 4;   // cp.async ring depth, 32 points per stage
-constexpr int kChainCtasPerSm = 2;  // residency cap: the chain is latency bound, so few warps per scheduler keep the
-                                    // long (zone-0) patches fast while the many short ones fill the remaining slots
+// plane of one R-GPF iteration from the nine sequential sums (estimate_plane_, patchwork.h:217-232) and the gating
+// decision of the patch (patchwork.h:339-384): shared by the warp-per-patch and the thread-per-patch chain kernels
+struct PlaneState {
+  float n0 = 0.f, n1 = 0.f, n2 = 0.f, th = 0.f;
+  float meanx = 0.f, meany = 0.f, meanz = 0.f, sv0 = 0.f, sv1 = 0.f, sv2 = 0.f, d = 0.f;
+};
+
+__device__ __forceinline__ void solve_plane(float accu[9], int cnt, PlaneState& pl) {
+  const float fn = (float)cnt;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) accu[k] = dd(accu[k], fn);
+  float C[3][3];
+  C[0][0] = ds(accu[0], dm(accu[6], accu[6]));
+  C[0][1] = ds(accu[1], dm(accu[6], accu[7]));
+  C[0][2] = ds(accu[2], dm(accu[6], accu[8]));
+  C[1][1] = ds(accu[3], dm(accu[7], accu[7]));
+  C[1][2] = ds(accu[4], dm(accu[7], accu[8]));
+  C[2][2] = ds(accu[5], dm(accu[8], accu[8]));
+  C[1][0] = C[0][1];
+  C[2][0] = C[0][2];
+  C[2][1] = C[1][2];
+  float U[3][3], sv[3];
+  dev_svd3(C, U, sv);
+  pl.n0 = U[0][2];
+  pl.n1 = U[1][2];
+  pl.n2 = U[2][2];
+  // d_ = -(normal^T * mean): Eigen 3-term unrolled redux a0 + (a1 + a2)
+  pl.d = -da(dm(pl.n0, accu[6]), da(dm(pl.n1, accu[7]), dm(pl.n2, accu[8])));
+  pl.th = (float)__dsub_rn(0.1, (double)pl.d);  // th_dist_d_ = th_dist_ - d_
+  pl.meanx = accu[6];
+  pl.meany = accu[7];
+  pl.meanz = accu[8];
+  pl.sv0 = sv[0];
+  pl.sv1 = sv[1];
+  pl.sv2 = sv[2];
+}
+
+__device__ __forceinline__ void write_gating(const FitArgs& a, int p, int b, int n, int zone, const PlaneState& pl) {
+  const double ground_z_vec = (double)fabsf(pl.n2);
+  const double ground_z_elevation = (double)pl.meanz;
+  const float minsv = fminf(pl.sv0, fminf(pl.sv1, pl.sv2));
+  const double surface_variable = (double)dd(minsv, da(da(pl.sv0, pl.sv1), pl.sv2));
+  const int ring_i = (p - c_zone_base[zone]) / c_zone_sectors[zone];
+  const int concentric_idx = c_zone_ring0[zone] + ring_i;
+  int decision = 0;
+  if (ground_z_vec < 0.707) {
+    decision = 1;
+  } else if (concentric_idx < 4) {
+    if (ground_z_elevation > c_elev_thr[ring_i + 2 * zone]) decision = (c_flat_thr[ring_i + 2 * zone] > surface_variable) ? 3 : 2;
+  }
+  float* rec = a.patch_plane + (size_t)(b * kNumPatches + p) * 12;
+  rec[0] = pl.n0;
+  rec[1] = pl.n1;
+  rec[2] = pl.n2;
+  rec[3] = pl.meanx;
+  rec[4] = pl.meany;
+  rec[5] = pl.meanz;
+  rec[6] = pl.sv0;
+  rec[7] = pl.sv1;
+  rec[8] = pl.sv2;
+  rec[9] = pl.d;
+  rec[10] = (float)decision;
+  rec[11] = (float)n;
+}
 
 // smallest float >= d: for a float z, ((double)z < d) == (z < float_at_or_above(d))
 __device__ __forceinline__ float float_at_or_above(double d) { return __double2float_ru(d); }
+
+constexpr int kChainWarps = 4;    // warps (= patches) per CTA of k_patch_chain
+constexpr int kChainStages = 4;   // cp.async ring depth, 32 points per stage
+constexpr int kChainCtasPerSm = 3;  // residency cap: the chain is latency bound, so few warps per scheduler keep the
+                                    // long (zone-0) patches fast while the many short ones fill the remaining slots
 
 __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int nscans, const int32_t* __restrict__ sort_list,
                                                                   int32_t* __restrict__ sort_ctr, int list_cap) {
@@ -659,8 +724,8 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
   }
   const float seed_cut = float_at_or_above(__dadd_rn(lpr, 0.3));  // z < lpr + th_seeds_ (patchwork.h:262)
 
-  float n0 = 0.f, n1 = 0.f, n2 = 0.f, th = 0.f;
-  float st_meanx = 0.f, st_meany = 0.f, st_meanz = 0.f, st_sv0 = 0.f, st_sv1 = 0.f, st_sv2 = 0.f, st_d = 0.f;
+  PlaneState pl;
+  float &n0 = pl.n0, &n1 = pl.n1, &n2 = pl.n2, &th = pl.th;
   const int nstages = (n + 31) >> 5;
   auto issue = [&](int st) {  // branch-free: past the end of the patch the copy degenerates to a zero fill (src-size 0)
     const int j = st * 32 + lane;
@@ -725,63 +790,10 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
     if (cnt == 0) {
       if (lane == 0) atomicOr(a.err, 2);  // cannot happen for finite input; plane kept
     } else {  // every lane evaluates the (tiny) plane solve redundantly: no broadcast, no divergence
-      const float fn = (float)cnt;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) accu[k] = dd(accu[k], fn);
-      float C[3][3];
-      C[0][0] = ds(accu[0], dm(accu[6], accu[6]));
-      C[0][1] = ds(accu[1], dm(accu[6], accu[7]));
-      C[0][2] = ds(accu[2], dm(accu[6], accu[8]));
-      C[1][1] = ds(accu[3], dm(accu[7], accu[7]));
-      C[1][2] = ds(accu[4], dm(accu[7], accu[8]));
-      C[2][2] = ds(accu[5], dm(accu[8], accu[8]));
-      C[1][0] = C[0][1];
-      C[2][0] = C[0][2];
-      C[2][1] = C[1][2];
-      float U[3][3], sv[3];
-      dev_svd3(C, U, sv);
-      n0 = U[0][2];
-      n1 = U[1][2];
-      n2 = U[2][2];
-      // d_ = -(normal^T * mean): Eigen 3-term unrolled redux a0 + (a1 + a2)
-      st_d = -da(dm(n0, accu[6]), da(dm(n1, accu[7]), dm(n2, accu[8])));
-      th = (float)__dsub_rn(0.1, (double)st_d);  // th_dist_d_ = th_dist_ - d_
-      st_meanx = accu[6];
-      st_meany = accu[7];
-      st_meanz = accu[8];
-      st_sv0 = sv[0];
-      st_sv1 = sv[1];
-      st_sv2 = sv[2];
+      solve_plane(accu, cnt, pl);
     }
   }
-  // ---- gating (patchwork.h:339-384) ------------------------------------------------------------------
-  if (lane == 0) {
-    const double ground_z_vec = (double)fabsf(n2);
-    const double ground_z_elevation = (double)st_meanz;
-    const float minsv = fminf(st_sv0, fminf(st_sv1, st_sv2));
-    const double surface_variable = (double)dd(minsv, da(da(st_sv0, st_sv1), st_sv2));
-    const int ring_i = (p - c_zone_base[zone]) / c_zone_sectors[zone];
-    const int concentric_idx = c_zone_ring0[zone] + ring_i;
-    int decision = 0;
-    if (ground_z_vec < 0.707) {
-      decision = 1;
-    } else if (concentric_idx < 4) {
-      if (ground_z_elevation > c_elev_thr[ring_i + 2 * zone]) decision = (c_flat_thr[ring_i + 2 * zone] > surface_variable) ? 3 : 2;
-    }
-    float* rec = a.patch_plane + (size_t)(b * kNumPatches + p) * 12;
-    rec[0] = n0;
-    rec[1] = n1;
-    rec[2] = n2;
-    rec[3] = st_meanx;
-    rec[4] = st_meany;
-    rec[5] = st_meanz;
-    rec[6] = st_sv0;
-    rec[7] = st_sv1;
-    rec[8] = st_sv2;
-    rec[9] = st_d;
-    rec[10] = (float)decision;
-    rec[11] = (float)n;
-  }
+  if (lane == 0) write_gating(a, p, b, n, zone, pl);
   __syncwarp();
   }  // queue loop
 }
@@ -1204,15 +1216,34 @@ __global__ void __launch_bounds__(256) k_vox_nbr(const int64_t* __restrict__ off
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
     int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
     int32_t* out = vox_nbr + 27 * (base + v);
-    int t = 0;
+    // the three sector neighbours of a (range, azimuth) row are consecutive bits of the occupancy bitmap: one or two
+    // word loads per row instead of three lookups; output order = findVoxelNeighbors order (x, y, z nested, :400-407)
+    const int y_lo = max(0, si - 1), y_hi = min(g.sector_num - 1, si + 1);
     for (int x = ri - 1; x <= ri + 1; ++x)
-      for (int y = si - 1; y <= si + 1; ++y)
-        for (int z = ei - 1; z <= ei + 1; ++z) {
-          int cid = -1;
-          if (!(x > g.range_num - 1 || x < 0 || y > g.sector_num - 1 || y < 0 || z > g.azimuth_num - 1 || z < 0))
-            cid = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
-          out[t++] = cid;
+      for (int z = ei - 1; z <= ei + 1; ++z) {
+        uint32_t occ = 0, w_lo = 0, w_hi = 0;
+        int key_lo = 0;
+        if (!(x > g.range_num - 1 || x < 0 || z > g.azimuth_num - 1 || z < 0) && y_lo <= y_hi) {
+          key_lo = x * g.sector_num + y_lo + z * g.range_num * g.sector_num + g.key_off;
+          const int key_hi = key_lo + (y_hi - y_lo);
+          if (key_lo >= 0 && key_hi < g.key_count) {
+            w_lo = bm[key_lo >> 5];
+            w_hi = ((key_hi >> 5) != (key_lo >> 5)) ? bm[key_hi >> 5] : 0u;
+            occ = (uint32_t)((((unsigned long long)w_hi << 32) | w_lo) >> (key_lo & 31)) & ((1u << (y_hi - y_lo + 1)) - 1u);
+          }
         }
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int y = si + dy, j = y - y_lo;
+          int cid = -1;
+          if (y >= y_lo && y <= y_hi && ((occ >> j) & 1u)) {
+            const int key = key_lo + j;
+            const uint32_t w = ((key >> 5) == (key_lo >> 5)) ? w_lo : w_hi;
+            cid = wr[key >> 5] + __popc(w & ((1u << (key & 31)) - 1u));
+          }
+          out[((x - ri + 1) * 3 + (dy + 1)) * 3 + (z - ei + 1)] = cid;
+        }
+      }
     vox_root[base + v] = v;
   }
 }
@@ -1269,9 +1300,10 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(const int64_t* __restrict__
 }
 
 // directed component edges (root(v) -> root(n)) for every voxel pair that satisfies the intensity
-// similarity test of refineClusterByIntensity (ssc.cpp:588-594); self pairs included.  One warp per voxel:
-// the lanes share the up to 125 neighbour lookups (two dependent L2 loads each), duplicates inside a round are
-// dropped with match_any, the rest by the per-scan hash set.
+// similarity test of refineClusterByIntensity (ssc.cpp:588-594); self pairs included.  One warp per voxel, one lane
+// per (range, azimuth) row of the search cube: the <= 5 sector neighbours of a row are consecutive bits of the
+// occupancy bitmap, so a row costs one or two word loads instead of five lookups; only occupied neighbours go on
+// to the rank / descriptor loads.  Duplicates inside a round are dropped with match_any, the rest by the hash set.
 __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts, GridSpec g,
                                                        const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
                                                        const int32_t* __restrict__ vox_tri, const float* __restrict__ vox_av,
@@ -1290,42 +1322,61 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
     const int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
     const int size = ((double)ri > (double)g.range_num * 0.6) ? 1 : search_c;  // ssc.cpp:397-399
-    const int side = 2 * size + 1, total = side * side * side;
+    const int side = 2 * size + 1, rows = side * side;
     const float avv = vox_av[base + v];
     const int rv = vox_root[base + v];
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      int ru = -1;
-      if (t < total) {
-        const int x = ri - size + t / (side * side), y = si - size + (t / side) % side, z = ei - size + t % side;
-        if (!(x > g.range_num - 1 || x < 0 || y > g.sector_num - 1 || y < 0 || z > g.azimuth_num - 1 || z < 0)) {
-          const int u = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
-          if (u >= 0 && vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) ru = vox_root[base + u];
+    const int y_lo = max(0, si - size), y_hi = min(g.sector_num - 1, si + size);  // clipped, no wrap (ssc.cpp:400-407)
+    for (int r0 = 0; r0 < rows; r0 += 32) {  // search_c <= 2: a single round
+      const int row = r0 + lane;
+      uint32_t occ = 0;   // occupied sectors y_lo + j of this lane's row
+      uint32_t w_lo = 0, w_hi = 0;
+      int key_lo = 0;
+      if (row < rows && y_lo <= y_hi) {
+        const int x = ri - size + row / side, z = ei - size + row % side;
+        if (!(x > g.range_num - 1 || x < 0 || z > g.azimuth_num - 1 || z < 0)) {
+          key_lo = x * g.sector_num + y_lo + z * g.range_num * g.sector_num + g.key_off;
+          const int key_hi = key_lo + (y_hi - y_lo);
+          if (key_lo >= 0 && key_hi < g.key_count) {
+            w_lo = bm[key_lo >> 5];
+            w_hi = ((key_hi >> 5) != (key_lo >> 5)) ? bm[key_hi >> 5] : 0u;
+            const unsigned long long both = ((unsigned long long)w_hi << 32) | w_lo;
+            occ = (uint32_t)(both >> (key_lo & 31)) & ((1u << (y_hi - y_lo + 1)) - 1u);
+          }
         }
       }
-      const unsigned same = __match_any_sync(0xffffffffu, ru);
-      if (ru < 0 || (same & ((1u << lane) - 1u))) continue;  // nothing, or a lower lane inserts this root
-      unsigned long long key = ((unsigned long long)(uint32_t)rv << 32) | (uint32_t)ru;
-      unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
-      int slot = (int)(h >> 40) % hash_cap;
-      bool inserted = false, done = false;
-      for (int probe = 0; probe < hash_cap && !done; ++probe) {
-        unsigned long long old = atomicCAS(&table[slot], ~0ull, key);
-        if (old == ~0ull) {
-          inserted = true;
-          done = true;
-        } else if (old == key) {
-          done = true;
-        } else {
-          slot = (slot + 1 == hash_cap) ? 0 : slot + 1;
+      for (int j = 0; j < side; ++j) {  // warp-uniform trip count; lanes without a j-th sector idle
+        int ru = -1;
+        if ((occ >> j) & 1u) {
+          const int key = key_lo + j;
+          const uint32_t w = ((key >> 5) == (key_lo >> 5)) ? w_lo : w_hi;
+          const int u = wr[key >> 5] + __popc(w & ((1u << (key & 31)) - 1u));
+          if (vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) ru = vox_root[base + u];
         }
-      }
-      if (!done) atomicExch(&scan_counts[b * 8 + 7], -1 << 20);  // table full
-      if (inserted) {
-        int e = atomicAdd(&scan_counts[b * 8 + 7], 1);
-        if (e >= 0 && e < edge_cap) {
-          edge_buf[((size_t)b * edge_cap + e) * 2] = rv;
-          edge_buf[((size_t)b * edge_cap + e) * 2 + 1] = ru;
+        if (__ballot_sync(0xffffffffu, ru >= 0) == 0u) continue;
+        const unsigned same = __match_any_sync(0xffffffffu, ru);
+        if (ru < 0 || (same & ((1u << lane) - 1u))) continue;  // nothing, or a lower lane inserts this root
+        unsigned long long key = ((unsigned long long)(uint32_t)rv << 32) | (uint32_t)ru;
+        unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
+        int slot = (int)(h >> 40) % hash_cap;
+        bool inserted = false, done = false;
+        for (int probe = 0; probe < hash_cap && !done; ++probe) {
+          unsigned long long old = atomicCAS(&table[slot], ~0ull, key);
+          if (old == ~0ull) {
+            inserted = true;
+            done = true;
+          } else if (old == key) {
+            done = true;
+          } else {
+            slot = (slot + 1 == hash_cap) ? 0 : slot + 1;
+          }
+        }
+        if (!done) atomicExch(&scan_counts[b * 8 + 7], -1 << 20);  // table full
+        if (inserted) {
+          int e = atomicAdd(&scan_counts[b * 8 + 7], 1);
+          if (e >= 0 && e < edge_cap) {
+            edge_buf[((size_t)b * edge_cap + e) * 2] = rv;
+            edge_buf[((size_t)b * edge_cap + e) * 2 + 1] = ru;
+          }
         }
       }
     }
@@ -1904,13 +1955,6 @@ __global__ void __launch_bounds__(256) k_submap(const float4* __restrict__ pts, 
   }
 }
 
-// Small host -> device uploads (tracking segments, per-voxel classes, poses) done by SMs reading pinned host memory:
-// a cudaMemcpyAsync would queue on the copy engine behind the bulk scan uploads of the other contexts of this GPU,
-// which stalls the latency-critical tracking chain for milliseconds.
-__global__ void __launch_bounds__(256) k_upload_words(const int32_t* __restrict__ src_host, int32_t* __restrict__ dst, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src_host[i];
-}
-
 // gather of the per-scan voxel tables into one packed buffer (one D2H instead of hundreds)
 __global__ void __launch_bounds__(256) k_pack(const PackDesc* __restrict__ descs, int32_t* __restrict__ out) {
   const PackDesc d = descs[blockIdx.y];
@@ -2259,14 +2303,6 @@ int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, boo
   } else {  // very dense scans: union-find state in (L2-resident) global scratch that the earlier stages are done with
     { TIMED("k_name_replay_global", TSTREAM); k_name_replay<NW, true><<<nscans, NW * 32, ring, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, d.slot_pos, vox_name, name_first, name_cap); }
   }
-  return 1;
-}
-
-int launch_upload_words(const void* src_pinned_host, void* dst_dev, long long nwords, void* stream_) {
-  if (nwords <= 0) return 0;
-  long long blocks = (nwords + 1023) / 1024;
-  if (blocks > 64) blocks = 64;
-  { TIMED("k_upload_words", TSTREAM); k_upload_words<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const int32_t*)src_pinned_host, (int32_t*)dst_dev, nwords); }
   return 1;
 }
 

@@ -104,6 +104,7 @@ class SSC : public Utility {
  private:
   void fillFrameFromContext(int f, const pcl::PointCloud<pcl::PointXYZI>::Ptr& cloudIn_);
   void refreshClusters(Frame& frame_);
+  void refreshClustersFrom(Frame& frame_, int scvod_frame_index);  // SCVOD_INIT_FRAME: the initialised frame
   scvod_ctx* ctx_ = nullptr;
   int ctx_points_ = 0, ctx_batch_ = 0;
   pcl::PointCloud<pcl::PointXYZI>::Ptr last_input_;

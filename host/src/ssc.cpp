@@ -314,9 +314,12 @@ void SSC::process(const pcl::PointCloud<pcl::PointXYZI>::Ptr& cloudIn_) {
 }
 
 void SSC::refreshClusters(Frame& fr) {
+  if (fr.scvod_frame >= 0) refreshClustersFrom(fr, fr.scvod_frame);
+}
+
+// cluster_set / voxel labels of `fr` from frame f of the library (f may be SCVOD_INIT_FRAME)
+void SSC::refreshClustersFrom(Frame& fr, int f) {
   scvod_ctx* c = context();
-  const int f = fr.scvod_frame;
-  if (f < 0) return;
   int32_t cnt[9];
   check(scvod_frame_counts(c, f, cnt), "scvod_frame_counts");
   const int V = cnt[4], C = cnt[8];
@@ -440,11 +443,27 @@ void SSC::tracking(Frame& frame_pre_, Frame& frame_next_, Pose pose_pre_, Pose p
   refreshClusters(frame_next_);
 }
 
-// SSC::intialization (src/ssc.cpp:1148-1248) is dead code in the reference (never called by segDF) and is the
-// first "next" row of the scope table: not implemented; the base frame is returned unchanged.
-Frame SSC::intialization(const std::vector<Frame>& frames_, const std::vector<Pose>&) {
-  ROS_WARN("SSC::intialization is not implemented on the B200 path yet");
-  return frames_.empty() ? Frame() : frames_.front();
+// SSC::intialization (src/ssc.cpp:1148-1248; dead code in the reference, never called by segDF): the frames must be the
+// frames of this object in order (they carry their library index); the diff against the base frame and the cluster
+// fusion run in scvod_initialization, the returned frame is a copy of the base frame with the fused clusters.
+Frame SSC::intialization(const std::vector<Frame>& frames_, const std::vector<Pose>& poses_) {
+  if (frames_.empty() || poses_.size() < frames_.size()) return Frame();
+  scvod_ctx* c = context();
+  for (size_t i = 0; i < frames_.size(); ++i) {
+    if (frames_[i].scvod_frame != (int)i) {
+      ROS_WARN("intialization: frame %d is not frame %d of this SSC object", frames_[i].scvod_frame, (int)i);
+      return frames_.front();
+    }
+  }
+  std::vector<float> poses((size_t)6 * frames_.size(), 0.f);
+  for (size_t i = 0; i < frames_.size(); ++i) pose6(poses_[i], &poses[6 * i]);
+  int32_t id_based = -1;
+  check(scvod_initialization(c, poses.data(), (int)frames_.size(), &id_based), "scvod_initialization");
+  Frame frame_based = frames_[id_based];
+  refreshClustersFrom(frame_based, SCVOD_INIT_FRAME);
+  mapping_init = true;  // ssc.cpp:1243
+  ROS_INFO("initialization: based_id: %d, initialized cluster_num: %d", frame_based.id, (int)frame_based.cluster_set.size());
+  return frame_based;
 }
 
 // ---------------------------------------------------------------------------------------------------------

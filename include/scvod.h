@@ -129,6 +129,15 @@ int scvod_push_scans_dev(scvod_ctx* ctx, const void* xyzi_dev, const int64_t* of
  * tracking() reads (utility.h:77-93).  first_frame = index of the first pose's frame. */
 int scvod_track(scvod_ctx* ctx, const float* poses6, int nposes);
 
+/* SSC::intialization (ssc.cpp:1148-1248; dead code in the reference, its call is commented out at :1456-1470): every pushed
+ * frame is diffed against the "base" frame — the LAST frame with the fewest clusters (:1153-1158) — through
+ * trans_based.inverse() * trans_i, and the base-frame clusters that one transformed cluster bridges with a voxel ratio
+ * >= occupancy are fused (:1208-1233); recognize() then re-types the clusters of the result (:1241).  Must run before
+ * scvod_track (it reads the untracked clouds).  The initialised frame is kept in the context: pass SCVOD_INIT_FRAME as the
+ * frame index of scvod_frame_counts / scvod_frame_clusters / scvod_frame_voxels (labels) to read it. */
+#define SCVOD_INIT_FRAME (-1)
+int scvod_initialization(scvod_ctx* ctx, const float* poses6, int nposes, int32_t* id_based);
+
 int scvod_num_frames(const scvod_ctx* ctx);
 int scvod_reset_frames(scvod_ctx* ctx); /* SSC::reset + frame_set.clear() */
 

@@ -993,6 +993,78 @@ class SSCOracle {
     }
   }
 
+  // SSC::intialization (ssc.cpp:1148-1248; dead code in the reference: the call is commented out at :1456-1470).
+  // Every frame of the window is diffed against the frame with the fewest clusters; base-frame clusters that one
+  // transformed cluster bridges with enough occupancy are fused.  Returns the index of the base frame; the
+  // initialised frame is kept in init_frame.
+  Frame init_frame;
+  int initialization(const float* poses6, int nposes) {
+    const int nf = (int)std::min<size_t>(frame_set.size(), (size_t)nposes);
+    int max_num = 999999, id_based = 0;
+    for (int i = 0; i < nf; i++) {
+      if ((int)frame_set[i].cluster_set.size() <= max_num) {
+        max_num = (int)frame_set[i].cluster_set.size();
+        id_based = i;
+      }
+    }
+    Frame frame_based = frame_set[id_based];
+    float trans_based[3][4], inv_based[3][4];
+    pcl_get_transformation(poses6 + 6 * id_based, trans_based);
+    affine_inverse(trans_based, inv_based);
+    for (int i = 0; i < nf; i++) {
+      if (i == id_based) continue;
+      Frame frame_i = frame_set[i];
+      float trans_i[3][4], trans_bi[3][4];
+      pcl_get_transformation(poses6 + 6 * i, trans_i);
+      affine_mul(inv_based, trans_i, trans_bi);
+      for (auto& c : frame_i.cluster_set) {
+        Cloud cluster;
+        transformCloud(c.second.cloud, trans_bi, cluster);
+        std::unordered_map<int, std::vector<int>> remap_name;
+        for (size_t k = 0; k < cluster.size(); k++) {
+          Pt pt = cluster[k];
+          float dis, angle, azimuth;
+          int ri, si, ei, voxel_idx;
+          binPoint(pt, dis, angle, azimuth, ri, si, ei, voxel_idx);
+          auto it_find = frame_based.hash_cloud.find(voxel_idx);
+          if (it_find != frame_based.hash_cloud.end() && it_find->second.label != -1) {
+            auto l_find = remap_name.find(it_find->second.label);
+            if (l_find == remap_name.end()) {
+              std::vector<int> vec;
+              vec.emplace_back(it_find->first);
+              remap_name.insert(std::make_pair(it_find->second.label, vec));
+            } else {
+              l_find->second.emplace_back(it_find->first);
+            }
+          }
+        }
+        if (remap_name.size() > 1) {
+          Cluster cluster_fusion;  // name stays -1 when no label passes the occupancy test (utility.h:154)
+          std::vector<int> erase_id;
+          for (auto& re : remap_name) {
+            sampleVec(re.second);
+            if (((float)re.second.size() / (float)frame_based.cluster_set[re.first].occupy_voxels.size()) >= P.occupancy) {
+              erase_id.emplace_back(re.first);
+              cluster_fusion.name = re.first;
+              addVec(cluster_fusion.occupy_pts, frame_based.cluster_set[re.first].occupy_pts);
+              addVec(cluster_fusion.occupy_voxels, frame_based.cluster_set[re.first].occupy_voxels);
+              Cloud& src = frame_based.cluster_set[re.first].cloud;
+              cluster_fusion.cloud.insert(cluster_fusion.cloud.end(), src.begin(), src.end());
+            }
+          }
+          for (auto& e : erase_id) frame_based.cluster_set.erase(e);
+          frame_based.cluster_set.insert(std::make_pair(cluster_fusion.name, cluster_fusion));
+          for (auto& v : cluster_fusion.occupy_voxels) frame_based.hash_cloud[v].label = cluster_fusion.name;
+        }
+      }
+    }
+    // recognize(frame_based) (ssc.cpp:1241) takes the bounding box of the cluster clouds as they are now
+    for (auto& c : frame_based.cluster_set) getBoundingBoxOfCloud(c.second.cloud, c.second.bb_min, c.second.bb_max);
+    recognize(frame_based);
+    init_frame = frame_based;
+    return id_based;
+  }
+
   // one iteration of the scan loop of segDF (ssc.cpp:1435-1444) without saveSegCloud
   int pushScan(const float* xyzi, int n) {
     Cloud in(n);
@@ -1040,6 +1112,9 @@ class SSCOracle {
 // ---------------------------------------------------------------------------------------------
 // extern "C" surface for ctypes (tests / bench cpu_baseline only)
 // ---------------------------------------------------------------------------------------------
+// frame f of the sequence, or the frame produced by orc_initialization when f == -1
+static Frame& frame_ref(void* h, int f) { return f < 0 ? ((SSCOracle*)h)->init_frame : ((SSCOracle*)h)->frame_set[f]; }
+
 extern "C" {
 
 void* orc_create(const scvod_params* p) { return new SSCOracle(*p); }
@@ -1063,7 +1138,7 @@ void orc_reset_frames(void* h) {
 }
 void orc_frame_labels(void* h, int f, uint8_t* cls) { ((SSCOracle*)h)->frameLabels(f, cls); }
 void orc_frame_counts(void* h, int f, int32_t c[9]) {
-  Frame& fr = ((SSCOracle*)h)->frame_set[f];
+  Frame& fr = frame_ref(h, f);
   c[0] = fr.n_in;
   c[1] = (int)fr.ground_src.size();
   c[2] = (int)fr.nonground_src.size();
@@ -1084,9 +1159,11 @@ void orc_frame_apri(void* h, int f, int32_t* src, int32_t* vid) {
   if (src) std::memcpy(src, fr.apri_src.data(), fr.apri_src.size() * 4);
   if (vid) std::memcpy(vid, fr.apri_vid.data(), fr.apri_vid.size() * 4);
 }
+int orc_initialization(void* h, const float* poses6, int nposes) { return ((SSCOracle*)h)->initialization(poses6, nposes); }
+
 void orc_frame_voxels(void* h, int f, int32_t* vid, int32_t* count, float* av, float* cov, float* center, int32_t* tri,
                       int32_t* label) {
-  Frame& fr = ((SSCOracle*)h)->frame_set[f];
+  Frame& fr = frame_ref(h, f);
   std::vector<int> keys;
   for (auto& v : fr.hash_cloud) keys.push_back(v.first);
   std::sort(keys.begin(), keys.end());
@@ -1115,7 +1192,7 @@ void orc_frame_point_cluster(void* h, int f, int stage, int32_t* name) {
 }
 int orc_frame_clusters(void* h, int f, int cap, int32_t* name, int32_t* type, int32_t* state, int32_t* npts, int32_t* nvox,
                        float* bbox) {
-  Frame& fr = ((SSCOracle*)h)->frame_set[f];
+  Frame& fr = frame_ref(h, f);
   int i = 0;
   for (auto& c : fr.cluster_set) {
     if (i >= cap) break;

@@ -70,6 +70,12 @@ class Oracle:
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
         self.lib.orc_track(self.h, _ptr(poses), len(poses))
 
+    def initialization(self, poses):
+        """SSC::intialization restated (oracle/scvod_oracle.cpp); the initialised frame is read with f = -1."""
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        self.lib.orc_initialization.restype = ctypes.c_int
+        return int(self.lib.orc_initialization(self.h, _ptr(poses), len(poses)))
+
     def reset(self):
         self.lib.orc_reset_frames(self.h)
         self.sizes = []

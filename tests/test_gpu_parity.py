@@ -186,6 +186,37 @@ def test_name_replay_global_memory_variant(pkg, oracle):
     s.close()
 
 
+@pytest.mark.parametrize("config,seed_off,rings,cols,nframes", [("semantickitti", 0, 64, 1800, 6), ("parkinglot", 3, 32, 900, 8),
+                                                               ("parkinglot", 0, 64, 1800, 6), ("semantickitti", 1, 32, 900, 10)])
+def test_initialization_matches_oracle(pkg, config, seed_off, rings, cols, nframes):
+    """SSC::intialization (ssc.cpp:1148-1248, SURVEY 8(f) row 1): base frame choice, fused clusters (including the nameless
+    cluster the reference inserts when no label passes the occupancy test), re-recognised types and voxel labels."""
+    params = getattr(pkg, config + "_params")()
+    s = pkg.SSC(params, device=0, max_points=rings * cols, max_batch=8)
+    orc = conftest.Oracle(params)
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED + seed_off, k, rings=rings, cols=cols) for k in range(nframes)])
+    poses = np.stack(poses)
+    s.process(scans)
+    for sc in scans:
+        orc.push_scan(sc)
+    base = s.intialization(poses)
+    assert base == orc.initialization(poses)
+    cg, co = s.frame_clusters(pkg.INIT_FRAME), orc.clusters(-1)
+    for k in ("name", "type", "npts", "nvox"):
+        assert np.array_equal(cg[k], co[k]), k  # same clusters in the same unordered_map iteration order
+    assert np.array_equal(cg["bbox"].view(np.uint32), co["bbox"].view(np.uint32))
+    assert np.array_equal(s.frame_voxels(pkg.INIT_FRAME)["label"], orc.voxels(-1)["label"])
+    # the sequence itself is untouched: tracking afterwards gives the usual labels
+    s.tracking(poses)
+    orc.track(poses)
+    for f in range(nframes):
+        assert np.array_equal(s.frame_labels(f), orc.labels(f))
+    with pytest.raises(pkg.ScvodError):
+        s.intialization(poses)  # only before tracking
+    s.close()
+    orc.close()
+
+
 def test_long_sequence_labels(pkg, oracle):
     """40-frame chain at reduced resolution: exercises carried clouds, splits and fusions of tracking."""
     s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=16)

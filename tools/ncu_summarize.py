@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Turn the ncu outputs of a gpurun call into the small CSVs kept under profiles/.
+
+  python tools/ncu_summarize.py launches <launches.csv> <out_by_kernel.csv>
+      per-kernel aggregation of an `ncu --metrics gpu__time_duration.sum --csv` launch list
+  python tools/ncu_summarize.py full <report.ncu-rep> <out_summary.csv>
+      one row per captured launch of an `ncu --set full` report (duration, grid, registers, shared memory, achieved
+      occupancy, DRAM bytes read/written, DRAM and SM throughput, L2 bytes, instructions, shared-memory bank conflicts)
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+FULL_COLS = [
+    "Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "smsp__inst_executed.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
+]
+
+
+def launches(src, dst):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", row["Kernel Name"])
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        v = v / 1000 if unit == "ns" else v * 1000 if unit == "ms" else v
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    total = sum(a[1] for a in agg.values())
+    with open(dst, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "launches", "total_us", "avg_us", "share"])
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([k, a[0], f"{a[1]:.1f}", f"{a[1] / a[0]:.1f}", f"{a[1] / total:.4f}"])
+    print(f"{len(agg)} kernels, {total / 1000:.3f} ms of kernel time -> {dst}")
+
+
+def full(rep, dst):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = [hdr.index(c) for c in FULL_COLS if c in hdr]
+    with open(dst, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in idx])
+        w.writerow([units[i] for i in idx])
+        for d in data:
+            w.writerow([d[i][:70] for i in idx])
+    print(f"{len(data)} launches -> {dst}")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) != 4 or sys.argv[1] not in ("launches", "full"):
+        sys.exit(__doc__)
+    (launches if sys.argv[1] == "launches" else full)(sys.argv[2], sys.argv[3])
