@@ -73,7 +73,6 @@ __constant__ int c_zone_ring0[4] = {0, 2, 6, 10};  // concentric_idx of the zone
 __constant__ double c_elev_thr[4] = {-1.2, -0.9984, -0.851, -0.605};
 __constant__ double c_flat_thr[4] = {0.0, 0.000125, 0.000185, 0.000185};
 
-constexpr int kTrackSegSmem = 8192;  // segments whose start offsets are staged in shared memory by k_track
 
 struct Mat34 {
   float m[12];
@@ -1787,33 +1786,40 @@ __global__ void __launch_bounds__(256) k_bin_only(const float4* __restrict__ pts
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, const int32_t* __restrict__ vox_off,
                                                const int32_t* __restrict__ vox_pts, const float4* __restrict__ carried,
-                                               const int4* __restrict__ segs, int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
+                                               const int4* __restrict__ segs /* pinned host memory */,
+                                               const int32_t* __restrict__ first_seg /* pinned host memory, per block of 256 points */,
+                                               int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
                                                float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
                                                int32_t* __restrict__ ctr /* [0] distinct hits, [1] finished CTAs */,
                                                int32_t* __restrict__ hit_list, int32_t* __restrict__ out_quads, int cap_quads) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_last;
-  // segment start offsets staged in shared memory: the per-point binary search then never leaves the SM
-  int* s_dst = reinterpret_cast<int*>(smem_raw);
-  const bool staged = nseg <= kTrackSegSmem;
-  if (staged) {
-    for (int t = threadIdx.x; t < nseg; t += blockDim.x) s_dst[t] = segs[t].x;
+  // The segment table stays in pinned host memory (no copy-engine hop on the latency-critical tracking chain, where it
+  // would queue behind the bulk scan uploads of the other contexts): a block of 256 points only needs the <= 257
+  // segments that overlap it, found through the per-block index the host wrote next to the table.
+  __shared__ int4 s_seg[257];
+  __shared__ int s_range[2];
+  const int nblk = (k + 255) >> 8;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     __syncthreads();
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
-    int lo = 0, hi = nseg - 1;  // last segment with dst_off <= i
+    if (threadIdx.x < 2) s_range[threadIdx.x] = (blk + (int)threadIdx.x < nblk) ? first_seg[blk + threadIdx.x] : nseg - 1;
+    __syncthreads();
+    const int s0 = s_range[0], cnt = s_range[1] - s0 + 1;
+    for (int t = threadIdx.x; t < cnt; t += 256) s_seg[t] = segs[s0 + t];
+    __syncthreads();
+    const int i = (blk << 8) + threadIdx.x;
+    if (i >= k) continue;
+    int lo = 0, hi = cnt - 1;  // last segment with dst_off <= i
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
-      int d = staged ? s_dst[mid] : segs[mid].x;
-      if (d <= i)
+      if (s_seg[mid].x <= i)
         lo = mid;
       else
         hi = mid - 1;
     }
     // x = dst_off, y = source (>= 0: voxel of frame_pre_, its points come from the CSR; < 0: carried range at -1-y),
     // z = cluster, w = order of the segment inside the cluster's cloud (part index / carried ordinal)
-    const int4 sg = segs[lo];
+    const int4 sg = s_seg[lo];
     const int j = i - sg.x;
     float4 p;
     unsigned low;
@@ -2255,9 +2261,9 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 }
 
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
-                 const int4* segs, int nseg, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
-                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
-                 int cap_quads, void* stream_) {
+                 const int4* segs_pinned, const int32_t* first_seg_pinned, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
+                 const int32_t* next_word_rank, int ncl, int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev,
+                 int32_t* hit_list_dev, int32_t* out_quads_mapped, int cap_quads, void* stream_) {
   if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
   Mat34 T;
@@ -2265,7 +2271,7 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   int blocks = (k + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, (nseg <= kTrackSegSmem ? nseg : 0) * sizeof(int), st>>>(own_xyzi, vox_off, vox_pts, carried, segs, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
+  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs_pinned, first_seg_pinned, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
   return 1;
 }
 
