@@ -196,9 +196,9 @@ struct scvod_ctx {
   DevBuf<int32_t> d_vox_name, d_name_first;
   int name_cap = 0;
   // tracking buffers: packed request (segments + own indices), ping-pong transformed clouds, hit table
-  DevBuf<int32_t> d_triples, d_track_ctr, d_track_list;
+  DevBuf<int32_t> d_treq, d_triples, d_track_ctr, d_track_list;
   DevBuf<unsigned long long> d_first;
-  PinBuf<int32_t> h_treq, h_tblk, h_triples;  // segment table, its per-block index, hit quads: pinned, device-accessible
+  PinBuf<int32_t> h_treq, h_triples;  // segment table + its per-block index; hit quads (written by the kernel)
   DevBuf<float4> d_tout[2];
   int tout_cur = 0;  // d_tout[tout_cur] holds the carried clouds of the frame that is the next frame_pre_
   // host scratch of track_pair, kept across pairs so that the steady state allocates nothing
@@ -445,7 +445,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_bucket_kv.release(); c->d_sorted_xyz.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
   c->h_scan_counts.release(); c->h_vox_cnt.release(); c->h_vox_root.release(); c->h_vox_nbr.release(); c->h_ev_cid.release();
   c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_first.release(); c->d_triples.release();
-  c->h_treq.release(); c->h_tblk.release(); c->h_triples.release(); c->d_track_ctr.release(); c->d_track_list.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
+  c->h_treq.release(); c->h_triples.release(); c->d_treq.release(); c->d_track_ctr.release(); c->d_track_list.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
   c->d_Ts.release(); c->h_Ts.release();
   c->d_counter.release();
   c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
@@ -793,7 +793,9 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
   const int in_buf = c->tout_cur, out_buf = 1 - c->tout_cur;
   {
     PROF("  track: gpu round trip");
-    CU(c->h_treq.alloc(std::max<size_t>(4, n_seg * 4)));
+    size_t k_bound = 0;  // upper bound of the number of points (the per-block index follows the segment table)
+    for (HCluster* cl : cars) k_bound += (size_t)std::max(0, cl->npts) + (size_t)std::max(0, cl->n_carried);
+    CU(c->h_treq.alloc(std::max<size_t>(4, n_seg * 4) + k_bound / 256 + 2));
     int32_t* seg = c->h_treq.p;
     size_t k = 0, si = 0;
     for (size_t i = 0; i < cars.size(); ++i) {
@@ -829,16 +831,18 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
     if (K > 0 && vn > 0 && si > 0) {
       c->stat_track_points += (int64_t)K;
       const int cap_quads = (int)std::min<size_t>((size_t)ncl * vn, (size_t)1 << 20);
-      // per block of 256 points: the segment that holds its first point (k_track reads only the segments of its block)
+      // per block of 256 points: the segment that holds its first point (a CTA of k_track stages only the segments of its
+      // block); the index follows the segment table in the same pinned buffer, so one small H2D copy carries both
       const size_t nblk = (K + 255) / 256;
-      CU(c->h_tblk.alloc(nblk + 1));
+      if (si * 4 + nblk + 1 > c->h_treq.n) return fail(SCVOD_ERR_STATE, "internal: cluster point counts disagree with the voxel table");
       {
-        int32_t* fs = c->h_tblk.p;
+        int32_t* fs = c->h_treq.p + si * 4;
         for (size_t s = 0; s < si; ++s) {
           const size_t lo = (size_t)seg[4 * s], hi = (s + 1 < si ? (size_t)seg[4 * (s + 1)] : K) - 1;  // points [lo, hi]
           for (size_t b = (lo + 255) / 256; b <= hi / 256; ++b) fs[b] = (int32_t)s;
         }
       }
+      CU(c->d_treq.alloc(si * 4 + nblk + 1));
       CU(c->d_tout[out_buf].alloc(K));
       {
         const size_t need = (size_t)ncl * vn;
@@ -858,8 +862,9 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
       *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
       std::atomic_thread_fence(std::memory_order_release);
       PROF("    track: enqueue+wait+read");
+      CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->stream));
       c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
-                                  reinterpret_cast<const int4*>(c->h_treq.p), c->h_tblk.p, (int)si, (int)K, T,
+                                  reinterpret_cast<const int4*>(c->d_treq.p), c->d_treq.p + si * 4, (int)si, (int)K, T,
                                   pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
                                   vn, c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads,
                                   c->stream);

@@ -98,9 +98,9 @@ int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int total
 int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t* pass, int32_t* vid, int32_t* ri, int32_t* si,
                     int32_t* ei, float* range, float* angle, float* azimuth, void* stream);
 // tracking diff of one frame pair: segments {dst_off, source (>=0 voxel of frame_pre_ / <0 carried range), cluster, order} and
-// first_seg[b] = segment that holds point 256*b, both in pinned (device-readable) host memory
+// first_seg[b] = segment that holds point 256*b (device memory)
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
-                 const int4* segs_pinned, const int32_t* first_seg_pinned, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
+                 const int4* segs, const int32_t* first_seg, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
                  const int32_t* next_word_rank, int ncl, int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev,
                  int32_t* hit_list_dev, int32_t* out_quads_mapped, int cap_quads, void* stream);
 int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,

@@ -1786,17 +1786,16 @@ __global__ void __launch_bounds__(256) k_bin_only(const float4* __restrict__ pts
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, const int32_t* __restrict__ vox_off,
                                                const int32_t* __restrict__ vox_pts, const float4* __restrict__ carried,
-                                               const int4* __restrict__ segs /* pinned host memory */,
-                                               const int32_t* __restrict__ first_seg /* pinned host memory, per block of 256 points */,
+                                               const int4* __restrict__ segs,
+                                               const int32_t* __restrict__ first_seg /* per block of 256 points */,
                                                int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
                                                float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
                                                int32_t* __restrict__ ctr /* [0] distinct hits, [1] finished CTAs */,
                                                int32_t* __restrict__ hit_list, int32_t* __restrict__ out_quads, int cap_quads) {
   __shared__ int s_last;
-  // The segment table stays in pinned host memory (no copy-engine hop on the latency-critical tracking chain, where it
-  // would queue behind the bulk scan uploads of the other contexts): a block of 256 points only needs the <= 257
-  // segments that overlap it, found through the per-block index the host wrote next to the table.
+  // A block of 256 points only needs the <= 257 segments that overlap it, found through the per-block index the host
+  // wrote next to the table: they are staged in shared memory, the per-point binary search never leaves the SM.
   __shared__ int4 s_seg[257];
   __shared__ int s_range[2];
   const int nblk = (k + 255) >> 8;
@@ -2261,7 +2260,7 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 }
 
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
-                 const int4* segs_pinned, const int32_t* first_seg_pinned, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
+                 const int4* segs, const int32_t* first_seg, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
                  const int32_t* next_word_rank, int ncl, int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev,
                  int32_t* hit_list_dev, int32_t* out_quads_mapped, int cap_quads, void* stream_) {
   if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
@@ -2271,7 +2270,7 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   int blocks = (k + 255) / 256;
   int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs_pinned, first_seg_pinned, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
+  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, first_seg, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
   return 1;
 }
 
