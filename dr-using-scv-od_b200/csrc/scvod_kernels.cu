@@ -1599,8 +1599,10 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
     const int2* my = lst + s_lbase[wid];
     // Neighbour rows (27 ints, L2 resident) are fetched one chunk of 32 events ahead with cp.async, and only for
     // voxels that are not yet stable (stable never resets): the common no-op events never touch global memory.
-    auto prefetch = [&](const int2 evn, int buf) {
-      const bool need = evn.y >= 0 && !stable[evn.y];
+    // The <= 3 events of a voxel usually sit in the same chunk: the row is fetched once per distinct voxel (by the first
+    // lane of its group, `same` = lanes with the same voxel) and the later events read it from that lane's ring slot.
+    auto prefetch = [&](const int2 evn, unsigned same, int buf) {
+      const bool need = evn.y >= 0 && !stable[evn.y] && (__ffs(same) - 1 == lane);
       unsigned pm = __ballot_sync(0xffffffffu, need);
       while (pm) {
         const int j = __ffs(pm) - 1;
@@ -1614,12 +1616,15 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
       asm volatile("cp.async.commit_group;\n" ::);
     };
     int2 nxt = (lane < L) ? my[lane] : make_int2(0, -1);
-    prefetch(nxt, 0);
+    unsigned nxt_same = __match_any_sync(0xffffffffu, nxt.y >= 0 ? nxt.y : -1 - lane);
+    prefetch(nxt, nxt_same, 0);
     for (int c = 0; c * 32 < L; ++c) {
       const int2 cur = nxt;
+      const unsigned cur_same = nxt_same;
       const int j1 = (c + 1) * 32 + lane;
       nxt = (j1 < L) ? my[j1] : make_int2(0, -1);
-      prefetch(nxt, (c + 1) & 1);
+      nxt_same = __match_any_sync(0xffffffffu, nxt.y >= 0 ? nxt.y : -1 - lane);
+      prefetch(nxt, nxt_same, (c + 1) & 1);
       asm volatile("cp.async.wait_group 1;\n" ::);
       __syncwarp();
       unsigned pend = __ballot_sync(0xffffffffu, cur.y >= 0 && !stable[cur.y]);
@@ -1628,8 +1633,13 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
         pend &= pend - 1;
         const int W = __shfl_sync(0xffffffffu, cur.y, i);
         const int e = __shfl_sync(0xffffffffu, cur.x, i);
-        if (stable[W]) continue;  // became stable inside this chunk (warp-uniform)
-        const int Vn = (lane < 27) ? ring[c & 1][i][lane] : -1;
+        const unsigned group = __shfl_sync(0xffffffffu, cur_same, i);  // events of this chunk on the same voxel
+        if (stable[W]) {  // became stable inside this chunk (warp-uniform): its other events here are no-ops too
+          pend &= ~group;
+          continue;
+        }
+        const int slot = __ffs(group) - 1;  // the row was fetched by the first event of the voxel in this chunk
+        const int Vn = (lane < 27) ? ring[c & 1][slot][lane] : -1;
         if (lane == 0 && first_ev[W] == 0x7fffffff) first_ev[W] = e;
         const bool exist = Vn >= 0;
         const int st = exist ? state[Vn] : 0;
@@ -2268,7 +2278,8 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   Mat34 T;
   for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
   int blocks = (k + 255) / 256;
-  int cap = num_sms() * 16;
+  static const int ctas_per_sm = getenv("SCVOD_TRACK_CTAS") ? std::max(1, atoi(getenv("SCVOD_TRACK_CTAS"))) : 1;  // few fat CTAs: the kernel is latency bound, a small footprint lets the other contexts' kernels co-run
+  int cap = num_sms() * ctas_per_sm;
   if (blocks > cap) blocks = cap;
   { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, first_seg, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
   return 1;

@@ -334,6 +334,45 @@ def test_full_size_batch_properties(pkg):
     t.close()
 
 
+def test_concurrent_contexts_give_the_sequential_result(pkg):
+    """bench.py runs up to 16 contexts (one per host thread and CUDA stream) on one GPU: results must not depend on it."""
+    import threading
+
+    nctx, nfr = 4, 8
+    chunks = []
+    for w in range(nctx):
+        scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 20 + w, k, rings=32, cols=900) for k in range(nfr)])
+        chunks.append((scans, np.stack(poses)))
+    ref = []
+    one = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=nfr)
+    for scans, poses in chunks:
+        one.reset()
+        ref.append([l.copy() for l in one.segDF(scans, poses)])
+    one.close()
+    ctxs = [pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=nfr) for _ in range(nctx)]
+    out, errs = [None] * nctx, []
+
+    def work(w):
+        try:
+            for _ in range(3):  # several rounds: buffers are reused, kernels of different contexts overlap
+                ctxs[w].reset()
+                out[w] = [l.copy() for l in ctxs[w].segDF(*chunks[w])]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(w,)) for w in range(nctx)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for w in range(nctx):
+        for f in range(nfr):
+            assert np.array_equal(out[w][f], ref[w][f]), (w, f)
+    for c in ctxs:
+        c.close()
+
+
 def test_aliased_voxel_scan_is_rejected_loudly(pkg):
     """Points with a -1 index (y == 0 exactly) alias voxels; clustering them is not supported yet and must
     fail with an explicit error rather than return different labels."""
