@@ -3,6 +3,7 @@
 //
 // There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -891,6 +892,7 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
               break;
             }
             if (qe != cudaErrorNotReady) return fail(SCVOD_ERR_CUDA, std::string("k_track: ") + cudaGetErrorString(qe));
+            sched_yield();  // more contexts than cores: let another worker's host work run
           }
 #if defined(__x86_64__)
           __builtin_ia32_pause();

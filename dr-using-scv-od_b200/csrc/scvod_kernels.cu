@@ -1343,17 +1343,10 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
           }
         }
       }
-      for (int j = 0; j < side; ++j) {  // warp-uniform trip count; lanes without a j-th sector idle
-        int ru = -1;
-        if ((occ >> j) & 1u) {
-          const int key = key_lo + j;
-          const uint32_t w = ((key >> 5) == (key_lo >> 5)) ? w_lo : w_hi;
-          const int u = wr[key >> 5] + __popc(w & ((1u << (key & 31)) - 1u));
-          if (vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) ru = vox_root[base + u];
-        }
-        if (__ballot_sync(0xffffffffu, ru >= 0) == 0u) continue;
-        const unsigned same = __match_any_sync(0xffffffffu, ru);
-        if (ru < 0 || (same & ((1u << lane) - 1u))) continue;  // nothing, or a lower lane inserts this root
+      // Nearly every similar neighbour is in the voxel's own component: the self edge (rv, rv) is only remembered here and
+      // inserted once per voxel after the loop; the rounds below only deal with edges to OTHER components.
+      bool self_edge = false;
+      auto insert_edge = [&](int ru) {
         unsigned long long key = ((unsigned long long)(uint32_t)rv << 32) | (uint32_t)ru;
         unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
         int slot = (int)(h >> 40) % hash_cap;
@@ -1377,7 +1370,26 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
             edge_buf[((size_t)b * edge_cap + e) * 2 + 1] = ru;
           }
         }
+      };
+      for (int j = 0; j < side; ++j) {  // warp-uniform trip count; lanes without a j-th sector idle
+        int ru = -1;
+        if ((occ >> j) & 1u) {
+          const int key = key_lo + j;
+          const uint32_t w = ((key >> 5) == (key_lo >> 5)) ? w_lo : w_hi;
+          const int u = wr[key >> 5] + __popc(w & ((1u << (key & 31)) - 1u));
+          if (vox_cov[base + u] <= intensity_cov && fabsf(ds(avv, vox_av[base + u])) <= intensity_diff) ru = vox_root[base + u];
+        }
+        if (ru == rv) {
+          self_edge = true;
+          ru = -1;
+        }
+        if (__ballot_sync(0xffffffffu, ru >= 0) == 0u) continue;
+        const unsigned same = __match_any_sync(0xffffffffu, ru);
+        if (ru < 0 || (same & ((1u << lane) - 1u))) continue;  // nothing, or a lower lane inserts this root
+        insert_edge(ru);
       }
+      const unsigned self_mask = __ballot_sync(0xffffffffu, self_edge);
+      if (self_mask && lane == __ffs(self_mask) - 1) insert_edge(rv);
     }
   }
 }
