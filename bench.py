@@ -395,6 +395,8 @@ def main():
         b0 = batches[0]
         nsample = args.cpu_sample or max(16, min(S, 4 * ncores))
         cpu_val, cpu_n, cpu_secs = cpu_baseline(pkg, params, b0["scans"], b0["poses"], ncores, nsample)
+        # the reference itself is single-threaded (OpenMP only inside transformCloud): the faithful figure, on a smaller sample
+        cpu1_val, cpu1_n, cpu1_secs = cpu_baseline(pkg, params, b0["scans"], b0["poses"], 1, 6)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * secs_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -412,7 +414,9 @@ def main():
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{cpu_n} scans of the same workload in {cpu_secs:.2f} s; oracle/scvod_oracle.cpp (reference not buildable here), "
-                                       f"per-scan stages on {ncores} threads, tracking chain serial"},
+                                       f"per-scan stages on {ncores} threads, tracking chain serial",
+                             "single_thread": {"value": cpu1_val, "unit": UNIT, "cores": 1,
+                                               "sample": f"{cpu1_n} scans in {cpu1_secs:.2f} s (how the reference itself runs: one thread)"}},
             "clocks": clocks,
             "clocks_e2e": clocks_e2e,
         }

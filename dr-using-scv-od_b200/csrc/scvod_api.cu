@@ -483,6 +483,8 @@ extern "C" int scvod_set_option(scvod_ctx* c, const char* key, int value) {
     c->host_threads = std::max(1, value);
   else if (k == "replay_global")
     c->replay_global = value != 0;
+  else if (k == "chain_tma")
+    c->hp.chain_tma = value != 0;
   else
     return fail(SCVOD_ERR_ARG, "unknown option " + k);
   return SCVOD_OK;

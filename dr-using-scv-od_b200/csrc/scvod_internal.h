@@ -89,6 +89,7 @@ struct PackDesc {
 struct HostParams {
   scvod_params p;
   GridSpec g;
+  bool chain_tma = false;  // k_patch_chain: stage the ring with cp.async.bulk + mbarrier instead of per-lane cp.async
 };
 
 // kernel launch wrappers (scvod_kernels.cu). All asynchronous on `stream`. Return launch count.

@@ -663,15 +663,56 @@ __device__ __forceinline__ void write_gating(const FitArgs& a, int p, int b, int
 __device__ __forceinline__ float float_at_or_above(double d) { return __double2float_ru(d); }
 
 constexpr int kChainWarps = 4;    // warps (= patches) per CTA of k_patch_chain
-constexpr int kChainStages = 4;   // cp.async ring depth, 32 points per stage
+constexpr int kChainStages = 4;   // ring depth, 32 points per stage
 constexpr int kChainCtasPerSm = 3;  // residency cap: the chain is latency bound, so few warps per scheduler keep the
                                     // long (zone-0) patches fast while the many short ones fill the remaining slots
 
+// ---- mbarrier + 1-D bulk async copy (TMA, UBLKCP in SASS): one elected lane moves a whole 512-byte stage ----------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+// TMA = false (default): the ring is filled with per-lane 16-byte cp.async (LDGSTS).  TMA = true: one elected lane issues one
+// 512-byte bulk copy per stage (cp.async.bulk, UBLKCP) that completes on an mbarrier.  Both were measured on B200 with the
+// same results bit for bit; the bulk-copy variant costs more issue slots per stage (elected-lane branch, arrive.expect_tx,
+// try_wait loop, one more __syncwarp) in a kernel that is issue bound: 0.31 ms vs 0.25 ms per 64 scans, so it is opt-in
+// (scvod_set_option "chain_tma").
+template <bool TMA>
 __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int nscans, const int32_t* __restrict__ sort_list,
                                                                   int32_t* __restrict__ sort_ctr, int list_cap) {
-  __shared__ float4 s_ring[kChainWarps][kChainStages][32];
+  __shared__ __align__(128) float4 s_ring[kChainWarps][kChainStages][32];
   __shared__ float s_prod[kChainWarps][2][32 * 9];
+  __shared__ __align__(8) uint64_t s_bar[kChainWarps][kChainStages];  // one "stage has landed" mbarrier per ring slot
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (TMA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kChainStages; ++i) mbar_init(&s_bar[wid][i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+  }
+  unsigned phase = 0;  // bit s: parity of the next completion of ring slot s (warp-uniform)
   // Persistent warps pull patches from one queue, longest chains first: the worklists of the sort tiers (above 16384,
   // above 4096, above 1024 points), then every remaining (patch, scan) in patch-major order (zone 0 = the largest first).
   const int c2 = sort_ctr[4], c1 = sort_ctr[2], c0 = sort_ctr[0];
@@ -726,12 +767,33 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
   PlaneState pl;
   float &n0 = pl.n0, &n1 = pl.n1, &n2 = pl.n2, &th = pl.th;
   const int nstages = (n + 31) >> 5;
-  auto issue = [&](int st) {  // branch-free: past the end of the patch the copy degenerates to a zero fill (src-size 0)
-    const int j = st * 32 + lane;
-    const bool live = j < n;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[st % kChainStages][lane]);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(S + (live ? j : 0)), "r"(live ? 16 : 0));
-    asm volatile("cp.async.commit_group;\n" ::);
+  // TMA staging: one lane arms the slot's mbarrier with the byte count and issues ONE bulk copy of the whole stage
+  // (32 points = 512 B, contiguous in the z-sorted copy); the warp waits on the mbarrier phase before it reads the slot.
+  // cp.async staging: every lane copies its own 16 bytes; past the end of the patch the copy degenerates to a zero fill.
+  uint64_t* bars = s_bar[wid];
+  auto issue = [&](int st) {
+    if (TMA) {
+      if (st < nstages && lane == 0) {
+        const unsigned bytes = 16u * (unsigned)min(32, n - st * 32);
+        mbar_expect_tx(&bars[st % kChainStages], bytes);
+        bulk_g2s(&ring[st % kChainStages][0], S + st * 32, bytes, &bars[st % kChainStages]);
+      }
+    } else {
+      const int j = st * 32 + lane;
+      const bool live = j < n;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[st % kChainStages][lane]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(S + (live ? j : 0)), "r"(live ? 16 : 0));
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
+  };
+  auto wait_stage = [&](int st) {  // stage st has landed in its ring slot
+    if (TMA) {
+      const int slot = st % kChainStages;
+      mbar_wait(&bars[slot], (phase >> slot) & 1u);
+      phase ^= 1u << slot;
+    } else {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));  // one group per stage, kChainStages in flight
+    }
   };
   // Lane L < 9 accumulates accu[L] of pcl::computeMeanAndCovarianceMatrix (xx xy xz yy yz zz x y z) STRICTLY in
   // z-sorted order — PCL's single-pass float sums are order dependent.  Per stage of 32 points the work is split:
@@ -769,20 +831,22 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
       pr[8] = in ? q.z : -0.0f;
     };
     for (int st = 0; st < kChainStages; ++st) issue(st);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));
+    wait_stage(0);
     produce(0);
-    issue(kChainStages);  // every lane refills the ring element it has just read itself
-    __syncwarp();
+    if (TMA) __syncwarp();  // every lane has read slot 0 before the async proxy overwrites it (cp.async: a lane refills its own element)
+    issue(kChainStages);
+    if (!TMA) __syncwarp();
     for (int st = 0; st < nstages; ++st) {
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(kChainStages - 1));  // stage st + 1 has landed
+      if (!TMA || st + 1 < nstages) wait_stage(st + 1);  // warp-uniform
       produce(st + 1);
-      issue(st + 1 + kChainStages);
+      if (!TMA) issue(st + 1 + kChainStages);
       const float* pc = s_prod[wid][st & 1] + col;
 #pragma unroll
       for (int t = 0; t < 32; ++t) acc = da(acc, pc[t * 9]);
-      __syncwarp();
+      __syncwarp();  // products of stage st + 1 visible; slot (st + 1) % kChainStages has been read by every lane
+      if (TMA) issue(st + 1 + kChainStages);
     }
-    asm volatile("cp.async.wait_group 0;\n" ::);
+    if (!TMA) asm volatile("cp.async.wait_group 0;\n" ::);
     float accu[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) accu[k] = __shfl_sync(0xffffffffu, acc, k);
@@ -1443,7 +1507,7 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
   const int E = scan_counts[b * 8 + 5];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nfw = (E + 31) >> 5;  // one "new class" bit per event
-  // dynamic shared memory: [neighbour-row ring NW x 2 x 32 x 32 ints][union-find state 14 B / voxel][flags + prefix]
+  // dynamic shared memory: [neighbour-row ring NW x 2 x 32 x 32 ints][union-find state 6 B / voxel][flags + prefix]
   int(*ring)[kReplayRows][32] = reinterpret_cast<int(*)[kReplayRows][32]>(smem_raw) + 2 * wid;
   unsigned char* sm_state = smem_raw + sizeof(int) * NW * 2 * kReplayRows * 32;
   int32_t *parent, *setname, *first_ev;
@@ -1459,13 +1523,15 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
     flags = reinterpret_cast<uint32_t*>(g_flags + base);  // E <= M <= N ints available: nfw flags, then nfw prefixes
     fprefix = g_flags + base + nfw;
   } else {
+    // shared memory holds what sits on the dependent path of every event (parent, state, stable: 6 B / voxel, so scans of
+    // up to ~25k voxels fit); set names and first events are written once and read at the end: global scratch
     parent = reinterpret_cast<int32_t*>(sm_state);
-    setname = parent + V;
-    first_ev = setname + V;
-    flags = reinterpret_cast<uint32_t*>(first_ev + V);
+    flags = reinterpret_cast<uint32_t*>(parent + V);
     fprefix = reinterpret_cast<int32_t*>(flags + nfw);
     state = reinterpret_cast<uint8_t*>(fprefix + nfw);
     stable = state + V;
+    setname = g_setname + base;
+    first_ev = g_first + base;
   }
   const int32_t* ev = ev_cid + base;
   const int32_t* root = vox_root + base;
@@ -1652,7 +1718,7 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
         }
         const int slot = __ffs(group) - 1;  // the row was fetched by the first event of the voxel in this chunk
         const int Vn = (lane < 27) ? ring[c & 1][slot][lane] : -1;
-        if (lane == 0 && first_ev[W] == 0x7fffffff) first_ev[W] = e;
+        if (lane == 0) atomicMin(&first_ev[W], e);  // fire-and-forget reduction: no load on the event path
         const bool exist = Vn >= 0;
         const int st = exist ? state[Vn] : 0;
         const bool lab = exist && st != 0;
@@ -2223,7 +2289,10 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
     // persistent: kChainCtasPerSm CTAs of kChainWarps warps per SM (the chain is issue/latency bound, see the kernel)
     static const int ctas_per_sm = getenv("SCVOD_CHAIN_CTAS") ? std::max(1, atoi(getenv("SCVOD_CHAIN_CTAS"))) : kChainCtasPerSm;  // tuning hook
     TIMED("k_patch_chain", TSTREAM);
-    k_patch_chain<<<num_sms() * ctas_per_sm, kChainWarps * 32, 0, st>>>(fa, nscans, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches);
+    if (hp.chain_tma)
+      k_patch_chain<true><<<num_sms() * ctas_per_sm, kChainWarps * 32, 0, st>>>(fa, nscans, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches);
+    else
+      k_patch_chain<false><<<num_sms() * ctas_per_sm, kChainWarps * 32, 0, st>>>(fa, nscans, d.sort_list, d.sort_ctr, d.cap_scans * kNumPatches);
   }
   { TIMED("k_patch_rank_small", TSTREAM); k_patch_rank_small<<<dim3((kNumPatches + kRankWarps - 1) / kRankWarps, nscans), kRankWarps * 32, 0, st>>>(fa); }
   if (max_scan_points > kSortT0) {
@@ -2319,7 +2388,7 @@ int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, boo
   constexpr int NW = kReplayWarps;
   const size_t ring = sizeof(int) * NW * 2 * kReplayRows * 32;
   const size_t nfw = ((size_t)max_events + 31) / 32;
-  const size_t smem = ring + (size_t)max_vox * 14 + nfw * 8 + 16;
+  const size_t smem = ring + (size_t)max_vox * 6 + nfw * 8 + 16;
   static std::once_flag replay_once;
   std::call_once(replay_once, [ring] {
     cudaFuncSetAttribute(k_name_replay<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -2327,7 +2396,7 @@ int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, boo
   });
   int2* ev_list = reinterpret_cast<int2*>(d.bucket_kv);  // the ground stage is done with its (key, index) buckets
   if (smem <= 220 * 1024 && !force_global) {
-    { TIMED("k_name_replay", TSTREAM); k_name_replay<NW, false><<<nscans, NW * 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, nullptr, nullptr, nullptr, nullptr, nullptr, vox_name, name_first, name_cap); }
+    { TIMED("k_name_replay", TSTREAM); k_name_replay<NW, false><<<nscans, NW * 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, nullptr, d.vox_pts_tmp, d.apri_rank, nullptr, nullptr, vox_name, name_first, name_cap); }
   } else {  // very dense scans: union-find state in (L2-resident) global scratch that the earlier stages are done with
     { TIMED("k_name_replay_global", TSTREAM); k_name_replay<NW, true><<<nscans, NW * 32, ring, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, d.slot_pos, vox_name, name_first, name_cap); }
   }

@@ -87,7 +87,9 @@ const char* scvod_last_error(void);
 int scvod_num_kernel_launches(const scvod_ctx* ctx, int64_t* out); /* kernels launched so far */
 /* options: "inspect" (keep per-stage cluster names for scvod_frame_point_cluster; default 1),
  * "host_threads" (threads used for the per-scan cluster bookkeeping), "replay_global" (test hook: run the cluster-name
- * replay with its union-find state in global memory, the variant very dense scans fall back to; default 0). */
+ * replay with its union-find state in global memory, the variant very dense scans fall back to; default 0), "chain_tma"
+ * (stage the plane-fit kernel's point ring with TMA bulk copies + mbarriers instead of per-lane cp.async; same results,
+ * measured slower on B200, default 0). */
 int scvod_set_option(scvod_ctx* ctx, const char* key, int value);
 /* cumulative work counters: "scans", "points", "apri_points", "voxels", "track_pairs", "track_points" */
 int scvod_get_stat(scvod_ctx* ctx, const char* key, int64_t* out);

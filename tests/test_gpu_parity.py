@@ -90,6 +90,18 @@ def test_ground_order_bit_exact(pkg, oracle, scan_id, rings, cols):
     s.close()
 
 
+def test_ground_with_tma_staged_chain(pkg, oracle):
+    """The opt-in variant of the plane-fit kernel (cp.async.bulk + mbarrier ring) gives the same ground / non-ground order."""
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=1)
+    s.set_option("chain_tma", 1)
+    for scan_id, rings, cols in ((3, 64, 1800), (5, 16, 450)):
+        cloud, _ = pkg.synth_scan(conftest.SEED, scan_id, rings=rings, cols=cols)
+        g, ng = s.extractGroudByPatchWork(cloud)
+        og, ong, _, _ = oracle.ground(cloud)
+        assert np.array_equal(g, og) and np.array_equal(ng, ong)
+    s.close()
+
+
 def test_ground_ragged_inputs(ssc, oracle, pkg):
     for cloud in (np.zeros((0, 4), np.float32), np.array([[5, 5, -1.7, 1]], np.float32),
                   np.tile(np.array([[6, 1, -1.7, 1]], np.float32), (11, 1)) + np.arange(11, dtype=np.float32)[:, None] * 1e-3):

@@ -6,6 +6,8 @@
   python tools/ncu_summarize.py full <report.ncu-rep> <out_summary.csv>
       one row per captured launch of an `ncu --set full` report (duration, grid, registers, shared memory, achieved
       occupancy, DRAM bytes read/written, DRAM and SM throughput, L2 bytes, instructions, shared-memory bank conflicts)
+  python tools/ncu_summarize.py roofline <full_summary.csv> <out_roofline.csv>
+      derived: DRAM GB/s per launch = (read + written bytes) / duration and its fraction of the HBM peak
 """
 import collections
 import csv
@@ -58,7 +60,32 @@ def full(rep, dst):
     print(f"{len(data)} launches -> {dst}")
 
 
+PEAK_GBPS = 6650.0  # fallback of B200_PROFILING.md; MEASURED_PEAKS.json is absent on this pool
+
+
+def roofline(src, dst):
+    rows = list(csv.reader(open(src)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tsc = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}
+    out = [["kernel", "launch_us", "grid", "block", "regs", "dram_read_MB", "dram_write_MB", "dram_GBps", f"frac_of_{PEAK_GBPS:.0f}GBps",
+            "warps_active_pct", "sm_throughput_pct", "dram_throughput_pct"]]
+    for d in data:
+        t = float(d[ix["gpu__time_duration.sum"]]) * tsc[units[ix["gpu__time_duration.sum"]]]
+        r = float(d[ix["dram__bytes_read.sum"]]) * scale[units[ix["dram__bytes_read.sum"]]]
+        w = float(d[ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]]
+        name = d[ix["Kernel Name"]].replace("void ", "").split("(")[0]
+        out.append([name, f"{t * 1e6:.1f}", d[ix["launch__grid_size"]], d[ix["launch__block_size"]], d[ix["launch__registers_per_thread"]],
+                    f"{r / 1e6:.2f}", f"{w / 1e6:.2f}", f"{(r + w) / t / 1e9:.0f}", f"{(r + w) / t / 1e9 / PEAK_GBPS:.4f}",
+                    f"{float(d[ix['sm__warps_active.avg.pct_of_peak_sustained_active']]):.1f}",
+                    f"{float(d[ix['sm__throughput.avg.pct_of_peak_sustained_elapsed']]):.1f}",
+                    f"{float(d[ix['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']]):.1f}"])
+    csv.writer(open(dst, "w", newline="")).writerows(out)
+    print(f"{len(data)} launches -> {dst}")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) != 4 or sys.argv[1] not in ("launches", "full"):
+    if len(sys.argv) != 4 or sys.argv[1] not in ("launches", "full", "roofline"):
         sys.exit(__doc__)
-    (launches if sys.argv[1] == "launches" else full)(sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "roofline": roofline}[sys.argv[1]](sys.argv[2], sys.argv[3])
