@@ -8,9 +8,10 @@ tracking diff over the chunk -> per-point classes -> static submap (+ one NCCL a
 submaps per chunk when N > 1).  Scans shard across ranks (one process per GPU, independent chunks, weak scaling).
 
   value : inputs already resident in HBM (scvod_push_scans_dev), labels stay on the device
-  e2e   : same work through the host-buffer C-ABI call a reference maintainer would bind
+  e2e   : same work through the host-buffer C-ABI calls a reference maintainer would bind
           (scvod_push_scans from pinned host memory, labels copied back to the host) — copies inside
-          the timed region
+          the timed region; a worker double-buffers: scvod_prefetch_scans starts the upload of its next
+          chunk while the tracking chain of the current one runs
   --impl reference : the reference's CPU path (the oracle restatement; the reference itself cannot be
           built in this image) on all host threads, bounded sample per step, rank 0 only.
 """
@@ -256,7 +257,7 @@ def main():
     par = entry._load_parallel()
     gatherer = par.SubmapGatherer(max_pts, dev) if world > 1 else None  # one NCCL all-gather of the static submaps per step
 
-    def step(wk, i, host_io):
+    def step(wk, i, host_io, prefetch_next=False):
         # every worker cycles through the whole pool (so its buffers reach their steady-state sizes during warm-up) and
         # neighbouring workers are on different batches at any time
         wk.count += 1
@@ -264,7 +265,10 @@ def main():
         ssc = wk.ssc
         ssc.reset()
         if host_io:
-            ssc.process_host_ptr(b["host"].data_ptr(), b["off"])
+            ssc.process_host_ptr(b["host"].data_ptr(), b["off"])  # finds its points on the device if they were prefetched
+            if prefetch_next:  # double buffering: the upload of this worker's next chunk overlaps the tracking chain of this one
+                nb = batches[(wk.wid + wk.count + 1) % len(batches)]
+                ssc.prefetch_host_ptr(nb["host"].data_ptr(), nb["off"])
         else:
             ssc.process_device(b["dev"].data_ptr(), b["off"])
         ssc.tracking(b["poses"])
@@ -292,8 +296,9 @@ def main():
         def work(wk):
             try:
                 with torch.cuda.stream(wk.stream):
-                    for i in range(first_step + wk.wid, first_step + nsteps, W):
-                        n_static = step(wk, i, host_io)
+                    mine = list(range(first_step + wk.wid, first_step + nsteps, W))
+                    for i in mine:
+                        n_static = step(wk, i, host_io, prefetch_next=(i != mine[-1]))
                         with cv:
                             done[i] = (wk, n_static)
                             cv.notify_all()

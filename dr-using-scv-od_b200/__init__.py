@@ -68,7 +68,7 @@ EXPORTS = (
     "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
     "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
     "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
-    "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization",
+    "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
 )
 
 _lib = None
@@ -325,6 +325,11 @@ class SSC:
 
     def labels_into(self, f0: int, f1: int, host_ptr: int, cap: int):
         _check(self._lib.scvod_labels_range(self._ctx, f0, f1, ctypes.c_void_p(host_ptr), ctypes.c_int64(cap)))
+
+    def prefetch_host_ptr(self, host_ptr: int, offsets: np.ndarray):
+        """Start uploading the batch a later process_host_ptr(host_ptr, offsets) will be given (scvod_prefetch_scans)."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        _check(self._lib.scvod_prefetch_scans(self._ctx, ctypes.c_void_p(host_ptr), _ptr(offsets), len(offsets) - 1))
 
     def process_host_ptr(self, host_ptr: int, offsets: np.ndarray):
         offsets = np.ascontiguousarray(offsets, np.int64)

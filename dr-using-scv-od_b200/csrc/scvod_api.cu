@@ -222,6 +222,12 @@ struct scvod_ctx {
   std::vector<std::unique_ptr<PersistBatch>> batch_pool;  // released batches kept for reuse (no cudaMalloc in steady state)
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
+  // scvod_prefetch_scans: upload of the next batch on a private stream, consumed by the next scvod_push_scans of the same buffer
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t prefetch_done = nullptr;
+  DevBuf<float4> d_prefetch;
+  const char* prefetch_host = nullptr;  // first prefetched byte in the caller's buffer
+  size_t prefetch_bytes = 0;
   FrameClusters init_fc;  // frame_based after scvod_initialization (read with frame index SCVOD_INIT_FRAME)
   int init_base = -1;
   bool have_init = false;
@@ -451,6 +457,12 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_counter.release();
   c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  if (c->prefetch_done) cudaEventDestroy(c->prefetch_done);
+  c->d_prefetch.release();
   delete c;
   return SCVOD_OK;
 }
@@ -587,9 +599,18 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
 
   std::chrono::steady_clock::time_point tk0 = std::chrono::steady_clock::now();
   CU(cudaMemcpyAsync(w.off, off.data(), sizeof(int64_t) * (nscans + 1), cudaMemcpyHostToDevice, st));
-  if (total > 0)
-    CU(cudaMemcpyAsync(w.pts, (const char*)xyzi + sizeof(float) * 4 * offsets[0], sizeof(float4) * total,
-                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  if (total > 0) {
+    const char* src = (const char*)xyzi + sizeof(float) * 4 * offsets[0];
+    const size_t bytes = sizeof(float4) * (size_t)total;
+    if (!on_device && c->prefetch_host && src >= c->prefetch_host && src + bytes <= c->prefetch_host + c->prefetch_bytes) {
+      // already on its way (scvod_prefetch_scans): wait for the private copy stream, then a device-to-device move
+      CU(cudaStreamWaitEvent(st, c->prefetch_done, 0));
+      CU(cudaMemcpyAsync(w.pts, (const char*)c->d_prefetch.p + (src - c->prefetch_host), bytes, cudaMemcpyDeviceToDevice, st));
+      if (src + bytes == c->prefetch_host + c->prefetch_bytes) c->prefetch_host = nullptr;  // consumed up to its end
+    } else {
+      CU(cudaMemcpyAsync(w.pts, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+  }
   CU(cudaMemsetAsync(w.scan_counts, 0, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), st));
   c->launches += launch_ground(c->hp, w, nscans, max_n, st);
   c->launches += launch_descriptor(c->hp, w, nscans, max_n, st);
@@ -746,6 +767,31 @@ static int push_scans_impl(scvod_ctx* c, const void* xyzi, bool on_device, const
     if (rc != SCVOD_OK) return rc;
     s = e;
   }
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_prefetch_scans(scvod_ctx* c, const float* xyzi, const int64_t* offsets, int nscans) {
+  if (!c || !offsets || nscans < 0 || (!xyzi && nscans > 0 && offsets[nscans] > offsets[0]))
+    return fail(SCVOD_ERR_ARG, "bad arguments to scvod_prefetch_scans");
+  CU(cudaSetDevice(c->device));
+  const int64_t total = offsets[nscans] - offsets[0];
+  if (total <= 0) return SCVOD_OK;
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->prefetch_done, cudaEventDisableTiming));
+  }
+  // the staging buffer may still feed the device-to-device move of the previous push: that move is on the compute stream
+  CU(cudaEventRecord(c->prefetch_done, c->stream));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->prefetch_done, 0));
+  if ((size_t)total > c->d_prefetch.n) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(c->d_prefetch.alloc((size_t)total));
+  }
+  const char* src = (const char*)xyzi + sizeof(float) * 4 * offsets[0];
+  CU(cudaMemcpyAsync(c->d_prefetch.p, src, sizeof(float4) * (size_t)total, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaEventRecord(c->prefetch_done, c->copy_stream));
+  c->prefetch_host = src;
+  c->prefetch_bytes = sizeof(float4) * (size_t)total;
   return SCVOD_OK;
 }
 

@@ -1824,7 +1824,9 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
   if (tid == 0) scan_counts[b * 8 + 6] = cluster_name;
 }
 
-// ordered compaction of the apri points whose rank inside their voxel is < 3 ("clustering events")
+// ordered compaction of the apri points whose rank inside their voxel is < 3 ("clustering events").  One CTA per scan;
+// every warp owns a contiguous slice: count (ballot / popcount), ONE block scan over the 32 warp totals, then the same
+// walk again writing at the warp's offset — two barriers per scan instead of three per 1024 points.
 __global__ void __launch_bounds__(1024) k_events(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
                                                  const int32_t* __restrict__ apri_cid, const int32_t* __restrict__ apri_rank,
                                                  int32_t* __restrict__ ev_cid) {
@@ -1832,16 +1834,25 @@ __global__ void __launch_bounds__(1024) k_events(const int64_t* __restrict__ off
   const int b = blockIdx.x;
   const int64_t base = off[b];
   const int M = scan_counts[b * 8 + 2];
-  int carry = 0;
-  for (int m0 = 0; m0 < M; m0 += 1024) {
-    int m = m0 + threadIdx.x;
-    int f = (m < M && apri_cid[base + m] >= 0 && apri_rank[base + m] < 3) ? 1 : 0;
-    int total;
-    int ex = block_excl_scan<1024>(f, &total, s_w);
-    if (f) ev_cid[base + carry + ex] = apri_cid[base + m];
-    carry += total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int slice = (((M + 31) / 32) + 31) & ~31;  // per warp, multiple of 32
+  const int m0 = min(M, wid * slice), m1 = min(M, m0 + slice);
+  int cnt = 0;
+  for (int m = m0 + lane; m < m1; m += 32) cnt += (apri_cid[base + m] >= 0 && apri_rank[base + m] < 3) ? 1 : 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+  int total;
+  const int ex = block_excl_scan<1024>(lane == 0 ? cnt : 0, &total, s_w);  // lane 0 of warp w carries the warp total
+  int pos = __shfl_sync(0xffffffffu, ex, 0);
+  for (int j = m0; j < m1; j += 32) {
+    const int m = j + lane;
+    const int cid = (m < m1) ? apri_cid[base + m] : -1;
+    const bool f = cid >= 0 && apri_rank[base + m] < 3;
+    const unsigned mask = __ballot_sync(0xffffffffu, f);
+    if (f) ev_cid[base + pos + __popc(mask & ((1u << lane) - 1u))] = cid;
+    pos += __popc(mask);
   }
-  if (threadIdx.x == 0) scan_counts[b * 8 + 5] = carry;
+  if (threadIdx.x == 0) scan_counts[b * 8 + 5] = total;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -123,7 +123,12 @@ int scvod_bin(scvod_ctx* ctx, const float* xyzi, int n, uint8_t* pass, int32_t* 
  * offsets has nscans+1 entries (point offsets into xyzi). */
 int scvod_push_scans(scvod_ctx* ctx, const float* xyzi, const int64_t* offsets, int nscans);
 
-/* Same, with the scans already resident in device memory (float4 per point). */
+/* Optional double buffering for streams of batches: start the host->device upload of the scans that a LATER scvod_push_scans call
+ * will be given (same buffer and offsets).  The copy runs on a private stream and overlaps whatever the context is doing (the
+ * tracking chain of the previous batch, typically); that push then finds its points on the device.  The host buffer must stay
+ * valid and unchanged until that push returns; pinned memory is needed for the copy to be asynchronous. */
+int scvod_prefetch_scans(scvod_ctx* ctx, const float* xyzi, const int64_t* offsets, int nscans);
+/* Same as scvod_push_scans, with the scans already resident in device memory (float4 per point). */
 int scvod_push_scans_dev(scvod_ctx* ctx, const void* xyzi_dev, const int64_t* offsets, int nscans);
 
 /* SSC::tracking chain of SSC::segDF (ssc.cpp:1448-1452, 1250-1426) over all frames pushed so far

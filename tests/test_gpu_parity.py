@@ -385,6 +385,45 @@ def test_concurrent_contexts_give_the_sequential_result(pkg):
         c.close()
 
 
+def test_prefetched_upload_gives_the_same_labels(pkg):
+    """scvod_prefetch_scans (double-buffered host -> device upload) only changes where the points come from."""
+    import torch
+
+    nfr = 6
+    chunks = []
+    for w in range(3):
+        scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 30 + w, k, rings=32, cols=900) for k in range(nfr)])
+        off = np.zeros(nfr + 1, np.int64)
+        off[1:] = np.cumsum([len(x) for x in scans])
+        chunks.append((torch.from_numpy(np.concatenate(scans)).pin_memory(), off, np.stack(poses), scans))
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=nfr)
+    ref = []
+    for host, off, poses, scans in chunks:
+        s.reset()
+        ref.append([l.copy() for l in s.segDF(scans, poses)])
+    got = []
+    s.reset()
+    s.prefetch_host_ptr(chunks[0][0].data_ptr(), chunks[0][1])
+    for i, (host, off, poses, scans) in enumerate(chunks):
+        s.reset()
+        s.process_host_ptr(host.data_ptr(), off)  # consumes the prefetched copy
+        if i + 1 < len(chunks):
+            s.prefetch_host_ptr(chunks[i + 1][0].data_ptr(), chunks[i + 1][1])  # overlaps the tracking below
+        s.tracking(poses)
+        got.append([s.frame_labels(f) for f in range(nfr)])
+    for a, b in zip(ref, got):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # a prefetch that is NOT followed by a push of the same buffer is simply ignored
+    s.reset()
+    s.prefetch_host_ptr(chunks[0][0].data_ptr(), chunks[0][1])
+    s.process_host_ptr(chunks[1][0].data_ptr(), chunks[1][1])
+    s.tracking(chunks[1][2])
+    for f in range(nfr):
+        assert np.array_equal(s.frame_labels(f), ref[1][f])
+    s.close()
+
+
 def test_aliased_voxel_scan_is_rejected_loudly(pkg):
     """Points with a -1 index (y == 0 exactly) alias voxels; clustering them is not supported yet and must
     fail with an explicit error rather than return different labels."""
