@@ -10,8 +10,8 @@ submaps per chunk when N > 1).  Scans shard across ranks (one process per GPU, i
   value : inputs already resident in HBM (scvod_push_scans_dev), labels stay on the device
   e2e   : same work through the host-buffer C-ABI calls a reference maintainer would bind
           (scvod_push_scans from pinned host memory, labels copied back to the host) — copies inside
-          the timed region; a worker double-buffers: scvod_prefetch_scans starts the upload of its next
-          chunk while the tracking chain of the current one runs
+          the timed region (16 workers already keep the copy engine 73 % busy; double buffering inside a
+          worker with scvod_prefetch_scans, --prefetch, was measured slower: 18.6k vs 21.7k scans/s)
   --impl reference : the reference's CPU path (the oracle restatement; the reference itself cannot be
           built in this image) on all host threads, bounded sample per step, rank 0 only.
 """
@@ -202,6 +202,9 @@ def main():
     ap.add_argument("--pool", type=int, default=3, help="distinct input batches rotated through (pool > L2)")
     ap.add_argument("--workers", type=int, default=0, help="independent sequence chunks processed side by side per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans for the cpu_baseline leg (0 = auto)")
+    ap.add_argument("--prefetch", action="store_true",
+                    help="e2e leg: scvod_prefetch_scans the worker's next chunk during the tracking chain (measured slower with 16 workers: "
+                         "a saturated PCIe link delays the launches of every tracking chain)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -266,7 +269,7 @@ def main():
         ssc.reset()
         if host_io:
             ssc.process_host_ptr(b["host"].data_ptr(), b["off"])  # finds its points on the device if they were prefetched
-            if prefetch_next:  # double buffering: the upload of this worker's next chunk overlaps the tracking chain of this one
+            if prefetch_next and args.prefetch:  # double buffering: the upload of this worker's next chunk overlaps the tracking chain of this one
                 nb = batches[(wk.wid + wk.count + 1) % len(batches)]
                 ssc.prefetch_host_ptr(nb["host"].data_ptr(), nb["off"])
         else:

@@ -32,6 +32,13 @@ struct HCluster {
   // device-resident output of the tracking pass that produced them
   std::vector<std::pair<int, int>> carried;
   int n_carried = 0;
+  // own voxels as runs of the frame's device-resident car CSR (built when the frame is pushed, concatenated by fusion
+  // like part_end): lets the tracking kernel take a car cluster as a handful of kernel arguments instead of one
+  // uploaded segment per voxel.  Empty for clusters that are not cars.
+  struct OwnRun {
+    int csr_start, csr_len, part_base, npts;
+  };
+  std::vector<OwnRun> own_runs;
 };
 
 // per-scan inputs from the GPU (host copies)

@@ -127,6 +127,11 @@ struct PersistBatch {
   DevBuf<int64_t> off_dev;           // device copy of off
   DevBuf<int32_t> scan_counts_dev;   // device copy of the per-scan counters
   PinBuf<int32_t> h_vox_off, h_vox_pts;  // host copy of the voxel CSR of every frame (packed per scan)
+  // car CSR of the batch, three arrays of csr_n ints: point offsets (one extra entry per frame), voxel ids, part indices;
+  // car clusters reference it by runs (HCluster::own_runs), see diff_clusters
+  DevBuf<int32_t> csr;
+  PinBuf<int32_t> h_csr;
+  int csr_n = 0;
   int max_n = 0;
   bool labels_current = false;
   // inspection-only
@@ -150,6 +155,8 @@ struct PersistBatch {
     scan_counts_dev.release();
     h_vox_off.release();
     h_vox_pts.release();
+    csr.release();
+    h_csr.release();
     vox_vid.release();
     vox_tri.release();
     vox_av.release();
@@ -159,6 +166,7 @@ struct PersistBatch {
 };
 
 struct FrameHost {
+  int csr_base = -1;  // first position of this frame in its batch's car CSR (PersistBatch::csr), -1: none
   int batch = -1, slot = -1;
   int64_t base = 0;
   int n_in = 0, n_ground = 0, n_ng = 0, n_apri = 0, n_vox = 0;
@@ -208,6 +216,7 @@ struct scvod_ctx {
     uint64_t min_key = 0;
     std::vector<int> vox;
   };
+  TrackRuns track_runs;
   std::vector<int> hit_start, hit_cur, hit_vox, label_order;
   std::vector<uint64_t> hit_key;
   std::vector<LabelAcc> label_accs;
@@ -741,6 +750,54 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     for (auto& t : th) t.join();
   }
   if (g_prof.on) g_prof.add("  host segment+recognize", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count());
+  // car CSR of the batch (see PersistBatch::csr): the own voxels of every car cluster, in occupy_voxels order, with running
+  // point offsets and part indices; one upload per batch, so that tracking needs no per-pair segment upload
+  {
+    size_t csr_n = 0;
+    for (int s = 0; s < nscans; ++s)
+      for (auto& cs : c->frames[f0 + s].fc.cluster_set)
+        if (cs.second.type == c->hp.p.car) csr_n += cs.second.occupy_voxels.size();
+    csr_n += (size_t)nscans;  // one closing point offset per frame
+    CU(pb->h_csr.alloc(3 * csr_n));
+    CU(pb->csr.alloc(3 * csr_n));
+    pb->csr_n = (int)csr_n;
+    int32_t* ptoff = pb->h_csr.p;
+    int32_t* cvox = pb->h_csr.p + csr_n;
+    int32_t* cpart = pb->h_csr.p + 2 * csr_n;
+    size_t pos = 0;
+    for (int s = 0; s < nscans; ++s) {
+      FrameHost& fr = c->frames[f0 + s];
+      fr.csr_base = (int)pos;
+      int run_pts = 0;
+      for (auto& cs : fr.fc.cluster_set) {
+        HCluster& cl = cs.second;
+        cl.own_runs.clear();
+        if (cl.type != c->hp.p.car) continue;
+        HCluster::OwnRun orun;
+        orun.csr_start = (int)(pos - fr.csr_base);
+        orun.csr_len = (int)cl.occupy_voxels.size();
+        orun.part_base = 0;
+        const int pts0 = run_pts;
+        int part = 0, vi = 0;
+        for (int v : cl.occupy_voxels) {
+          while (part < (int)cl.part_end.size() && vi >= cl.part_end[part]) ++part;
+          ++vi;
+          ptoff[pos] = run_pts;
+          cvox[pos] = v;
+          cpart[pos] = part;
+          run_pts += std::max(0, fr.vox_cnt[v]);
+          ++pos;
+        }
+        orun.npts = run_pts - pts0;
+        cl.own_runs.push_back(orun);
+      }
+      ptoff[pos] = run_pts;  // closing offset (the voxel / part slots of this position stay unused)
+      cvox[pos] = 0;
+      cpart[pos] = 0;
+      ++pos;
+    }
+    CU(cudaMemcpyAsync(pb->csr.p, pb->h_csr.p, sizeof(int32_t) * 3 * csr_n, cudaMemcpyHostToDevice, st));
+  }
   c->stat_scans += nscans;
   c->stat_points += total;
   c->stat_apri += mbase[nscans];
@@ -829,9 +886,7 @@ extern "C" int scvod_reset_frames(scvod_ctx* c) {
 // (cluster, hit voxel) pairs with their first-occurrence keys are grouped by cluster in c->hit_start / hit_key / hit_vox,
 // cstart holds the offset of every cluster's transformed cloud in c->d_tout[1 - c->tout_cur].
 static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float T[12], const std::vector<HCluster*>& cars,
-                         std::vector<size_t>& cstart) {
-  size_t n_seg = 0;
-  for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size();
+                         std::vector<size_t>& cstart, bool allow_runs) {
   const int ncl = (int)cars.size();
   const int vn = next.n_vox;
   cstart.assign(cars.size() + 1, 0);
@@ -840,13 +895,61 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
   // which is what the 64-bit key encodes.
   c->hit_start.assign(cars.size() + 1, 0);
   const int in_buf = c->tout_cur, out_buf = 1 - c->tout_cur;
-  {
-    PROF("  track: gpu round trip");
+  PROF("  track: gpu round trip");
+  PersistBatch& pbp = *c->batches[pre.batch];
+  PersistBatch& pbn = *c->batches[next.batch];
+  // ---- which points: a run table in the kernel arguments (car clusters described by runs of the frame's device CSR) ... ----
+  size_t K = 0;
+  size_t nruns = 0;
+  bool use_runs = allow_runs && pre.csr_base >= 0;
+  if (use_runs) {
+    for (HCluster* cl : cars) {
+      if (cl->own_runs.empty() && !cl->occupy_voxels.empty()) use_runs = false;
+      nruns += cl->own_runs.size() + cl->carried.size();
+    }
+    if (nruns > (size_t)kTrackMaxRuns) use_runs = false;
+  }
+  TrackRuns& runs = c->track_runs;
+  size_t si = 0;  // segments (fallback path)
+  if (use_runs) {
+    int r = 0;
+    for (size_t i = 0; i < cars.size(); ++i) {
+      cstart[i] = K;
+      HCluster& cl = *cars[i];
+      for (auto& orun : cl.own_runs) {
+        if (orun.npts <= 0) continue;
+        runs.dst_off[r] = (int)K;
+        runs.src[r] = pre.csr_base + orun.csr_start;
+        runs.len[r] = orun.csr_len;
+        runs.order[r] = orun.part_base;
+        runs.cluster[r] = (int)i;
+        ++r;
+        K += (size_t)orun.npts;
+      }
+      int ord = 0x40000000;
+      for (auto& cr : cl.carried) {
+        if (cr.second <= 0) continue;
+        runs.dst_off[r] = (int)K;
+        runs.src[r] = -1 - cr.first;
+        runs.len[r] = cr.second;
+        runs.order[r] = ord++;
+        runs.cluster[r] = (int)i;
+        ++r;
+        K += (size_t)cr.second;
+      }
+    }
+    runs.n = r;
+    cstart[cars.size()] = K;
+    if (r == 0) K = 0;
+  } else {
+    // ---- ... or one uploaded segment per voxel (clusters without runs: scvod_initialization; more runs than fit) ----
+    size_t n_seg = 0;
+    for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size();
     size_t k_bound = 0;  // upper bound of the number of points (the per-block index follows the segment table)
     for (HCluster* cl : cars) k_bound += (size_t)std::max(0, cl->npts) + (size_t)std::max(0, cl->n_carried);
     CU(c->h_treq.alloc(std::max<size_t>(4, n_seg * 4) + k_bound / 256 + 2));
     int32_t* seg = c->h_treq.p;
-    size_t k = 0, si = 0;
+    size_t k = 0;
     for (size_t i = 0; i < cars.size(); ++i) {
       cstart[i] = k;
       HCluster& cl = *cars[i];
@@ -875,98 +978,102 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
       }
     }
     cstart[cars.size()] = k;
-    const size_t K = k;
-    c->stat_track_pairs += 1;
-    if (K > 0 && vn > 0 && si > 0) {
-      c->stat_track_points += (int64_t)K;
-      const int cap_quads = (int)std::min<size_t>((size_t)ncl * vn, (size_t)1 << 20);
-      // per block of 256 points: the segment that holds its first point (a CTA of k_track stages only the segments of its
-      // block); the index follows the segment table in the same pinned buffer, so one small H2D copy carries both
-      const size_t nblk = (K + 255) / 256;
-      if (si * 4 + nblk + 1 > c->h_treq.n) return fail(SCVOD_ERR_STATE, "internal: cluster point counts disagree with the voxel table");
-      {
-        int32_t* fs = c->h_treq.p + si * 4;
-        for (size_t s = 0; s < si; ++s) {
-          const size_t lo = (size_t)seg[4 * s], hi = (s + 1 < si ? (size_t)seg[4 * (s + 1)] : K) - 1;  // points [lo, hi]
-          for (size_t b = (lo + 255) / 256; b <= hi / 256; ++b) fs[b] = (int32_t)s;
-        }
-      }
-      CU(c->d_treq.alloc(si * 4 + nblk + 1));
-      CU(c->d_tout[out_buf].alloc(K));
-      {
-        const size_t need = (size_t)ncl * vn;
-        if (need > c->d_first.n) {  // (re)allocation: the table must start out "empty"; afterwards the epilogue of k_track keeps it so
-          CU(c->d_first.alloc(need));
-          CU(cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream));
-        }
-      }
-      CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));
-      if (!c->d_track_ctr.p) {
-        CU(c->d_track_ctr.alloc(4));
-        CU(cudaMemsetAsync(c->d_track_ctr.p, 0, sizeof(int32_t) * c->d_track_ctr.n, c->stream));
-      }
-      CU(c->d_track_list.alloc((size_t)cap_quads));  // pinned + device-accessible (UVA): the kernel writes the hits straight to the host
-      PersistBatch& pbp = *c->batches[pre.batch];
-      PersistBatch& pbn = *c->batches[next.batch];
-      *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
-      std::atomic_thread_fence(std::memory_order_release);
-      PROF("    track: enqueue+wait+read");
-      CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->stream));
-      c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
-                                  reinterpret_cast<const int4*>(c->d_treq.p), c->d_treq.p + si * 4, (int)si, (int)K, T,
-                                  pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl,
-                                  vn, c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads,
-                                  c->stream);
-      CU(cudaGetLastError());
-      // The kernel's last CTA writes the hits and then their count straight into this pinned buffer: poll the count
-      // instead of paying a stream synchronisation per frame pair (stream order still protects every device buffer).
-      int nt;
-      static const bool sync_wait = getenv("SCVOD_TRACK_SYNC") != nullptr;  // A/B switch: stream synchronisation instead of polling
-      if (sync_wait) {
-        PROF("    track: wait (sync)");
-        CU(cudaStreamSynchronize(c->stream));
-        nt = c->h_triples.p[0];
-      } else {
-        PROF("    track: wait (poll)");
-        volatile int32_t* flag = c->h_triples.p;
-        int spins = 0;
-        while ((nt = *flag) < 0) {
-          if (++spins >= 2000) {  // ~every few tens of microseconds: make sure the stream is still alive
-            spins = 0;
-            cudaError_t qe = cudaStreamQuery(c->stream);
-            if (qe == cudaSuccess) {
-              nt = *flag;
-              if (nt < 0) return fail(SCVOD_ERR_CUDA, "k_track finished without publishing its hit count");
-              break;
-            }
-            if (qe != cudaErrorNotReady) return fail(SCVOD_ERR_CUDA, std::string("k_track: ") + cudaGetErrorString(qe));
-            sched_yield();  // more contexts than cores: let another worker's host work run
+    K = k;
+    if (si == 0) K = 0;
+  }
+  c->stat_track_pairs += 1;
+  if (K == 0 || vn <= 0) return SCVOD_OK;
+  c->stat_track_points += (int64_t)K;
+  std::chrono::steady_clock::time_point ta0 = std::chrono::steady_clock::now();
+  const int cap_quads = (int)std::min<size_t>((size_t)ncl * vn, (size_t)1 << 20);
+  size_t nblk = 0;
+  if (!use_runs) {
+    // per block of 256 points: the segment that holds its first point (a CTA of k_track stages only the segments of its
+    // block); the index follows the segment table in the same pinned buffer, so one small H2D copy carries both
+    int32_t* seg = c->h_treq.p;
+    nblk = (K + 255) / 256;
+    if (si * 4 + nblk + 1 > c->h_treq.n) return fail(SCVOD_ERR_STATE, "internal: cluster point counts disagree with the voxel table");
+    int32_t* fs = c->h_treq.p + si * 4;
+    for (size_t s = 0; s < si; ++s) {
+      const size_t lo = (size_t)seg[4 * s], hi = (s + 1 < si ? (size_t)seg[4 * (s + 1)] : K) - 1;  // points [lo, hi]
+      for (size_t b = (lo + 255) / 256; b <= hi / 256; ++b) fs[b] = (int32_t)s;
+    }
+    CU(c->d_treq.alloc(si * 4 + nblk + 1));
+  }
+  CU(c->d_tout[out_buf].alloc(K));
+  {
+    const size_t need = (size_t)ncl * vn;
+    if (need > c->d_first.n) {  // (re)allocation: the table must start out "empty"; afterwards the epilogue of k_track keeps it so
+      CU(c->d_first.alloc(need));
+      CU(cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream));
+    }
+  }
+  CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));
+  if (!c->d_track_ctr.p) {
+    CU(c->d_track_ctr.alloc(4));
+    CU(cudaMemsetAsync(c->d_track_ctr.p, 0, sizeof(int32_t) * c->d_track_ctr.n, c->stream));
+  }
+  CU(c->d_track_list.alloc((size_t)cap_quads));
+  *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
+  std::atomic_thread_fence(std::memory_order_release);
+  if (g_prof.on) g_prof.add("    track: buffers", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ta0).count());
+  {
+    PROF("    track: enqueue+wait+read");
+    if (!use_runs) CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
+                                use_runs ? nullptr : reinterpret_cast<const int4*>(c->d_treq.p), use_runs ? nullptr : c->d_treq.p + si * 4,
+                                (int)si, use_runs ? &runs : nullptr, pbp.csr.p, pbp.csr.p + pbp.csr_n, pbp.csr.p + 2 * pbp.csr_n, (int)K, T,
+                                pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl, vn,
+                                c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads, c->stream);
+    CU(cudaGetLastError());
+    // The kernel's last CTA writes the hits and then their count straight into this pinned buffer: poll the count
+    // instead of paying a stream synchronisation per frame pair (stream order still protects every device buffer).
+    int nt;
+    static const bool sync_wait = getenv("SCVOD_TRACK_SYNC") != nullptr;  // A/B switch: stream synchronisation instead of polling
+    if (sync_wait) {
+      PROF("    track: wait (sync)");
+      CU(cudaStreamSynchronize(c->stream));
+      nt = c->h_triples.p[0];
+    } else {
+      PROF("    track: wait (poll)");
+      volatile int32_t* flag = c->h_triples.p;
+      int spins = 0;
+      while ((nt = *flag) < 0) {
+        if (++spins >= 2000) {  // ~every few tens of microseconds: make sure the stream is still alive
+          spins = 0;
+          cudaError_t qe = cudaStreamQuery(c->stream);
+          if (qe == cudaSuccess) {
+            nt = *flag;
+            if (nt < 0) return fail(SCVOD_ERR_CUDA, "k_track finished without publishing its hit count");
+            break;
           }
-#if defined(__x86_64__)
-          __builtin_ia32_pause();
-#endif
+          if (qe != cudaErrorNotReady) return fail(SCVOD_ERR_CUDA, std::string("k_track: ") + cudaGetErrorString(qe));
+          sched_yield();  // more contexts than cores: let another worker's host work run
         }
-        std::atomic_thread_fence(std::memory_order_acquire);
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
       }
-      if (nt > cap_quads) {  // entries past the list were not reset by the kernel epilogue: wipe the table before giving up
-        cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream);
-        cudaStreamSynchronize(c->stream);
-        return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
-      }
-      // counting sort of the quads by cluster (no order inside a cluster: the decisions only need, per next-frame
-      // label, the smallest key and the set of hit voxels)
-      const int32_t* quads = c->h_triples.p + 4;
-      for (int t = 0; t < nt; ++t) c->hit_start[quads[4 * t] + 1]++;
-      for (size_t i = 0; i < cars.size(); ++i) c->hit_start[i + 1] += c->hit_start[i];
-      c->hit_key.resize(nt);
-      c->hit_vox.resize(nt);
-      c->hit_cur.assign(c->hit_start.begin(), c->hit_start.end() - 1);
-      for (int t = 0; t < nt; ++t) {
-        const int32_t* q = quads + 4 * t;
-        const int pos = c->hit_cur[q[0]]++;
-        c->hit_key[pos] = ((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3];
-        c->hit_vox[pos] = q[1];
-      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (nt > cap_quads) {  // entries past the list were not reset by the kernel epilogue: wipe the table before giving up
+      cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream);
+      cudaStreamSynchronize(c->stream);
+      return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
+    }
+    // counting sort of the quads by cluster (no order inside a cluster: the decisions only need, per next-frame
+    // label, the smallest key and the set of hit voxels)
+    const int32_t* quads = c->h_triples.p + 4;
+    for (int t = 0; t < nt; ++t) c->hit_start[quads[4 * t] + 1]++;
+    for (size_t i = 0; i < cars.size(); ++i) c->hit_start[i + 1] += c->hit_start[i];
+    c->hit_key.resize(nt);
+    c->hit_vox.resize(nt);
+    c->hit_cur.assign(c->hit_start.begin(), c->hit_start.end() - 1);
+    for (int t = 0; t < nt; ++t) {
+      const int32_t* q = quads + 4 * t;
+      const int pos = c->hit_cur[q[0]]++;
+      c->hit_key[pos] = ((uint64_t)(uint32_t)q[2] << 32) | (uint32_t)q[3];
+      c->hit_vox[pos] = q[1];
     }
   }
   return SCVOD_OK;
@@ -1021,7 +1128,7 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
   std::vector<size_t> cstart;
   const int out_buf = 1 - c->tout_cur;
   {
-    int rc = diff_clusters(c, pre, next, T, cars, cstart);
+    int rc = diff_clusters(c, pre, next, T, cars, cstart, true);
     if (rc) return rc;
   }
 
@@ -1093,7 +1200,12 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
           HCluster& src = nset[re.first];
           const int basev = (int)cluster_new.occupy_voxels.size();  // addVec of pts and voxels (ssc.cpp:1409-1410): parts are kept
           cluster_new.occupy_voxels.insert(cluster_new.occupy_voxels.end(), src.occupy_voxels.begin(), src.occupy_voxels.end());
+          const int base_parts = (int)cluster_new.part_end.size();
           for (int pe : src.part_end) cluster_new.part_end.push_back(basev + pe);
+          for (auto orun : src.own_runs) {  // the same concatenation, as runs of the frame's car CSR
+            orun.part_base += base_parts;
+            cluster_new.own_runs.push_back(orun);
+          }
           cluster_new.npts += src.npts;
           nset.erase(re.first);
         }
@@ -1149,7 +1261,7 @@ extern "C" int scvod_initialization(scvod_ctx* c, const float* poses6, int npose
     relative_pose(poses6 + 6 * id_based, poses6 + 6 * i, T);  // trans_based.inverse() * trans_i (:1172)
     std::vector<HCluster*> all;  // every cluster of frame i, in cluster_set order (:1180)
     for (auto& cs : fi.fc.cluster_set) all.push_back(&cs.second);
-    int rc = diff_clusters(c, fi, base, T, all, cstart);
+    int rc = diff_clusters(c, fi, base, T, all, cstart, false);
     if (rc) return rc;
     for (size_t ci = 0; ci < all.size(); ++ci) {
       std::unordered_map<int, std::vector<int>> remap_name;

@@ -98,12 +98,25 @@ int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int total_p
 int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
 int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t* pass, int32_t* vid, int32_t* ri, int32_t* si,
                     int32_t* ei, float* range, float* angle, float* azimuth, void* stream);
-// tracking diff of one frame pair: segments {dst_off, source (>=0 voxel of frame_pre_ / <0 carried range), cluster, order} and
-// first_seg[b] = segment that holds point 256*b (device memory)
+// Run table of one tracking launch, passed in the kernel arguments (no upload): run r covers points [dst_off[r], dst_off[r+1]);
+// src >= 0: own voxels, positions [src, src + len) of the frame's car CSR, part order = order + csr_part; src < 0: carried
+// range at -1 - src of the previous launch's output, order = 0x40000000 + ordinal.
+constexpr int kTrackMaxRuns = 176;
+struct TrackRuns {
+  int n;
+  int dst_off[kTrackMaxRuns];
+  int src[kTrackMaxRuns];
+  int len[kTrackMaxRuns];
+  int order[kTrackMaxRuns];
+  int cluster[kTrackMaxRuns];
+};
+// tracking diff of one frame pair.  runs != nullptr: run table (above) + the frame's car CSR; else uploaded segments
+// {dst_off, source (>=0 voxel of frame_pre_ / <0 carried range), cluster, order} and first_seg[b] = segment holding point 256*b
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
-                 const int4* segs, const int32_t* first_seg, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
-                 const int32_t* next_word_rank, int ncl, int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev,
-                 int32_t* hit_list_dev, int32_t* out_quads_mapped, int cap_quads, void* stream);
+                 const int4* segs, const int32_t* first_seg, int nseg, const TrackRuns* runs, const int32_t* csr_ptoff, const int32_t* csr_vox,
+                 const int32_t* csr_part, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
+                 int cap_quads, void* stream);
 int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
                         const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream);
 int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,

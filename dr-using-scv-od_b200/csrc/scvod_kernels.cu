@@ -78,6 +78,7 @@ struct Mat34 {
   float m[12];
 };
 
+
 struct GroundConst {
   double low_thr;   // -1.8 * sensor_height_  (patchwork.h:304)
   double seed_thr;  // adaptive_seed_selection_margin_ * sensor_height_ (patchwork.h:247)
@@ -1883,11 +1884,20 @@ __global__ void __launch_bounds__(256) k_bin_only(const float4* __restrict__ pts
 // keeps, per (cluster, hit voxel), the smallest point position: that is exactly the information the
 // reference's remap_name needs (set of hit voxels per label + order of first occurrence).
 // ------------------------------------------------------------------------------------------------
+// Two ways to tell the kernel which points to take:
+//   RUNS = true   the usual one: a car cluster is a few runs of the frame's device-resident car CSR (csr_ptoff / csr_vox /
+//                 csr_part, uploaded once per batch) plus carried ranges; the run table (<= kTrackMaxRuns entries) travels in
+//                 the kernel arguments, so a frame pair costs NO host->device copy (on the copy engine it would queue
+//                 behind the bulk scan uploads of the other contexts);
+//   RUNS = false  one uploaded segment per voxel + per-block index (scvod_initialization, or more runs than fit).
+template <bool RUNS>
 __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, const int32_t* __restrict__ vox_off,
                                                const int32_t* __restrict__ vox_pts, const float4* __restrict__ carried,
                                                const int4* __restrict__ segs,
                                                const int32_t* __restrict__ first_seg /* per block of 256 points */,
-                                               int nseg, int k, Mat34 T, BinParams bp, GridSpec g,
+                                               int nseg, const __grid_constant__ TrackRuns runs, const int32_t* __restrict__ csr_ptoff,
+                                               const int32_t* __restrict__ csr_vox, const int32_t* __restrict__ csr_part,
+                                               int k, Mat34 T, BinParams bp, GridSpec g,
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
                                                float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
                                                int32_t* __restrict__ ctr /* [0] distinct hits, [1] finished CTAs */,
@@ -1899,25 +1909,58 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
   __shared__ int s_range[2];
   const int nblk = (k + 255) >> 8;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x < 2) s_range[threadIdx.x] = (blk + (int)threadIdx.x < nblk) ? first_seg[blk + threadIdx.x] : nseg - 1;
-    __syncthreads();
-    const int s0 = s_range[0], cnt = s_range[1] - s0 + 1;
-    for (int t = threadIdx.x; t < cnt; t += 256) s_seg[t] = segs[s0 + t];
-    __syncthreads();
+    int4 sg;  // x = dst_off, y = source (>= 0: voxel of frame_pre_, its points come from the voxel CSR; < 0: carried range
+              // at -1-y), z = cluster, w = order of the segment inside the cluster's cloud (part index / carried ordinal)
     const int i = (blk << 8) + threadIdx.x;
-    if (i >= k) continue;
-    int lo = 0, hi = cnt - 1;  // last segment with dst_off <= i
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (s_seg[mid].x <= i)
-        lo = mid;
-      else
-        hi = mid - 1;
+    if (RUNS) {
+      if (i >= k) continue;
+      int lo = 0, hi = runs.n - 1;  // last run with dst_off <= i (kernel-argument table: constant bank)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (runs.dst_off[mid] <= i)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      const int src = runs.src[lo];
+      sg.z = runs.cluster[lo];
+      if (src >= 0) {  // own voxels: find the voxel inside the run by its point offsets (a short, L1-resident slice)
+        const int32_t* po = csr_ptoff + src;
+        const int jr = i - runs.dst_off[lo] + po[0];
+        int a = 0, b = runs.len[lo] - 1;  // last CSR position with ptoff <= jr
+        while (a < b) {
+          const int mid = (a + b + 1) >> 1;
+          if (po[mid] <= jr)
+            a = mid;
+          else
+            b = mid - 1;
+        }
+        sg.x = i - (jr - po[a]);
+        sg.y = csr_vox[src + a];
+        sg.w = runs.order[lo] + csr_part[src + a];
+      } else {
+        sg.x = runs.dst_off[lo];
+        sg.y = src;
+        sg.w = runs.order[lo];
+      }
+    } else {
+      __syncthreads();
+      if (threadIdx.x < 2) s_range[threadIdx.x] = (blk + (int)threadIdx.x < nblk) ? first_seg[blk + threadIdx.x] : nseg - 1;
+      __syncthreads();
+      const int s0 = s_range[0], cnt = s_range[1] - s0 + 1;
+      for (int t = threadIdx.x; t < cnt; t += 256) s_seg[t] = segs[s0 + t];
+      __syncthreads();
+      if (i >= k) continue;
+      int lo = 0, hi = cnt - 1;  // last segment with dst_off <= i
+      while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (s_seg[mid].x <= i)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      sg = s_seg[lo];
     }
-    // x = dst_off, y = source (>= 0: voxel of frame_pre_, its points come from the CSR; < 0: carried range at -1-y),
-    // z = cluster, w = order of the segment inside the cluster's cloud (part index / carried ordinal)
-    const int4 sg = s_seg[lo];
     const int j = i - sg.x;
     float4 p;
     unsigned low;
@@ -2362,9 +2405,10 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 }
 
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
-                 const int4* segs, const int32_t* first_seg, int nseg, int k, const float T12[12], const uint32_t* next_bitmap,
-                 const int32_t* next_word_rank, int ncl, int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev,
-                 int32_t* hit_list_dev, int32_t* out_quads_mapped, int cap_quads, void* stream_) {
+                 const int4* segs, const int32_t* first_seg, int nseg, const TrackRuns* runs, const int32_t* csr_ptoff, const int32_t* csr_vox,
+                 const int32_t* csr_part, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
+                 int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
+                 int cap_quads, void* stream_) {
   if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
   Mat34 T;
@@ -2373,7 +2417,18 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   static const int ctas_per_sm = getenv("SCVOD_TRACK_CTAS") ? std::max(1, atoi(getenv("SCVOD_TRACK_CTAS"))) : 1;  // few fat CTAs: the kernel is latency bound, a small footprint lets the other contexts' kernels co-run
   int cap = num_sms() * ctas_per_sm;
   if (blocks > cap) blocks = cap;
-  { TIMED("k_track", TSTREAM); k_track<<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, first_seg, nseg, k, T, make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev, out_quads_mapped, cap_quads); }
+  if (runs) {
+    TIMED("k_track", TSTREAM);
+    k_track<true><<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, nullptr, nullptr, 0, *runs, csr_ptoff, csr_vox, csr_part, k, T,
+                                           make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev,
+                                           out_quads_mapped, cap_quads);
+  } else {
+    static const TrackRuns none = {};
+    TIMED("k_track_segs", TSTREAM);
+    k_track<false><<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, first_seg, nseg, none, nullptr, nullptr, nullptr, k, T,
+                                            make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev,
+                                            out_quads_mapped, cap_quads);
+  }
   return 1;
 }
 
