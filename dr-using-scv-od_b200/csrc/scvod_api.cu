@@ -25,6 +25,7 @@
 using namespace scvod;
 
 static thread_local std::string g_err;
+static std::atomic<int> g_live_contexts(0);  // contexts alive in this process: sizes the footprint of the latency-bound tracking kernel
 static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -439,12 +440,14 @@ extern "C" int scvod_create(const scvod_params* p, int device, int max_points, i
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   int rc = alloc_workspace(c.get());
   if (rc != SCVOD_OK) return rc;
+  g_live_contexts.fetch_add(1);
   *out = c.release();
   return SCVOD_OK;
 }
 
 extern "C" int scvod_destroy(scvod_ctx* c) {
   if (!c) return SCVOD_OK;
+  g_live_contexts.fetch_sub(1);
   g_prof.dump();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
@@ -1020,6 +1023,8 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
   {
     PROF("    track: enqueue+wait+read");
     if (!use_runs) CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->stream));
+    // one context: the kernel may fill the GPU (shortest latency); many contexts: one CTA per SM so that their kernels co-run
+    c->hp.track_ctas_per_sm = g_live_contexts.load() <= 2 ? 16 : g_live_contexts.load() <= 6 ? 4 : 1;
     c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                 use_runs ? nullptr : reinterpret_cast<const int4*>(c->d_treq.p), use_runs ? nullptr : c->d_treq.p + si * 4,
                                 (int)si, use_runs ? &runs : nullptr, pbp.csr.p, pbp.csr.p + pbp.csr_n, pbp.csr.p + 2 * pbp.csr_n, (int)K, T,

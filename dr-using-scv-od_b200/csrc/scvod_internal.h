@@ -90,6 +90,7 @@ struct HostParams {
   scvod_params p;
   GridSpec g;
   bool chain_tma = false;  // k_patch_chain: stage the ring with cp.async.bulk + mbarrier instead of per-lane cp.async
+  int track_ctas_per_sm = 1;  // grid cap of k_track (set per launch from the number of live contexts)
 };
 
 // kernel launch wrappers (scvod_kernels.cu). All asynchronous on `stream`. Return launch count.

@@ -2414,7 +2414,8 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   Mat34 T;
   for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
   int blocks = (k + 255) / 256;
-  static const int ctas_per_sm = getenv("SCVOD_TRACK_CTAS") ? std::max(1, atoi(getenv("SCVOD_TRACK_CTAS"))) : 1;  // few fat CTAs: the kernel is latency bound, a small footprint lets the other contexts' kernels co-run
+  static const int forced = getenv("SCVOD_TRACK_CTAS") ? std::max(1, atoi(getenv("SCVOD_TRACK_CTAS"))) : 0;  // tuning hook
+  const int ctas_per_sm = forced ? forced : std::max(1, hp.track_ctas_per_sm);
   int cap = num_sms() * ctas_per_sm;
   if (blocks > cap) blocks = cap;
   if (runs) {
