@@ -3,8 +3,8 @@
 
   python tools/ncu_summarize.py launches <launches.csv> <out_by_kernel.csv>
       per-kernel aggregation of an `ncu --metrics gpu__time_duration.sum --csv` launch list
-  python tools/ncu_summarize.py full <report.ncu-rep> <out_summary.csv>
-      one row per captured launch of an `ncu --set full` report (duration, grid, registers, shared memory, achieved
+  python tools/ncu_summarize.py full <report.ncu-rep>[,<report2>...] <out_summary.csv> [kernels,to,skip,in,the,first]
+      one row per captured launch of `ncu --set full` reports (duration, grid, registers, shared memory, achieved
       occupancy, DRAM bytes read/written, DRAM and SM throughput, L2 bytes, instructions, shared-memory bank conflicts)
   python tools/ncu_summarize.py roofline <full_summary.csv> <out_roofline.csv>
       derived: DRAM GB/s per launch = (read + written bytes) / duration and its fraction of the HBM peak
@@ -46,18 +46,54 @@ def launches(src, dst):
     print(f"{len(agg)} kernels, {total / 1000:.3f} ms of kernel time -> {dst}")
 
 
-def full(rep, dst):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    idx = [hdr.index(c) for c in FULL_COLS if c in hdr]
+_TIME = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}  # -> us
+_BYTES = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}  # -> Mbyte
+_SMEM = {"byte/block": 1e-3, "Kbyte/block": 1.0, "Mbyte/block": 1e3}  # -> Kbyte/block
+
+
+def _normalise(value, unit):
+    """ncu picks a unit per column and report: bring times to us, byte counts to Mbyte, shared memory to Kbyte/block."""
+    try:
+        v = float(value.replace(",", ""))
+    except ValueError:
+        return value, unit
+    if unit in _TIME:
+        return f"{v * _TIME[unit]:.3f}", "us"
+    if unit in _BYTES:
+        return f"{v * _BYTES[unit]:.6f}", "Mbyte"
+    if unit in _SMEM:
+        return f"{v * _SMEM[unit]:.3f}", "Kbyte/block"
+    return value, unit
+
+
+def full(reps, dst, skip=()):
+    """One row per captured launch of one or several reports (comma separated), units normalised; kernels whose name starts
+    with an entry of `skip` are dropped (stale rows of an older capture that a newer report replaces)."""
+    out_rows, out_units, cols = [], None, None
+    for rep in reps.split(","):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        idx = [hdr.index(c) for c in FULL_COLS if c in hdr]
+        cols = [hdr[i] for i in idx]
+        for d in data:
+            name = d[idx[0]].replace("void ", "")
+            if any(name.startswith(k) for k in skip):
+                continue
+            vals, us = [], []
+            for i in idx:
+                v, u = _normalise(d[i][:70], units[i])
+                vals.append(v)
+                us.append(u)
+            out_units = us
+            out_rows.append(vals)
+        skip = ()  # only the first report is filtered
     with open(dst, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow([hdr[i] for i in idx])
-        w.writerow([units[i] for i in idx])
-        for d in data:
-            w.writerow([d[i][:70] for i in idx])
-    print(f"{len(data)} launches -> {dst}")
+        w.writerow(cols)
+        w.writerow(out_units)
+        w.writerows(out_rows)
+    print(f"{len(out_rows)} launches -> {dst}")
 
 
 PEAK_GBPS = 6650.0  # fallback of B200_PROFILING.md; MEASURED_PEAKS.json is absent on this pool
@@ -86,6 +122,9 @@ def roofline(src, dst):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) != 4 or sys.argv[1] not in ("launches", "full", "roofline"):
+    if len(sys.argv) not in (4, 5) or sys.argv[1] not in ("launches", "full", "roofline"):
         sys.exit(__doc__)
-    {"launches": launches, "full": full, "roofline": roofline}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "full":
+        full(sys.argv[2], sys.argv[3], tuple(sys.argv[4].split(",")) if len(sys.argv) == 5 else ())
+    else:
+        {"launches": launches, "roofline": roofline}[sys.argv[1]](sys.argv[2], sys.argv[3])
