@@ -1,4 +1,4 @@
-// scvod_internal.h — shared declarations between the CUDA kernels (scvod_kernels.cu), the C-ABI
+// scvod_internal.h — shared declarations between the CUDA kernels (scvod_ground.cu, scvod_voxel.cu, scvod_track.cu), the C-ABI
 // layer (scvod_api.cpp) and the host-side cluster logic (host_cluster.cpp).
 #pragma once
 #include <cstdint>
@@ -93,7 +93,7 @@ struct HostParams {
   int track_ctas_per_sm = 1;  // grid cap of k_track (set per launch from the number of live contexts)
 };
 
-// kernel launch wrappers (scvod_kernels.cu). All asynchronous on `stream`. Return launch count.
+// kernel launch wrappers (scvod_ground.cu / scvod_voxel.cu / scvod_track.cu). All asynchronous on `stream`. Return launch count.
 int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
 int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
 int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int total_points, void* stream);
