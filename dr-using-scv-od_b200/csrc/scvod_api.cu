@@ -232,6 +232,7 @@ struct scvod_ctx {
   std::vector<std::unique_ptr<PersistBatch>> batch_pool;  // released batches kept for reuse (no cudaMalloc in steady state)
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
+  cudaEvent_t sync_event = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning (see wait_stream)
   // scvod_prefetch_scans: upload of the next batch on a private stream, consumed by the next scvod_push_scans of the same buffer
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t prefetch_done = nullptr;
@@ -246,6 +247,19 @@ struct scvod_ctx {
   void* gicp = nullptr;  // GICP state (scvod_gicp.cu)
   void (*gicp_free)(void*) = nullptr;
 };
+
+// Wait for everything queued on the context's stream.  The wait sleeps on a blocking-sync event instead of spinning in
+// cudaStreamSynchronize: with several contexts per GPU (one host thread each) and few host cores per GPU, a thread that
+// waits for the GPU must leave its core to the threads that have cluster bookkeeping to do.
+static cudaError_t wait_stream(scvod_ctx* c, cudaStream_t st) {
+  if (!c->sync_event) {
+    cudaError_t e = cudaEventCreateWithFlags(&c->sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(c->sync_event, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(c->sync_event);
+}
 
 namespace scvod {
 void* ctx_stream(scvod_ctx* c) { return (void*)c->stream; }
@@ -474,6 +488,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
     cudaStreamDestroy(c->copy_stream);
   }
   if (c->prefetch_done) cudaEventDestroy(c->prefetch_done);
+  if (c->sync_event) cudaEventDestroy(c->sync_event);
   c->d_prefetch.release();
   delete c;
   return SCVOD_OK;
@@ -629,7 +644,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   c->launches += launch_cluster_prep(c->hp, w, nscans, max_n, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_scan_counts.p, w.scan_counts, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(wait_stream(c, st));
   if (g_prof.on) g_prof.add("  h2d + kernels + sync", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
   const int32_t* sc = c->h_scan_counts.p;
   if (sc[(size_t)w.cap_scans * 8] & 1) return fail(SCVOD_ERR_CAPACITY, "a PatchWork patch holds more points than the largest fit tile");
@@ -698,7 +713,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   c->launches += launch_pack(c->d_desc.p, nd, max_desc_n, c->d_pack.p, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_pack.p, c->d_pack.p, sizeof(int32_t) * pack_ints, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(wait_stream(c, st));
   const int32_t* hp_cnt = c->h_pack.p + o_cnt;
   const int32_t* hp_root = c->h_pack.p + o_root;
   const int32_t* hp_name = c->h_pack.p + o_name;
@@ -1042,10 +1057,14 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
     } else {
       PROF("    track: wait (poll)");
       volatile int32_t* flag = c->h_triples.p;
-      int spins = 0;
+      // Spin for a few microseconds (a lone context gets its answer with the lowest latency), then yield the core on
+      // every probe: with more contexts than host cores per GPU the waiting threads must not starve the ones that have
+      // cluster decisions to compute.  Every ~2000 probes make sure the stream is still alive.
+      static const int spin_first = getenv("SCVOD_POLL_SPINS") ? atoi(getenv("SCVOD_POLL_SPINS")) : 200;
+      int spins = 0, since_query = 0;
       while ((nt = *flag) < 0) {
-        if (++spins >= 2000) {  // ~every few tens of microseconds: make sure the stream is still alive
-          spins = 0;
+        if (++since_query >= 2000) {
+          since_query = 0;
           cudaError_t qe = cudaStreamQuery(c->stream);
           if (qe == cudaSuccess) {
             nt = *flag;
@@ -1053,11 +1072,14 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
             break;
           }
           if (qe != cudaErrorNotReady) return fail(SCVOD_ERR_CUDA, std::string("k_track: ") + cudaGetErrorString(qe));
-          sched_yield();  // more contexts than cores: let another worker's host work run
         }
+        if (++spins > spin_first) {
+          sched_yield();
+        } else {
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+          __builtin_ia32_pause();
 #endif
+        }
       }
       std::atomic_thread_fence(std::memory_order_acquire);
     }
@@ -1339,7 +1361,7 @@ static int refresh_batch_labels(scvod_ctx* c, int batch) {
   c->launches += launch_final_labels(pb.off_dev.p, pb.scan_counts_dev.p, pb.nscans, pb.max_n, pb.apri_src.p, pb.apri_cid.p, c->d_vcls.p,
                                      reinterpret_cast<const uint8_t*>(c->d_vcls.p + pb.nscans), pb.cls.p, c->stream);
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next batch
+  CU(wait_stream(c, c->stream));  // the staging buffer is reused by the next batch
   pb.labels_current = true;
   return SCVOD_OK;
 }
@@ -1383,7 +1405,7 @@ extern "C" int scvod_labels_range(scvod_ctx* c, int f0, int f1, uint8_t* cls, in
     pos += bytes;
     f = g;
   }
-  CU(cudaStreamSynchronize(c->stream));
+  CU(wait_stream(c, c->stream));
   return SCVOD_OK;
 }
 
@@ -1414,7 +1436,7 @@ extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float
   }
   unsigned long long cnt = 0;
   CU(cudaMemcpyAsync(&cnt, c->d_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(wait_stream(c, c->stream));
   *n_points = (int64_t)std::min<unsigned long long>(cnt, (unsigned long long)cap_points);
   return cnt > (unsigned long long)cap_points ? fail(SCVOD_ERR_CAPACITY, "submap buffer too small") : SCVOD_OK;
 }
