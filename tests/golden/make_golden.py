@@ -75,6 +75,26 @@ def main():
         out[f"labels{f}"] = orc.labels(f)
     np.savez_compressed(os.path.join(HERE, "scan_small.npz"), **out)
 
+    # SSC::intialization (ssc.cpp:1148-1248): six small scans whose base frame gets two fusions
+    orc2 = conftest.Oracle(P)
+    init = {}
+    iposes = []
+    for k in range(6):
+        s, pose = pkg.synth_scan(conftest.SEED, k, rings=16, cols=450)
+        init[f"xyzi{k}"] = s
+        iposes.append(pose)
+        orc2.push_scan(s)
+    iposes = np.stack(iposes)
+    init["poses"] = iposes
+    init["base"] = np.int32(orc2.initialization(iposes))
+    cl = orc2.clusters(-1)
+    for key in ("name", "type", "npts", "nvox", "bbox"):
+        init["cl_" + key] = cl[key]
+    init["vox_label"] = orc2.voxels(-1)["label"]
+    init["n_clusters_before"] = np.int32(len(orc2.clusters(int(init["base"]))["name"]))
+    np.savez_compressed(os.path.join(HERE, "init_small.npz"), **init)
+    orc2.close()
+
     hashes = {}
     for k in range(3):
         s, pose = pkg.synth_scan(conftest.SEED, k)

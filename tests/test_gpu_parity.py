@@ -295,6 +295,19 @@ def test_golden_fixture_through_gpu(pkg):
     s.close()
 
 
+def test_initialization_golden_fixture_through_gpu(pkg):
+    z = np.load(os.path.join(GOLD, "init_small.npz"))
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=16 * 450, max_batch=8)
+    s.process([z[f"xyzi{k}"] for k in range(6)])
+    assert s.intialization(z["poses"]) == int(z["base"])
+    cl = s.frame_clusters(pkg.INIT_FRAME)
+    for key in ("name", "type", "npts", "nvox"):
+        assert np.array_equal(cl[key], z["cl_" + key]), key
+    assert np.array_equal(cl["bbox"].view(np.uint32), z["cl_bbox"].view(np.uint32))
+    assert np.array_equal(s.frame_voxels(pkg.INIT_FRAME)["label"], z["vox_label"])
+    s.close()
+
+
 # ---- size-independent properties at the benchmark size ----------------------------------------------------
 def test_full_size_batch_properties(pkg):
     n = 16

@@ -81,6 +81,22 @@ def test_oracle_reproduces_scan_fixture(oracle):
         assert np.array_equal(oracle.labels(f), z[f"labels{f}"])
 
 
+def test_oracle_reproduces_initialization_fixture(oracle):
+    """SSC::intialization restated (SURVEY 8(f) row 1): base frame choice, fused clusters, re-recognised types, voxel labels."""
+    z = np.load(os.path.join(GOLD, "init_small.npz"))
+    for k in range(6):
+        oracle.push_scan(z[f"xyzi{k}"])
+    assert oracle.initialization(z["poses"]) == int(z["base"])
+    cl = oracle.clusters(-1)
+    for key in ("name", "type", "npts", "nvox"):
+        assert np.array_equal(cl[key], z["cl_" + key]), key
+    assert np.array_equal(cl["bbox"].view(np.uint32), z["cl_bbox"].view(np.uint32))
+    assert np.array_equal(oracle.voxels(-1)["label"], z["vox_label"])
+    assert len(cl["name"]) < int(z["n_clusters_before"])  # the fixture does contain fusions
+    # the sequence itself is left untouched (frames are copied, ssc.cpp:1161,1168)
+    assert len(oracle.clusters(int(z["base"]))["name"]) == int(z["n_clusters_before"])
+
+
 def test_synth_generator_is_deterministic(pkg):
     h = json.load(open(os.path.join(GOLD, "synth_hash.json")))
     import hashlib
