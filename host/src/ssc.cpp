@@ -10,6 +10,7 @@
 // filled from the library's inspection calls so that downstream code reading them keeps working; filling them
 // is bookkeeping, not a compute path — nothing here bins, fits or clusters on the CPU.
 #include "ssc.h"
+#include "voxel_grid.h"
 
 #include <cstring>
 #include <stdexcept>
@@ -552,9 +553,9 @@ void SSC::getCloud() {
     ros::shutdown();
     return;
   }
-  // KITTI velodyne .bin (+ .label): drop labels 0/1, intensity * max_intensity (src/ssc.cpp:1041-1071).
-  // The reference's 0.08 m pcl::VoxelGrid downsample (src/ssc.cpp:1108-1111) is a loader step outside the
-  // hot-path scope and is NOT applied here.
+  // KITTI velodyne .bin (+ .label): drop labels 0/1, intensity * max_intensity (src/ssc.cpp:1041-1071), then the
+  // 0.08 m pcl::VoxelGrid downsample of src/ssc.cpp:1108-1111 (restated in include/voxel_grid.h; loader code, it runs
+  // on the host as in the reference).
   std::vector<std::string> bins, labels;
   for (auto& e : fs::directory_iterator(data_path)) bins.push_back(e.path().string());
   std::sort(bins.begin(), bins.end());
@@ -590,6 +591,7 @@ void SSC::getCloud() {
       p.intensity = values[4 * k + 3] * max_intensity;
       cloud->points.push_back(p);
     }
+    ufo::voxelGridXYZI(*cloud, 0.08f, *cloud);
     cloud_vec.emplace_back(cloud);
   }
   ROS_DEBUG("load cloud size: %d", (int)cloud_vec.size());
@@ -685,4 +687,26 @@ Pose SSC::gicpScanToMap(const pcl::PointCloud<pcl::PointXYZI>::Ptr& cloud_, cons
   out.pitch = res.pose6[4];
   out.yaw = res.pose6[5];
   return out;
+}
+
+
+// test hook (tests/test_host_cpp.py): the loader's voxel-grid downsample on a flat xyzi array
+extern "C" int ufo_voxel_grid(const float* xyzi, int n, float leaf, float* out_xyzi, int* n_out) {
+  pcl::PointCloud<pcl::PointXYZI> in, out;
+  in.points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    in.points[i].x = xyzi[4 * i];
+    in.points[i].y = xyzi[4 * i + 1];
+    in.points[i].z = xyzi[4 * i + 2];
+    in.points[i].intensity = xyzi[4 * i + 3];
+  }
+  const bool ok = ufo::voxelGridXYZI(in, leaf, out);
+  *n_out = (int)out.points.size();
+  for (size_t i = 0; i < out.points.size(); ++i) {
+    out_xyzi[4 * i] = out.points[i].x;
+    out_xyzi[4 * i + 1] = out.points[i].y;
+    out_xyzi[4 * i + 2] = out.points[i].z;
+    out_xyzi[4 * i + 3] = out.points[i].intensity;
+  }
+  return ok ? 0 : 1;
 }

@@ -36,6 +36,42 @@ def test_host_layer_builds(host_build):
         assert sym in out, sym
 
 
+def test_loader_voxel_grid(host_build):
+    """The 0.08 m VoxelGrid of the KITTI loader (reference src/ssc.cpp:1108-1111, restated in host/include/voxel_grid.h):
+    one output per occupied leaf, in ascending leaf index, each the mean of the leaf's points (float sums: 1e-4)."""
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(host_build, "libufo_host.so"))
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([rng.uniform(-20, 20, (20000, 3)), rng.uniform(0, 255, (20000, 1))], axis=1).astype(np.float32)
+    pts[:, 2] = rng.uniform(-2, 4, 20000).astype(np.float32)
+    pts[:5000, :3] = (pts[:5000, :3] / 40).astype(np.float32)  # a dense blob: many points per leaf
+    out = np.zeros_like(pts)
+    n_out = ctypes.c_int(0)
+    leaf = np.float32(0.08)
+    rc = lib.ufo_voxel_grid(pts.ctypes.data_as(ctypes.c_void_p), len(pts), ctypes.c_float(float(leaf)), out.ctypes.data_as(ctypes.c_void_p),
+                            ctypes.byref(n_out))
+    assert rc == 0
+    out = out[: n_out.value]
+    inv = np.float32(1.0) / leaf
+    ijk = np.floor(pts[:, :3] * inv).astype(np.int64)
+    mn = ijk.min(axis=0)
+    div = ijk.max(axis=0) - mn + 1
+    idx = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+    uniq, inverse, counts = np.unique(idx, return_inverse=True, return_counts=True)
+    assert len(out) == len(uniq) and counts.max() > 10
+    sums = np.zeros((len(uniq), 4), np.float64)
+    np.add.at(sums, inverse, pts.astype(np.float64))
+    assert np.allclose(out, sums / counts[:, None], rtol=0, atol=1e-4 * max(1.0, float(np.abs(pts).max())) / 100)
+    # an empty cloud stays empty, a single point is returned as it is
+    assert lib.ufo_voxel_grid(pts.ctypes.data_as(ctypes.c_void_p), 0, ctypes.c_float(0.08), out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n_out)) == 0
+    assert n_out.value == 0
+    one = np.array([[1.0, 2.0, 3.0, 4.0]], np.float32)
+    o1 = np.zeros_like(one)
+    lib.ufo_voxel_grid(one.ctypes.data_as(ctypes.c_void_p), 1, ctypes.c_float(0.08), o1.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n_out))
+    assert n_out.value == 1 and np.array_equal(o1, one)
+
+
 @pytest.mark.skipif(not os.path.exists(REF_MAIN), reason="reference checkout not present (GPU box)")
 def test_reference_main_cpp_compiles_unchanged(host_build):
     subprocess.check_call(["make", "-C", HOST, "ref_main"], stdout=subprocess.DEVNULL)
