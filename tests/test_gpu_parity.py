@@ -186,6 +186,26 @@ def test_pipeline_stage_by_stage_kitti(pkg, ssc, oracle):
     assert ndyn > 0  # the sequence does contain moving cars
 
 
+def test_degenerate_scans_inside_a_batch(pkg, oracle):
+    """Empty, tiny and ground-only scans between normal ones: same classes as the oracle, nothing crashes."""
+    rng = np.random.default_rng(3)
+    normal = [pkg.synth_scan(conftest.SEED + 40, k, rings=16, cols=450) for k in range(3)]
+    flat = np.concatenate([rng.uniform(-20, 20, (3000, 2)), np.full((3000, 1), -1.73) + rng.normal(0, 0.01, (3000, 1)),
+                           np.full((3000, 1), 20.0)], axis=1).astype(np.float32)
+    scans = [normal[0][0], np.zeros((0, 4), np.float32), normal[1][0], np.array([[5, 5, -1.7, 1], [6, 5, 0.5, 9], [7, 1, 0.2, 3]], np.float32),
+             flat, normal[2][0]]
+    poses = np.stack([normal[0][1], normal[0][1], normal[1][1], normal[1][1], normal[1][1], normal[2][1]])
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=16 * 450, max_batch=8)
+    labels = s.segDF(scans, poses)
+    for sc in scans:
+        oracle.push_scan(sc)
+    oracle.track(poses)
+    for f in range(len(scans)):
+        assert np.array_equal(s.frame_counts(f)[:8], oracle.counts(f)[:8]), f
+        assert np.array_equal(labels[f], oracle.labels(f)), f
+    s.close()
+
+
 def test_name_replay_global_memory_variant(pkg, oracle):
     """Very dense scans keep the union-find state of k_name_replay in global memory: same names, same clusters."""
     s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=4)
