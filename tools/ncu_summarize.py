@@ -6,6 +6,8 @@
   python tools/ncu_summarize.py full <report.ncu-rep>[,<report2>...] <out_summary.csv> [kernels,to,skip,in,the,first]
       one row per captured launch of `ncu --set full` reports (duration, grid, registers, shared memory, achieved
       occupancy, DRAM bytes read/written, DRAM and SM throughput, L2 bytes, instructions, shared-memory bank conflicts)
+  python tools/ncu_summarize.py hotspots <report.ncu-rep> <out.txt> <kernel,regexes>
+      per kernel, the SASS instructions with the most warp-stall samples and their stall reasons
   python tools/ncu_summarize.py roofline <full_summary.csv> <out_roofline.csv>
       derived: DRAM GB/s per launch = (read + written bytes) / duration and its fraction of the HBM peak
 """
@@ -96,6 +98,43 @@ def full(reps, dst, skip=()):
     print(f"{len(out_rows)} launches -> {dst}")
 
 
+def hotspots(rep, dst, kernels):
+    """Per kernel: the instructions with the most warp-stall samples (SASS, needs -lineinfo / --import-source for the source
+    page), with their dominant stall reasons and their share of the kernel's samples."""
+    lines_out = []
+    for kern in kernels:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern, "-c", "1"], capture_output=True, text=True).stdout
+        lines = out.splitlines()
+        start = next((i for i, l in enumerate(lines) if l.startswith('"Address"')), None)
+        if start is None:
+            continue
+        name = lines[0].split('","')[1][:90] if lines and '","' in lines[0] else kern
+        r = csv.reader(lines[start:])
+        hdr = next(r)
+        ia, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+        stalls = [(j, h) for j, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+        rows = []
+        for row in r:
+            if len(row) != len(hdr) or row[0] == "Address":
+                break
+            rows.append(row)
+        total = sum(int(x[isamp]) for x in rows) or 1
+        by_reason = collections.Counter()
+        for row in rows:
+            for j, h in stalls:
+                by_reason[h] += int(row[j])
+        lines_out.append(f"== {name}  ({len(rows)} SASS instructions, {total} stall samples)")
+        lines_out.append("   stall reasons: " + ", ".join(f"{h[6:]} {100.0 * c / max(1, sum(by_reason.values())):.0f}%" for h, c in by_reason.most_common(6)))
+        top = sorted(range(len(rows)), key=lambda k: -int(rows[k][isamp]))[:15]
+        for k in sorted(top):
+            row = rows[k]
+            st = sorted([(int(row[j]), h[6:]) for j, h in stalls if int(row[j]) > 0], reverse=True)[:2]
+            lines_out.append(f"   #{k:<5d} {100.0 * int(row[isamp]) / total:5.1f}%  exec {row[iex]:>9s}  {row[ia].strip()[:64]:64s} {st}")
+        lines_out.append("")
+    open(dst, "w").write("\n".join(lines_out) + "\n")
+    print(f"{len(kernels)} kernels -> {dst}")
+
+
 PEAK_GBPS = 6650.0  # fallback of B200_PROFILING.md; MEASURED_PEAKS.json is absent on this pool
 
 
@@ -122,9 +161,11 @@ def roofline(src, dst):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) not in (4, 5) or sys.argv[1] not in ("launches", "full", "roofline"):
+    if len(sys.argv) not in (4, 5) or sys.argv[1] not in ("launches", "full", "roofline", "hotspots"):
         sys.exit(__doc__)
-    if sys.argv[1] == "full":
+    if sys.argv[1] == "hotspots":
+        hotspots(sys.argv[2], sys.argv[3], sys.argv[4].split(","))
+    elif sys.argv[1] == "full":
         full(sys.argv[2], sys.argv[3], tuple(sys.argv[4].split(",")) if len(sys.argv) == 5 else ())
     else:
         {"launches": launches, "roofline": roofline}[sys.argv[1]](sys.argv[2], sys.argv[3])
