@@ -66,7 +66,7 @@ EXPORTS = (
     "scvod_push_scans_dev", "scvod_track", "scvod_num_frames", "scvod_reset_frames", "scvod_frame_labels",
     "scvod_labels_range", "scvod_frame_counts", "scvod_frame_ground_order", "scvod_frame_apri", "scvod_frame_voxels",
     "scvod_frame_point_cluster", "scvod_frame_clusters", "scvod_static_submap_dev", "scvod_last_patch_records",
-    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
+    "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_host_segment_pts", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
     "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
 )

@@ -50,25 +50,44 @@ struct NameReplay {
   }
 };
 
-int replay_cluster_names(const ScanTables& t, std::vector<int>& vox_name) {
-  const int V = t.V;
+// Hybrid replay.  Nodes are the voxels [0, V) and, for the voxels that hold a point with a -1 index ("tainted", see
+// ScanTables), their points one by one [V, V + n_tpts): such a voxel is seen by visitors as the sequence of its points
+// (ptIdx order), and each of its points visits with its OWN findVoxelNeighbors list (which need not contain the voxel it
+// hashes into, ssc.cpp:185-188,311).  Every point of a tainted voxel is an event; ordinary voxels keep the three-state logic.
+int replay_cluster_names(const ScanTables& t, std::vector<int>& vox_name, std::vector<int>& tp_name) {
+  const int V = t.V, N = V + t.n_tpts;
   NameReplay u;
-  u.parent.resize(V);
-  u.setname.assign(V, -1);
-  u.state.assign(V, 0);
-  u.stable.assign(V, 0);
-  for (int v = 0; v < V; ++v) u.parent[v] = v;
+  u.parent.resize(N);
+  u.setname.assign(N, -1);
+  u.state.assign(N, 0);
+  u.stable.assign(N, 0);
+  for (int v = 0; v < N; ++v) u.parent[v] = v;
+  std::vector<int> tbase(t.n_tvox ? V : 0, -1), tcnt(t.n_tvox ? V : 0, 0);
+  for (int i = 0; i < t.n_tvox; ++i) {
+    tbase[t.tv_cid[i]] = t.tv_base[i];
+    tcnt[t.tv_cid[i]] = t.tv_base[i + 1] - t.tv_base[i];
+  }
+  std::vector<int> seq;
   int cluster_name = 4;  // ssc.cpp:300
   for (int e = 0; e < t.n_events; ++e) {
     const int W = t.ev_cid[e];
-    if (u.stable[W]) continue;
-    const int32_t* nb = t.vox_nbr + 27 * (size_t)W;
+    const bool is_pt = W >= V;
+    if (!is_pt && u.stable[W]) continue;
+    const int32_t* nb = is_pt ? t.tp_nbr + 27 * (size_t)(W - V) : t.vox_nbr + 27 * (size_t)W;
     const bool labelled = (u.state[W] == 2);
     int oc = labelled ? u.find(W) : -1;
     bool skipped = false;
-    for (int k = 0; k < 27; ++k) {
+    seq.clear();
+    for (int k = 0; k < 27; ++k) {  // the visiting sequence: whole ordinary voxels, tainted voxels point by point
       const int Vn = nb[k];
       if (Vn < 0) continue;
+      if (t.n_tvox && tbase[Vn] >= 0) {
+        for (int j = 0; j < tcnt[Vn]; ++j) seq.push_back(V + tbase[Vn] + j);
+      } else {
+        seq.push_back(Vn);
+      }
+    }
+    for (int Vn : seq) {
       if (u.state[Vn] == 0) {
         if (oc >= 0) {
           u.parent[Vn] = oc;  // clusterIdxs[neighbor] = oc (:338)
@@ -92,13 +111,17 @@ int replay_cluster_names(const ScanTables& t, std::vector<int>& vox_name) {
       u.parent[W] = W;
       u.setname[W] = cluster_name;
       u.state[W] = 2;
-      for (int k = 0; k < 27; ++k) {
-        const int Vn = nb[k];
-        if (Vn < 0 || Vn == W) continue;
+      for (int Vn : seq) {
+        if (Vn == W) continue;
         u.parent[Vn] = W;
         u.state[Vn] = 2;
       }
       u.stable[W] = 1;
+    } else if (is_pt) {
+      if (u.state[W] == 0) {
+        u.state[W] = 2;
+        u.parent[W] = oc;
+      }
     } else {
       if (u.state[W] == 0) {  // only this (first) point of W got the label
         u.state[W] = 1;
@@ -108,7 +131,9 @@ int replay_cluster_names(const ScanTables& t, std::vector<int>& vox_name) {
     }
   }
   vox_name.resize(V);
-  for (int v = 0; v < V; ++v) vox_name[v] = u.setname[u.find(v)];
+  for (int v = 0; v < V; ++v) vox_name[v] = (t.n_tvox && tbase[v] >= 0) ? -1 : u.setname[u.find(v)];
+  tp_name.resize(t.n_tpts);
+  for (int q = 0; q < t.n_tpts; ++q) tp_name[q] = u.setname[u.find(V + q)];
   return cluster_name;
 }
 
@@ -143,13 +168,15 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   double tp_last = now_us();
 #endif
   const int V = t.V;
+  const bool taint = t.n_tvox > 0;
   // ---- clusterAndCreateFrame (ssc.cpp:299-393) ---------------------------------------------------
-  std::vector<int> vox_name;
+  std::vector<int> vox_name, tp_name;
   int last_name;
   // cluster_pt is filled in point order, so its keys are inserted in order of each cluster's first point (:360-375)
   std::unordered_map<int, int> cluster_pt;
   if (t.vox_name) {  // names replayed on the device
     vox_name.assign(t.vox_name, t.vox_name + V);
+    if (taint) tp_name.assign(t.tp_name, t.tp_name + t.n_tpts);
     last_name = t.max_name;
     std::vector<std::pair<int, int>> order;  // (first event, name)
     for (int nm = 0; nm <= last_name; ++nm)
@@ -157,10 +184,12 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     std::sort(order.begin(), order.end());
     for (auto& o : order) cluster_pt.insert(std::make_pair(o.second, 0));
   } else {
-    last_name = replay_cluster_names(t, vox_name);
+    last_name = replay_cluster_names(t, vox_name, tp_name);
     std::vector<char> seen(last_name + 2, 0);
     for (int e = 0; e < t.n_events; ++e) {
-      int nm = vox_name[t.ev_cid[e]];
+      const int node = t.ev_cid[e];
+      int nm = node >= V ? tp_name[node - V] : vox_name[node];
+      if (nm < 0) return false;
       if (!seen[nm]) {
         seen[nm] = 1;
         cluster_pt.insert(std::make_pair(nm, 0));
@@ -171,36 +200,111 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   out.max_name = last_name;  // frame_ssc.max_name = cluster_name++ (:354)
   out.vox_label = vox_name;
   out.cluster_set.clear();
+  out.tvox.clear();
+  out.sgs_of_tvox.clear();
+  out.subgroups.clear();
+  std::vector<uint8_t> tflag;
+  if (taint) {
+    tflag.assign(V, 0);
+    for (int i = 0; i < t.n_tvox; ++i) {
+      if (t.tv_cid[i] < 0 || t.tv_cid[i] >= V || (i && t.tv_cid[i] <= t.tv_cid[i - 1])) return false;
+      tflag[t.tv_cid[i]] = 1;
+    }
+    for (int q = 0; q < t.n_tpts; ++q)
+      if (tp_name[q] < 0 || tp_name[q] > last_name) return false;
+  }
   for (int v = 0; v < V; ++v)
-    if (vox_name[v] < 0 || vox_name[v] > last_name) return false;
+    if (!(taint && tflag[v]) && (vox_name[v] < 0 || vox_name[v] > last_name)) return false;
 
   // voxels of every cluster in ascending compact id (== sorted voxel_idx): counting sort by name
   std::vector<int> name_start(last_name + 3, 0), vox_sorted(V);
-  for (int v = 0; v < V; ++v) name_start[vox_name[v] + 1]++;
+  for (int v = 0; v < V; ++v)
+    if (!(taint && tflag[v])) name_start[vox_name[v] + 1]++;
   for (int nm = 0; nm <= last_name + 1; ++nm) name_start[nm + 1] += name_start[nm];
   {
     std::vector<int> cur(name_start.begin(), name_start.end() - 1);
-    for (int v = 0; v < V; ++v) vox_sorted[cur[vox_name[v]]++] = v;
+    for (int v = 0; v < V; ++v)
+      if (!(taint && tflag[v])) vox_sorted[cur[vox_name[v]]++] = v;
   }
-  std::unordered_map<int, std::vector<int>> roots_of;  // cluster name -> CVC component roots it contains
+  // tainted voxels: their points grouped by the name clusterAndCreateFrame gave them
+  std::unordered_map<int, std::vector<int>> sgs_of_name;  // name -> subgroups, ascending voxel
+  if (taint) {
+    out.tvox.assign(t.tv_cid, t.tv_cid + t.n_tvox);
+    out.sgs_of_tvox.resize(t.n_tvox);
+    for (int i = 0; i < t.n_tvox; ++i) {
+      for (int q = t.tv_base[i]; q < t.tv_base[i + 1]; ++q) {
+        int sg = -1;
+        for (int k : out.sgs_of_tvox[i])
+          if (out.subgroups[k].stage_name[0] == tp_name[q]) sg = k;
+        if (sg < 0) {
+          sg = (int)out.subgroups.size();
+          out.subgroups.emplace_back();
+          SubGroup& g = out.subgroups.back();
+          g.vox = t.tv_cid[i];
+          g.stage_name[0] = tp_name[q];
+          for (int d = 0; d < 3; ++d) {
+            g.bb_min[d] = 3.402823466e38f;
+            g.bb_max[d] = -3.402823466e38f;
+          }
+          out.sgs_of_tvox[i].push_back(sg);
+          sgs_of_name[tp_name[q]].push_back(sg);
+        }
+        SubGroup& g = out.subgroups[sg];
+        g.pts.push_back(t.tp_m[q]);
+        for (int d = 0; d < 3; ++d) {
+          g.bb_min[d] = std::min(g.bb_min[d], t.tp_xyz[4 * (size_t)q + d]);
+          g.bb_max[d] = std::max(g.bb_max[d], t.tp_xyz[4 * (size_t)q + d]);
+        }
+      }
+    }
+  }
+  std::unordered_map<int, std::vector<int>> roots_of;  // cluster name -> classes of voxels it contains: roots of the CVC components
+                                                       // of ordinary voxels, tainted voxels one by one
   for (auto& c : cluster_pt) {  // (:377-385) same iteration order as the reference's cluster_pt
     HCluster cl;
     cl.name = c.first;
     cl.occupy_voxels.assign(vox_sorted.begin() + name_start[c.first], vox_sorted.begin() + name_start[c.first + 1]);
-    cl.part_end.push_back((int)cl.occupy_voxels.size());
     int np = 0;
     for (int v : cl.occupy_voxels) np += t.vox_cnt[v];
+    if (!taint) {
+      if (!cl.occupy_voxels.empty()) roots_of[c.first].push_back(t.vox_root[cl.occupy_voxels[0]]);
+    } else {
+      std::vector<int>& ro = roots_of[c.first];
+      for (int v : cl.occupy_voxels) ro.push_back(t.vox_root[v]);
+      sample_vec(ro);
+      auto sit = sgs_of_name.find(c.first);
+      if (sit != sgs_of_name.end()) {
+        std::vector<int> tv;
+        for (int sg : sit->second) {
+          cl.tunits.push_back(HCluster::TUnit{sg, 0});
+          np += (int)out.subgroups[sg].pts.size();
+          tv.push_back(out.subgroups[sg].vox);
+          ro.push_back(out.subgroups[sg].vox);
+        }
+        std::vector<int> merged(cl.occupy_voxels.size() + tv.size());  // sampleVec(occupy_voxels), :383
+        std::merge(cl.occupy_voxels.begin(), cl.occupy_voxels.end(), tv.begin(), tv.end(), merged.begin());
+        cl.occupy_voxels.swap(merged);
+      }
+    }
+    cl.part_end.push_back((int)cl.occupy_voxels.size());
     cl.npts = np;
-    if (!cl.occupy_voxels.empty()) roots_of[c.first].push_back(t.vox_root[cl.occupy_voxels[0]]);
     out.cluster_set.insert(std::make_pair(cl.name, std::move(cl)));
   }
+  std::vector<int>& vox_label = out.vox_label;
+  if (taint) {  // hash_cloud[v].label = c.first in cluster_set order (:387-391): a tainted voxel keeps the LAST cluster that lists it
+    for (int i = 0; i < t.n_tvox; ++i) vox_label[t.tv_cid[i]] = -1;
+    for (auto& c : out.cluster_set)
+      for (auto& tu : c.second.tunits) vox_label[out.subgroups[tu.sg].vox] = c.first;
+  }
   out.n_clusters[0] = (int)out.cluster_set.size();
-  if (keep_stages) out.vox_name_stage[0] = vox_name;
-  // the replayed name partition must coincide with the GPU's connected components
+  if (keep_stages) out.vox_name_stage[0] = vox_label;
+  // the replayed names must be constant on the GPU's connected components of ordinary voxels (and, without tainted voxels,
+  // the two partitions coincide)
   {
     std::vector<int> root_name(V, -1);
     int nroots = 0;
     for (int v = 0; v < V; ++v) {
+      if (taint && tflag[v]) continue;
       int r = t.vox_root[v];
       if (r < 0 || r >= V) return false;
       if (root_name[r] == -1) {
@@ -210,21 +314,22 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
         return false;
       }
     }
-    if (nroots != (int)out.cluster_set.size()) return false;
+    if (!taint && nroots != (int)out.cluster_set.size()) return false;
   }
 
   TP(1);
   // ---- refineClusterByIntensity (ssc.cpp:571-635) at component granularity -------------------------
-  // E(K): components reached from component K by a voxel pair passing the similarity test (:588-594)
+  // E(K): classes reached from class K by a voxel pair passing the similarity test (:588-594).  All voxels of a class
+  // carry the same label at any time (an ordinary component lies inside one cluster and labels are written per cluster).
   std::unordered_map<int, std::vector<int>> comp_edges;
   for (int e = 0; e < t.n_edges; ++e) comp_edges[t.edges[2 * e]].push_back(t.edges[2 * e + 1]);
-  std::vector<int>& vox_label = out.vox_label;
   int iter = p.iteration;
   while (iter) {
     std::vector<std::pair<int, const HCluster*>> clusters;
     clusters.reserve(out.cluster_set.size());
     for (auto& c : out.cluster_set) clusters.push_back(std::make_pair(c.first, &c.second));
-    // sort1 (:24-26): occupy_voxels compared with >= ; the vectors are pairwise different
+    // sort1 (:24-26): occupy_voxels compared with >= ; the vectors are pairwise different (equal only for two clusters that
+    // consist of points of the same tainted voxels: std::sort with >= on equal elements is not reproduced, they stay adjacent)
     std::sort(clusters.begin(), clusters.end(), [](const std::pair<int, const HCluster*>& a, const std::pair<int, const HCluster*>& b) {
       return a.second->occupy_voxels > b.second->occupy_voxels;
     });
@@ -239,7 +344,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
           auto eit = comp_edges.find(K);
           if (eit == comp_edges.end()) continue;
           for (int K2 : eit->second) {
-            int lab = vox_label[K2];  // hash_cloud[n].label: every voxel of a component carries the same label
+            int lab = vox_label[K2];  // hash_cloud[n].label
             if (!name_in(invalid_name, lab)) neighbor_name.push_back(lab);
           }
         }
@@ -258,8 +363,10 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
         fusion.name = f;
         HCluster& src = out.cluster_set[f];
         int basev = (int)fusion.occupy_voxels.size();
+        const int base_parts = (int)fusion.part_end.size();
         fusion.occupy_voxels.insert(fusion.occupy_voxels.end(), src.occupy_voxels.begin(), src.occupy_voxels.end());
         for (int pe : src.part_end) fusion.part_end.push_back(basev + pe);
+        for (auto tu : src.tunits) fusion.tunits.push_back(HCluster::TUnit{tu.sg, base_parts + tu.part});
         fusion.npts += src.npts;
         auto rf = roots_of.find(f);
         if (rf != roots_of.end()) {
@@ -275,7 +382,11 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     iter--;
   }
   out.n_clusters[1] = (int)out.cluster_set.size();
-  if (keep_stages) out.vox_name_stage[1] = vox_label;
+  if (keep_stages) {
+    out.vox_name_stage[1] = vox_label;
+    for (auto& c : out.cluster_set)
+      for (auto& tu : c.second.tunits) out.subgroups[tu.sg].stage_name[1] = c.first;
+  }
 
   TP(2);
   // ---- refineClusterByBoundingBox (ssc.cpp:437-467) ------------------------------------------------
@@ -284,10 +395,18 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     HCluster& cl = c.second;
     float lo[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, hi[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
     for (int v : cl.occupy_voxels) {
+      if (taint && tflag[v]) continue;  // only the cluster's own points of a tainted voxel count: below
       const float* bb = t.vox_bbox + 6 * (size_t)v;
       for (int d = 0; d < 3; ++d) {
         lo[d] = std::min(lo[d], bb[d]);
         hi[d] = std::max(hi[d], bb[3 + d]);
+      }
+    }
+    for (auto& tu : cl.tunits) {
+      const SubGroup& g = out.subgroups[tu.sg];
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = std::min(lo[d], g.bb_min[d]);
+        hi[d] = std::max(hi[d], g.bb_max[d]);
       }
     }
     for (int d = 0; d < 3; ++d) {
@@ -302,7 +421,11 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     out.cluster_set.erase(e);
   }
   out.n_clusters[2] = (int)out.cluster_set.size();
-  if (keep_stages) out.vox_name_stage[2] = vox_label;
+  if (keep_stages) {
+    out.vox_name_stage[2] = vox_label;
+    for (auto& c : out.cluster_set)
+      for (auto& tu : c.second.tunits) out.subgroups[tu.sg].stage_name[2] = c.first;
+  }
 
   TP(3);
   recognize_clusters(p, out);

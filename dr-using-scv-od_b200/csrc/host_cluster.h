@@ -8,6 +8,7 @@
 // sequence as the reference so that cluster names, fusion order and tracking decisions come out
 // identical; the data it touches is O(voxels + clusters) per scan, not O(points).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <unordered_map>
 #include <vector>
@@ -39,6 +40,21 @@ struct HCluster {
     int csr_start, csr_len, part_base, npts;
   };
   std::vector<OwnRun> own_runs;
+  // Points of "tainted" voxels (voxels that hold a point with a -1 index, ssc.cpp:185-188): such a voxel appears in
+  // occupy_voxels of every cluster that owns one of its points, but only the listed subgroups (FrameClusters::subgroups)
+  // are in occupy_pts.  `part` is the part (see part_end) the subgroup's points belong to.  Empty for ordinary scans.
+  struct TUnit {
+    int sg, part;
+  };
+  std::vector<TUnit> tunits;
+};
+
+// The points of one tainted voxel that clusterAndCreateFrame put into one cluster (apri indices, ascending)
+struct SubGroup {
+  int vox = -1;
+  std::vector<int> pts;
+  float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+  int stage_name[3] = {-1, -1, -1};  // cluster that holds it after CVC / intensity refine / bbox refine (inspection)
 };
 
 // per-scan inputs from the GPU (host copies)
@@ -54,6 +70,16 @@ struct ScanTables {
   const int32_t* vox_name = nullptr;    // [V]
   const int32_t* name_first = nullptr;  // [max_name + 1] first event of every name (0x7fffffff: name vanished)
   int max_name = 0;
+  // Tainted voxels (a point with range / sector / azimuth index -1 hashes into a voxel that is not its own cell, ssc.cpp:185-188):
+  // their points are named one by one.  tv_cid ascending; points of voxel i are tp_*[tv_base[i] .. tv_base[i+1]) in ascending
+  // apri index.  An event with ev_cid >= V is point V + t of these tables.
+  int n_tvox = 0, n_tpts = 0;
+  const int32_t* tv_cid = nullptr;   // [n_tvox]
+  const int32_t* tv_base = nullptr;  // [n_tvox + 1]
+  const int32_t* tp_m = nullptr;     // [n_tpts] apri index
+  const float* tp_xyz = nullptr;     // [n_tpts][4]
+  const int32_t* tp_name = nullptr;  // [n_tpts] names replayed on the device (with vox_name)
+  const int32_t* tp_nbr = nullptr;   // [n_tpts][27] the point's own findVoxelNeighbors list (host replay only)
 };
 
 struct FrameClusters {
@@ -62,6 +88,15 @@ struct FrameClusters {
   std::unordered_map<int, HCluster> cluster_set;
   int n_clusters[3] = {0, 0, 0};
   std::vector<int> vox_name_stage[3];  // per-voxel cluster name after CVC / intensity refine / bbox refine (inspection)
+  // tainted voxels of the frame (ascending compact id), the subgroups of each, and all subgroups
+  std::vector<int> tvox;
+  std::vector<std::vector<int>> sgs_of_tvox;
+  std::vector<SubGroup> subgroups;
+  bool tainted(int v) const { return !tvox.empty() && std::binary_search(tvox.begin(), tvox.end(), v); }
+  const std::vector<int>* subgroups_of(int v) const {
+    auto it = std::lower_bound(tvox.begin(), tvox.end(), v);
+    return (it != tvox.end() && *it == v) ? &sgs_of_tvox[it - tvox.begin()] : nullptr;
+  }
 };
 
 // SSC::clusterAndCreateFrame + refineClusterByIntensity + refineClusterByBoundingBox + recognize

@@ -133,6 +133,7 @@ struct PersistBatch {
   DevBuf<int32_t> csr;
   PinBuf<int32_t> h_csr;
   int csr_n = 0;
+  int tv_n = 0;  // 4th section of csr: apri indices of the subgroups of tainted voxels (FrameHost::sg_tv_off)
   int max_n = 0;
   bool labels_current = false;
   // inspection-only
@@ -173,6 +174,7 @@ struct FrameHost {
   int n_in = 0, n_ground = 0, n_ng = 0, n_apri = 0, n_vox = 0;
   FrameClusters fc;
   std::vector<int32_t> vox_cnt;
+  std::vector<int> sg_tv_off;  // per subgroup of fc: offset of its points in the batch's tv_pts
 };
 
 }  // namespace
@@ -196,6 +198,10 @@ struct scvod_ctx {
   DevBuf<uint64_t> d_bucket_kv, d_edge_hash;
   DevBuf<float4> d_sorted_xyz;
   DevBuf<float> d_patch_dbg, d_vox_bbox, d_T;
+  // tainted voxels (points with a -1 index, see scvod_internal.h): side tables of the batch
+  DevBuf<int32_t> d_taint_cnt, d_q_list, d_vox_tnt, d_vox_group, d_tv_cid, d_tv_base, d_tp_m, d_tp_cid, d_tp_name;
+  DevBuf<float4> d_tp_xyz;
+  PinBuf<int32_t> h_taint_cnt;
   // pinned host mirrors of what the host logic reads per batch
   PinBuf<int32_t> h_scan_counts, h_vox_cnt, h_vox_root, h_vox_nbr, h_ev_cid, h_edge_buf;
   PinBuf<float> h_vox_bbox;
@@ -222,8 +228,8 @@ struct scvod_ctx {
   std::vector<uint64_t> hit_key;
   std::vector<LabelAcc> label_accs;
   // label refresh staging
-  DevBuf<int32_t> d_vcls;
-  PinBuf<int32_t> h_vcls;
+  DevBuf<int32_t> d_vcls, d_lov;
+  PinBuf<int32_t> h_vcls, h_lov;  // per-voxel classes; (apri position, class, scan) of the points of tainted voxels
   DevBuf<float> d_Ts;
   PinBuf<float> h_Ts;
   DevBuf<unsigned long long> d_counter;
@@ -243,7 +249,7 @@ struct scvod_ctx {
   int init_base = -1;
   bool have_init = false;
   int track_name = 0;  // SSC::name (ssc.h:49)
-  int64_t stat_track_points = 0, stat_track_pairs = 0, stat_scans = 0, stat_points = 0, stat_apri = 0, stat_voxels = 0;
+  int64_t stat_track_points = 0, stat_track_pairs = 0, stat_scans = 0, stat_points = 0, stat_apri = 0, stat_voxels = 0, stat_tvox = 0, stat_tpts = 0;
   void* gicp = nullptr;  // GICP state (scvod_gicp.cu)
   void (*gicp_free)(void*) = nullptr;
 };
@@ -394,6 +400,27 @@ static int alloc_workspace(scvod_ctx* c) {
   CU(c->d_edge_hash.alloc(S * w.hash_cap));
   CU(c->d_T.alloc(16));
   CU(c->d_counter.alloc(1));
+  CU(c->d_taint_cnt.alloc(S * kTaintCntStride));
+  CU(c->d_q_list.alloc(S * kQuirkCap));
+  CU(c->d_vox_tnt.alloc(P));
+  CU(c->d_vox_group.alloc(P));
+  CU(c->d_tv_cid.alloc(S * kTvCap));
+  CU(c->d_tv_base.alloc(S * (kTvCap + 1)));
+  CU(c->d_tp_m.alloc(S * kTpCap));
+  CU(c->d_tp_cid.alloc(S * kTpCap));
+  CU(c->d_tp_name.alloc(S * kTpCap));
+  CU(c->d_tp_xyz.alloc(S * kTpCap));
+  CU(c->h_taint_cnt.alloc(S * kTaintCntStride));
+  w.taint_cnt = c->d_taint_cnt.p;
+  w.q_list = c->d_q_list.p;
+  w.vox_tnt = c->d_vox_tnt.p;
+  w.vox_group = c->d_vox_group.p;
+  w.tv_cid = c->d_tv_cid.p;
+  w.tv_base = c->d_tv_base.p;
+  w.tp_m = c->d_tp_m.p;
+  w.tp_cid = c->d_tp_cid.p;
+  w.tp_name = c->d_tp_name.p;
+  w.tp_xyz = c->d_tp_xyz.p;
   c->name_cap = c->max_points + 8;
   CU(c->d_vox_name.alloc(P));
   CU(c->d_name_first.alloc(S * (size_t)c->name_cap));
@@ -478,9 +505,11 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_bucket_kv.release(); c->d_sorted_xyz.release(); c->d_edge_hash.release(); c->d_patch_dbg.release(); c->d_vox_bbox.release(); c->d_T.release();
   c->h_scan_counts.release(); c->h_vox_cnt.release(); c->h_vox_root.release(); c->h_vox_nbr.release(); c->h_ev_cid.release();
   c->h_edge_buf.release(); c->h_vox_bbox.release(); c->d_first.release(); c->d_triples.release();
-  c->h_treq.release(); c->h_triples.release(); c->d_treq.release(); c->d_track_ctr.release(); c->d_track_list.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release();
+  c->h_treq.release(); c->h_triples.release(); c->d_treq.release(); c->d_track_ctr.release(); c->d_track_list.release(); c->d_tout[0].release(); c->d_tout[1].release(); c->d_vcls.release(); c->h_vcls.release(); c->d_lov.release(); c->h_lov.release();
   c->d_Ts.release(); c->h_Ts.release();
   c->d_counter.release();
+  c->d_taint_cnt.release(); c->d_q_list.release(); c->d_vox_tnt.release(); c->d_vox_group.release(); c->d_tv_cid.release(); c->d_tv_base.release();
+  c->d_tp_m.release(); c->d_tp_cid.release(); c->d_tp_name.release(); c->d_tp_xyz.release(); c->h_taint_cnt.release();
   c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) {
@@ -509,6 +538,8 @@ extern "C" int scvod_get_stat(scvod_ctx* c, const char* key, int64_t* out) {
   else if (k == "points") *out = c->stat_points;
   else if (k == "apri_points") *out = c->stat_apri;
   else if (k == "voxels") *out = c->stat_voxels;
+  else if (k == "tainted_voxels") *out = c->stat_tvox;
+  else if (k == "tainted_points") *out = c->stat_tpts;
   else return fail(SCVOD_ERR_ARG, "unknown stat " + k);
   return SCVOD_OK;
 }
@@ -644,6 +675,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   c->launches += launch_cluster_prep(c->hp, w, nscans, max_n, st);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_scan_counts.p, w.scan_counts, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_taint_cnt.p, w.taint_cnt, sizeof(int32_t) * (size_t)nscans * kTaintCntStride, cudaMemcpyDeviceToHost, st));
   CU(wait_stream(c, st));
   if (g_prof.on) g_prof.add("  h2d + kernels + sync", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
   const int32_t* sc = c->h_scan_counts.p;
@@ -653,13 +685,20 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   CU(cudaMemcpyAsync(pb->off_dev.p, w.off, sizeof(int64_t) * (nscans + 1), cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(pb->scan_counts_dev.p, w.scan_counts, sizeof(int32_t) * (size_t)nscans * 8, cudaMemcpyDeviceToDevice, st));
   std::vector<int64_t> vbase(nscans + 1, 0), ebase(nscans + 1, 0), gbase(nscans + 1, 0), mbase(nscans + 1, 0), obase(nscans + 1, 0);
+  // tainted voxels (points with a -1 index, ssc.cpp:185-188): tv = voxels, tp = their points
+  const int32_t* tc = c->h_taint_cnt.p;
+  std::vector<int64_t> tvb(nscans + 1, 0), tpb(nscans + 1, 0);
+  bool any_taint = false;
   for (int s = 0; s < nscans; ++s) {
     int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
     if (G < 0 || G > w.edge_cap) return fail(SCVOD_ERR_CAPACITY, "similarity edge table overflow");
-    if (sc[s * 8 + 4] > 0)
-      return fail(SCVOD_ERR_STATE,
-                  "scan contains points whose curved-voxel index is -1 (range==min_dis, angle==0 or azimuth==min_azimuth): "
-                  "clustering of aliased voxels is not supported yet");
+    if (tc[s * kTaintCntStride + 3])
+      return fail(SCVOD_ERR_CAPACITY, "scan holds more points with a -1 curved-voxel index (or voxels / points aliased by them) than the side tables take");
+    const int ntv = tc[s * kTaintCntStride + 1], ntp = tc[s * kTaintCntStride + 2];
+    if ((int64_t)V + ntp > off[s + 1] - off[s]) return fail(SCVOD_ERR_CAPACITY, "scan too small for the replay scratch of its aliased voxels");
+    any_taint = any_taint || ntp > 0;
+    tvb[s + 1] = tvb[s] + ntv;
+    tpb[s + 1] = tpb[s] + ntp;
     vbase[s + 1] = vbase[s] + V;
     ebase[s + 1] = ebase[s] + E;
     gbase[s + 1] = gbase[s] + G;
@@ -671,22 +710,26 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   // cluster names: one warp per scan replays the reference's sequential naming on the device
   int max_vox = 1, max_ev = 1;
   for (int s = 0; s < nscans; ++s) {
-    max_vox = std::max(max_vox, sc[s * 8 + 3]);
+    max_vox = std::max(max_vox, sc[s * 8 + 3] + tc[s * kTaintCntStride + 2]);  // union-find nodes: voxels + points of tainted voxels
     max_ev = std::max(max_ev, sc[s * 8 + 5]);
   }
-  c->launches += launch_name_replay(w, nscans, max_vox, max_ev, c->replay_global, c->d_vox_name.p, c->d_name_first.p, c->name_cap, st);
+  c->launches += launch_name_replay(c->hp, w, nscans, max_vox, max_ev, c->replay_global, any_taint, c->d_vox_name.p, c->d_name_first.p, c->name_cap, st);
   CU(cudaGetLastError());
   // one packed gather + one D2H for all per-scan tables: [cnt Vt][root Vt][name Vt][bbox 6Vt][name_first Nt][edges 2Gt][max_name S]
   const int64_t Vt = vbase[nscans], Gt = gbase[nscans];
   std::vector<int64_t> nbase(nscans + 1, 0);
-  for (int s = 0; s < nscans; ++s) nbase[s + 1] = nbase[s] + std::min<int64_t>(c->name_cap, (int64_t)sc[s * 8 + 3] + 6);
+  for (int s = 0; s < nscans; ++s)
+    nbase[s + 1] = nbase[s] + std::min<int64_t>(c->name_cap, (int64_t)sc[s * 8 + 3] + tc[s * kTaintCntStride + 2] + 6);
   const int64_t Nt = nbase[nscans];
+  const int64_t TVt = tvb[nscans], TPt = tpb[nscans];
   const int64_t o_cnt = 0, o_root = Vt, o_name = 2 * Vt, o_bbox = 3 * Vt, o_nf = 9 * Vt, o_edge = 9 * Vt + Nt, o_max = 9 * Vt + Nt + 2 * Gt;
-  const int64_t pack_ints = std::max<int64_t>(1, o_max + (int64_t)nscans * 8);
+  // [tv_cid TVt][tv_base TVt + S][tp_m TPt][tp_name TPt][tp_xyz 4 TPt] after the counters (empty without tainted voxels)
+  const int64_t o_tvc = o_max + (int64_t)nscans * 8, o_tvb = o_tvc + TVt, o_tpm = o_tvb + TVt + nscans, o_tpn = o_tpm + TPt, o_tpx = o_tpn + TPt;
+  const int64_t pack_ints = std::max<int64_t>(1, o_tpx + 4 * TPt);
   CU(c->h_pack.alloc(pack_ints));
   CU(c->d_pack.alloc(pack_ints));
-  CU(c->h_desc.alloc((size_t)nscans * 6 + 1));
-  CU(c->d_desc.alloc((size_t)nscans * 6 + 1));
+  CU(c->h_desc.alloc((size_t)nscans * 11 + 1));
+  CU(c->d_desc.alloc((size_t)nscans * 11 + 1));
   int nd = 0, max_desc_n = 1;
   auto add = [&](const void* src, int64_t dst, int n) {
     if (n <= 0) return;
@@ -707,6 +750,14 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     add(w.vox_bbox + b * 6, o_bbox + vbase[s] * 6, V * 6);
     add(c->d_name_first.p + (size_t)s * c->name_cap, o_nf + nbase[s], (int)(nbase[s + 1] - nbase[s]));
     add(w.edge_buf + (size_t)s * w.edge_cap * 2, o_edge + gbase[s] * 2, G * 2);
+    const int ntv = (int)(tvb[s + 1] - tvb[s]), ntp = (int)(tpb[s + 1] - tpb[s]);
+    if (ntp > 0) {
+      add(w.tv_cid + (size_t)s * kTvCap, o_tvc + tvb[s], ntv);
+      add(w.tv_base + (size_t)s * (kTvCap + 1), o_tvb + tvb[s] + s, ntv + 1);
+      add(w.tp_m + (size_t)s * kTpCap, o_tpm + tpb[s], ntp);
+      add(w.tp_name + (size_t)s * kTpCap, o_tpn + tpb[s], ntp);
+      add(w.tp_xyz + (size_t)s * kTpCap, o_tpx + 4 * tpb[s], 4 * ntp);
+    }
   }
   add(w.scan_counts, o_max, nscans * 8);  // re-read the counters: slot 6 now holds max_name
   CU(cudaMemcpyAsync(c->d_desc.p, c->h_desc.p, sizeof(PackDesc) * nd, cudaMemcpyHostToDevice, st));
@@ -727,6 +778,14 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   const int batch_id = (int)c->batches.size();
   const size_t f0 = c->frames.size();
   c->frames.resize(f0 + nscans);
+  struct FramesGuard {  // an error below leaves no frame that points at a batch that was never committed
+    scvod_ctx* c;
+    size_t f0;
+    bool ok = false;
+    ~FramesGuard() {
+      if (!ok) c->frames.resize(f0);
+    }
+  } guard{c, f0};
   std::atomic<int> next(0);
   std::atomic<int> bad(0);
   auto worker = [&]() {
@@ -754,8 +813,20 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
       t.vox_name = hp_name + vbase[s];
       t.name_first = hp_nf + nbase[s];
       t.max_name = hp_sc2[s * 8 + 6];
-      if (t.max_name + 1 > (int)(nbase[s + 1] - nbase[s])) bad.store(1);
+      t.n_tvox = (int)(tvb[s + 1] - tvb[s]);
+      t.n_tpts = (int)(tpb[s + 1] - tpb[s]);
+      if (t.n_tpts > 0) {
+        t.tv_cid = c->h_pack.p + o_tvc + tvb[s];
+        t.tv_base = c->h_pack.p + o_tvb + tvb[s] + s;
+        t.tp_m = c->h_pack.p + o_tpm + tpb[s];
+        t.tp_name = c->h_pack.p + o_tpn + tpb[s];
+        t.tp_xyz = reinterpret_cast<const float*>(c->h_pack.p + o_tpx + 4 * tpb[s]);
+      }
       fr.vox_cnt.assign(t.vox_cnt, t.vox_cnt + t.V);
+      if (t.max_name + 1 > (int)(nbase[s + 1] - nbase[s])) {  // more names than the table holds: name_first would be read past its slice
+        bad.store(1);
+        continue;
+      }
       if (!segment_and_recognize(c->hp.p, t, fr.fc, c->inspect)) bad.store(1);
     }
   };
@@ -769,22 +840,39 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   }
   if (g_prof.on) g_prof.add("  host segment+recognize", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count());
   // car CSR of the batch (see PersistBatch::csr): the own voxels of every car cluster, in occupy_voxels order, with running
-  // point offsets and part indices; one upload per batch, so that tracking needs no per-pair segment upload
+  // point offsets and part indices; one upload per batch, so that tracking needs no per-pair segment upload.  A tainted voxel
+  // contributes only the subgroups the cluster owns, as "virtual voxels" whose points sit in the 4th section (tv_pts).
+  if (bad.load()) {  // nothing of this batch stays queryable (FramesGuard)
+    c->batch_pool.push_back(std::move(pb));
+    return fail(SCVOD_ERR_STATE, "internal: replayed cluster partition differs from the GPU components");
+  }
   {
-    size_t csr_n = 0;
-    for (int s = 0; s < nscans; ++s)
-      for (auto& cs : c->frames[f0 + s].fc.cluster_set)
-        if (cs.second.type == c->hp.p.car) csr_n += cs.second.occupy_voxels.size();
+    size_t csr_n = 0, tv_n = 0;
+    for (int s = 0; s < nscans; ++s) {
+      FrameHost& fr = c->frames[f0 + s];
+      for (auto& cs : fr.fc.cluster_set)
+        if (cs.second.type == c->hp.p.car) csr_n += cs.second.occupy_voxels.size() + cs.second.tunits.size();
+      fr.sg_tv_off.assign(fr.fc.subgroups.size(), 0);
+      for (size_t g = 0; g < fr.fc.subgroups.size(); ++g) {
+        fr.sg_tv_off[g] = (int)tv_n;
+        tv_n += fr.fc.subgroups[g].pts.size();
+      }
+    }
     csr_n += (size_t)nscans;  // one closing point offset per frame
-    CU(pb->h_csr.alloc(3 * csr_n));
-    CU(pb->csr.alloc(3 * csr_n));
+    CU(pb->h_csr.alloc(3 * csr_n + tv_n));
+    CU(pb->csr.alloc(3 * csr_n + tv_n));
     pb->csr_n = (int)csr_n;
+    pb->tv_n = (int)tv_n;
     int32_t* ptoff = pb->h_csr.p;
     int32_t* cvox = pb->h_csr.p + csr_n;
     int32_t* cpart = pb->h_csr.p + 2 * csr_n;
+    int32_t* tvp = pb->h_csr.p + 3 * csr_n;
     size_t pos = 0;
     for (int s = 0; s < nscans; ++s) {
       FrameHost& fr = c->frames[f0 + s];
+      for (size_t g = 0; g < fr.fc.subgroups.size(); ++g)
+        std::copy(fr.fc.subgroups[g].pts.begin(), fr.fc.subgroups[g].pts.end(), tvp + fr.sg_tv_off[g]);
+      const bool taint = !fr.fc.tvox.empty();
       fr.csr_base = (int)pos;
       int run_pts = 0;
       for (auto& cs : fr.fc.cluster_set) {
@@ -793,19 +881,27 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
         if (cl.type != c->hp.p.car) continue;
         HCluster::OwnRun orun;
         orun.csr_start = (int)(pos - fr.csr_base);
-        orun.csr_len = (int)cl.occupy_voxels.size();
         orun.part_base = 0;
         const int pts0 = run_pts;
         int part = 0, vi = 0;
         for (int v : cl.occupy_voxels) {
           while (part < (int)cl.part_end.size() && vi >= cl.part_end[part]) ++part;
           ++vi;
+          if (taint && fr.fc.tainted(v)) continue;
           ptoff[pos] = run_pts;
           cvox[pos] = v;
           cpart[pos] = part;
           run_pts += std::max(0, fr.vox_cnt[v]);
           ++pos;
         }
+        for (auto& tu : cl.tunits) {
+          ptoff[pos] = run_pts;
+          cvox[pos] = kVirtualVox | fr.sg_tv_off[tu.sg];
+          cpart[pos] = tu.part;
+          run_pts += (int)fr.fc.subgroups[tu.sg].pts.size();
+          ++pos;
+        }
+        orun.csr_len = (int)(pos - fr.csr_base) - orun.csr_start;
         orun.npts = run_pts - pts0;
         cl.own_runs.push_back(orun);
       }
@@ -814,14 +910,16 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
       cpart[pos] = 0;
       ++pos;
     }
-    CU(cudaMemcpyAsync(pb->csr.p, pb->h_csr.p, sizeof(int32_t) * 3 * csr_n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pb->csr.p, pb->h_csr.p, sizeof(int32_t) * (3 * csr_n + tv_n), cudaMemcpyHostToDevice, st));
   }
   c->stat_scans += nscans;
   c->stat_points += total;
   c->stat_apri += mbase[nscans];
   c->stat_voxels += vbase[nscans];
+  c->stat_tvox += TVt;
+  c->stat_tpts += TPt;
   c->batches.push_back(std::move(pb));
-  if (bad.load()) return fail(SCVOD_ERR_STATE, "internal: replayed cluster partition differs from the GPU components");
+  guard.ok = true;
   return SCVOD_OK;
 }
 
@@ -962,7 +1060,8 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
   } else {
     // ---- ... or one uploaded segment per voxel (clusters without runs: scvod_initialization; more runs than fit) ----
     size_t n_seg = 0;
-    for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size();
+    for (HCluster* cl : cars) n_seg += cl->occupy_voxels.size() + cl->carried.size() + cl->tunits.size();
+    const bool taint = !pre.fc.tvox.empty();
     size_t k_bound = 0;  // upper bound of the number of points (the per-block index follows the segment table)
     for (HCluster* cl : cars) k_bound += (size_t)std::max(0, cl->npts) + (size_t)std::max(0, cl->n_carried);
     CU(c->h_treq.alloc(std::max<size_t>(4, n_seg * 4) + k_bound / 256 + 2));
@@ -976,13 +1075,21 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
         while (part < (int)cl.part_end.size() && vi >= cl.part_end[part]) ++part;
         ++vi;
         int cnt = pre.vox_cnt[v];
-        if (cnt <= 0) continue;
+        if (cnt <= 0 || (taint && pre.fc.tainted(v))) continue;  // of a tainted voxel only the owned subgroups: below
         seg[4 * si] = (int)k;
         seg[4 * si + 1] = v;
         seg[4 * si + 2] = (int)i;
         seg[4 * si + 3] = part;
         ++si;
         k += cnt;
+      }
+      for (auto& tu : cl.tunits) {
+        seg[4 * si] = (int)k;
+        seg[4 * si + 1] = kVirtualVox | pre.sg_tv_off[tu.sg];
+        seg[4 * si + 2] = (int)i;
+        seg[4 * si + 3] = tu.part;
+        ++si;
+        k += pre.fc.subgroups[tu.sg].pts.size();
       }
       int ord = 0x40000000;
       for (auto& cr : cl.carried) {
@@ -1042,7 +1149,8 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
     c->hp.track_ctas_per_sm = g_live_contexts.load() <= 2 ? 16 : g_live_contexts.load() <= 6 ? 4 : 1;
     c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                 use_runs ? nullptr : reinterpret_cast<const int4*>(c->d_treq.p), use_runs ? nullptr : c->d_treq.p + si * 4,
-                                (int)si, use_runs ? &runs : nullptr, pbp.csr.p, pbp.csr.p + pbp.csr_n, pbp.csr.p + 2 * pbp.csr_n, (int)K, T,
+                                (int)si, use_runs ? &runs : nullptr, pbp.csr.p, pbp.csr.p + pbp.csr_n, pbp.csr.p + 2 * pbp.csr_n,
+                                pbp.csr.p + 3 * (size_t)pbp.csr_n, (int)K, T,
                                 pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl, vn,
                                 c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads, c->stream);
     CU(cudaGetLastError());
@@ -1191,14 +1299,28 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
           for (int v : cluster_new.occupy_voxels) {  // reduceVec (utility.h:445-450)
             src.occupy_voxels.erase(std::remove(src.occupy_voxels.begin(), src.occupy_voxels.end(), v), src.occupy_voxels.end());
           }
-          int np = 0;
+          int np = 0, lost = 0;  // points the new cluster gets (whole voxels, :1367) / points the old one loses (reduceVec, :1370)
           for (int v : it->second) {
             nlabel[v] = cluster_new.name;
             np += next.vox_cnt[v];
+            const std::vector<int>* sgs = next.fc.subgroups_of(v);
+            if (!sgs) {
+              lost += next.vox_cnt[v];
+            } else {  // a tainted voxel: every subgroup goes to the new cluster, the old one loses those it owned
+              for (int g : *sgs) cluster_new.tunits.push_back(HCluster::TUnit{g, (int)cluster_new.part_end.size()});
+              for (size_t u = 0; u < src.tunits.size();) {
+                if (next.fc.subgroups[src.tunits[u].sg].vox == v) {
+                  lost += (int)next.fc.subgroups[src.tunits[u].sg].pts.size();
+                  src.tunits.erase(src.tunits.begin() + u);
+                } else {
+                  ++u;
+                }
+              }
+            }
             cluster_new.part_end.push_back((int)cluster_new.part_end.size() + 1);  // one voxel per part: ptIdx order (ssc.cpp:1367)
           }
           cluster_new.npts = np;
-          src.npts -= np;
+          src.npts -= lost;
           src.part_end.clear();  // point order of a split non-car cluster is never read again
           src.part_end.push_back((int)src.occupy_voxels.size());
           nset.insert(std::make_pair(cluster_new.name, cluster_new));
@@ -1233,6 +1355,7 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
             orun.part_base += base_parts;
             cluster_new.own_runs.push_back(orun);
           }
+          for (auto tu : src.tunits) cluster_new.tunits.push_back(HCluster::TUnit{tu.sg, base_parts + tu.part});
           cluster_new.npts += src.npts;
           nset.erase(re.first);
         }
@@ -1294,11 +1417,9 @@ extern "C" int scvod_initialization(scvod_ctx* c, const float* poses6, int npose
       std::unordered_map<int, std::vector<int>> remap_name;
       build_remap(c, ci, fb.vox_label, remap_name);
       if (remap_name.size() <= 1) continue;
-      HCluster fusion;  // name stays -1 when no label passes the occupancy test (utility.h:154)
-      for (int d = 0; d < 3; ++d) {
-        fusion.bb_min[d] = 3.402823466e38f;
-        fusion.bb_max[d] = -3.402823466e38f;
-      }
+      // name stays -1 when no label passes the occupancy test (utility.h:154).  bounding_box is never recomputed for the fused
+      // cluster (:1208-1241): it keeps the zeros of a default pcl::PointXYZI pair, which is what recognize(frame_based) then reads
+      HCluster fusion;
       std::vector<int> erase_id;
       for (auto& re : remap_name) {
         HCluster& src = fb.cluster_set[re.first];
@@ -1307,12 +1428,10 @@ extern "C" int scvod_initialization(scvod_ctx* c, const float* poses6, int npose
           fusion.name = re.first;
           const int basev = (int)fusion.occupy_voxels.size();
           fusion.occupy_voxels.insert(fusion.occupy_voxels.end(), src.occupy_voxels.begin(), src.occupy_voxels.end());
+          const int base_parts = (int)fusion.part_end.size();
           for (int pe : src.part_end) fusion.part_end.push_back(basev + pe);
+          for (auto tu : src.tunits) fusion.tunits.push_back(HCluster::TUnit{tu.sg, base_parts + tu.part});
           fusion.npts += src.npts;
-          for (int d = 0; d < 3; ++d) {  // bounding box of the concatenated clouds (getMinMax3D is exact)
-            fusion.bb_min[d] = std::min(fusion.bb_min[d], src.bb_min[d]);
-            fusion.bb_max[d] = std::max(fusion.bb_max[d], src.bb_max[d]);
-          }
         }
       }
       for (int e : erase_id) fb.cluster_set.erase(e);
@@ -1361,7 +1480,39 @@ static int refresh_batch_labels(scvod_ctx* c, int batch) {
   c->launches += launch_final_labels(pb.off_dev.p, pb.scan_counts_dev.p, pb.nscans, pb.max_n, pb.apri_src.p, pb.apri_cid.p, c->d_vcls.p,
                                      reinterpret_cast<const uint8_t*>(c->d_vcls.p + pb.nscans), pb.cls.p, c->stream);
   CU(cudaGetLastError());
-  CU(wait_stream(c, c->stream));  // the staging buffer is reused by the next batch
+  // Points of tainted voxels follow the cluster that owns them, not their voxel: the subgroup's class is that of the LAST
+  // cluster (cluster_set order, as the per-cluster emission of saveSegCloud, ssc.cpp:477-545) that lists it.
+  {
+    size_t nit = 0;
+    for (FrameHost* fr : frs)
+      if (fr)
+        for (auto& g : fr->fc.subgroups) nit += g.pts.size();
+    if (nit > 0) {
+      CU(c->h_lov.alloc(3 * nit));
+      CU(c->d_lov.alloc(3 * nit));
+      int32_t* items = c->h_lov.p;
+      int32_t* iscan = c->h_lov.p + 2 * nit;
+      size_t k = 0;
+      for (int s = 0; s < pb.nscans; ++s) {
+        FrameHost* fr = frs[s];
+        if (!fr || fr->fc.subgroups.empty()) continue;
+        std::vector<uint8_t> sg_cls(fr->fc.subgroups.size(), (uint8_t)SCVOD_PT_UNCLUSTERED);
+        for (auto& cs : fr->fc.cluster_set)
+          for (auto& tu : cs.second.tunits) sg_cls[tu.sg] = (cs.second.state == 1) ? SCVOD_PT_DYNAMIC : SCVOD_PT_STATIC;
+        for (size_t g = 0; g < fr->fc.subgroups.size(); ++g)
+          for (int m : fr->fc.subgroups[g].pts) {
+            items[2 * k] = (int32_t)(fr->base + m);
+            items[2 * k + 1] = sg_cls[g];
+            iscan[k] = s;
+            ++k;
+          }
+      }
+      CU(cudaMemcpyAsync(c->d_lov.p, c->h_lov.p, sizeof(int32_t) * 3 * nit, cudaMemcpyHostToDevice, c->stream));
+      c->launches += launch_label_override(c->d_lov.p, c->d_lov.p + 2 * nit, (int)nit, pb.apri_src.p, pb.off_dev.p, pb.cls.p, c->stream);
+      CU(cudaGetLastError());
+    }
+  }
+  CU(wait_stream(c, c->stream));  // the staging buffers are reused by the next batch
   pb.labels_current = true;
   return SCVOD_OK;
 }
@@ -1525,6 +1676,8 @@ extern "C" int scvod_frame_point_cluster(scvod_ctx* c, int frame, int stage, int
   if (rc) return rc;
   CU(cudaStreamSynchronize(c->stream));
   for (int m = 0; m < fr.n_apri; ++m) name[m] = cid[m] >= 0 ? fr.fc.vox_name_stage[stage][cid[m]] : -1;
+  for (auto& g : fr.fc.subgroups)  // points of tainted voxels: the cluster of the point, not of the voxel
+    for (int m : g.pts) name[m] = g.stage_name[stage];
   return SCVOD_OK;
 }
 
@@ -1663,11 +1816,13 @@ extern "C" int scvod_atan2f_device(scvod_ctx* c, const float* y, const float* x,
 // Host-only hook: the cluster bookkeeping (host_cluster.cpp) on caller-provided voxel tables, without a
 // GPU.  Used by the CPU test-suite to check the name replay / fusion / bounding-box / car logic against
 // the oracle; the product pipeline calls segment_and_recognize() directly with GPU-produced tables.
-extern "C" int scvod_host_segment(const scvod_params* p, int V, const int32_t* vox_cnt, const int32_t* vox_root, const int32_t* vox_nbr,
-                                  const float* vox_bbox, int n_events, const int32_t* ev_cid, int n_edges, const int32_t* edges,
-                                  int32_t* name_stage0, int32_t* name_stage1, int32_t* name_stage2, int32_t n_clusters[3], int cap,
-                                  int32_t* cluster_name, int32_t* cluster_type, int32_t* max_name) {
-  if (!p || V < 0) return fail(SCVOD_ERR_ARG, "bad arguments");
+extern "C" int scvod_host_segment_pts(const scvod_params* p, int V, const int32_t* vox_cnt, const int32_t* vox_root, const int32_t* vox_nbr,
+                                      const float* vox_bbox, int n_events, const int32_t* ev_cid, int n_edges, const int32_t* edges, int n_tvox,
+                                      const int32_t* tv_cid, const int32_t* tv_base, int n_tpts, const int32_t* tp_m, const float* tp_xyz,
+                                      const int32_t* tp_nbr, int32_t* name_stage0, int32_t* name_stage1, int32_t* name_stage2,
+                                      int32_t* tp_stage, int32_t n_clusters[3], int cap, int32_t* cluster_name, int32_t* cluster_type,
+                                      int32_t* cluster_npts, int32_t* cluster_nvox, int32_t* max_name) {
+  if (!p || V < 0 || n_tvox < 0 || n_tpts < 0) return fail(SCVOD_ERR_ARG, "bad arguments");
   ScanTables t;
   t.V = V;
   t.n_events = n_events;
@@ -1678,11 +1833,25 @@ extern "C" int scvod_host_segment(const scvod_params* p, int V, const int32_t* v
   t.vox_bbox = vox_bbox;
   t.ev_cid = ev_cid;
   t.edges = edges;
+  t.n_tvox = n_tvox;
+  t.n_tpts = n_tpts;
+  t.tv_cid = tv_cid;
+  t.tv_base = tv_base;
+  t.tp_m = tp_m;
+  t.tp_xyz = tp_xyz;
+  t.tp_nbr = tp_nbr;
   FrameClusters fc;
   if (!segment_and_recognize(*p, t, fc, true)) return fail(SCVOD_ERR_STATE, "replayed partition differs from the given components");
   if (name_stage0) std::memcpy(name_stage0, fc.vox_name_stage[0].data(), sizeof(int32_t) * V);
   if (name_stage1) std::memcpy(name_stage1, fc.vox_name_stage[1].data(), sizeof(int32_t) * V);
   if (name_stage2) std::memcpy(name_stage2, fc.vox_name_stage[2].data(), sizeof(int32_t) * V);
+  if (tp_stage && n_tpts > 0) {  // [3][n_tpts]: cluster of every point of a tainted voxel after the three stages
+    std::unordered_map<int, int> pos_of_m;
+    for (int q = 0; q < n_tpts; ++q) pos_of_m[tp_m[q]] = q;
+    for (auto& g : fc.subgroups)
+      for (int m : g.pts)
+        for (int st = 0; st < 3; ++st) tp_stage[(size_t)st * n_tpts + pos_of_m[m]] = g.stage_name[st];
+  }
   if (n_clusters)
     for (int i = 0; i < 3; ++i) n_clusters[i] = fc.n_clusters[i];
   if (max_name) *max_name = fc.max_name;
@@ -1691,7 +1860,18 @@ extern "C" int scvod_host_segment(const scvod_params* p, int V, const int32_t* v
     if (i >= cap) break;
     if (cluster_name) cluster_name[i] = cs.first;
     if (cluster_type) cluster_type[i] = cs.second.type;
+    if (cluster_npts) cluster_npts[i] = cs.second.npts;
+    if (cluster_nvox) cluster_nvox[i] = (int)cs.second.occupy_voxels.size();
     ++i;
   }
   return (int)fc.cluster_set.size();
+}
+
+extern "C" int scvod_host_segment(const scvod_params* p, int V, const int32_t* vox_cnt, const int32_t* vox_root, const int32_t* vox_nbr,
+                                  const float* vox_bbox, int n_events, const int32_t* ev_cid, int n_edges, const int32_t* edges,
+                                  int32_t* name_stage0, int32_t* name_stage1, int32_t* name_stage2, int32_t n_clusters[3], int cap,
+                                  int32_t* cluster_name, int32_t* cluster_type, int32_t* max_name) {
+  return scvod_host_segment_pts(p, V, vox_cnt, vox_root, vox_nbr, vox_bbox, n_events, ev_cid, n_edges, edges, 0, nullptr, nullptr, 0, nullptr,
+                                nullptr, nullptr, name_stage0, name_stage1, name_stage2, nullptr, n_clusters, cap, cluster_name, cluster_type,
+                                nullptr, nullptr, max_name);
 }

@@ -805,6 +805,7 @@ __global__ void __launch_bounds__(kChainWarps * 32) k_patch_chain(FitArgs a, int
 constexpr uint32_t F_G = 1u;      // final ground set
 constexpr uint32_t F_PASS = 2u;   // survives the SSC gates
 constexpr uint32_t F_QUIRK = 4u;  // some index is -1 (aliasing quirk, SURVEY.md hard part 7)
+constexpr int kAposQuirk = 1 << 30;
 
 // slot_pos encoding: role << 30 | in-ground-set << 29 | rank inside its class (ground set / complement);
 // slot_apos: rank among the gate-passing points of the same class, or -1.  k_emit turns them into positions with
@@ -861,7 +862,7 @@ __device__ __forceinline__ void rank_one_patch(const FitArgs& a, int p, int b, i
         role = 0;
       } else {
         role = ps ? 2 : 1;
-        if (ps) apos = g ? rGP : rNP;
+        if (ps) apos = (g ? rGP : rNP) | ((f & F_QUIRK) ? kAposQuirk : 0);  // the -1-index flag rides along to k_emit
       }
       a.slot_pos[base + slot0 + j] = (role << 30) | (g ? (1 << 29) : 0) | (g ? rG : rN);
       a.slot_apos[base + slot0 + j] = apos;
@@ -949,7 +950,8 @@ __global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ pts, co
                                               const int32_t* __restrict__ slot_vid, const int16_t* __restrict__ slot_patch,
                                               int32_t* __restrict__ ground_src, int32_t* __restrict__ ng_src,
                                               int32_t* __restrict__ apri_src, int32_t* __restrict__ apri_vid,
-                                              float4* __restrict__ apri_xyzi, uint8_t* __restrict__ cls) {
+                                              float4* __restrict__ apri_xyzi, uint8_t* __restrict__ cls,
+                                              int32_t* __restrict__ taint_cnt, int32_t* __restrict__ q_list) {
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int nslots = patch_off[b * (kNumPatches + 1) + kNumPatches];
@@ -975,8 +977,13 @@ __global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ pts, co
       if (role == 1) {
         cls[base + idx] = SCVOD_PT_GATED_OUT;
       } else {
-        const int ar = slot_apos[base + q];
+        const int ar_raw = slot_apos[base + q];
+        const int ar = ar_raw & (kAposQuirk - 1);
         const int m = o[2] + ((rejected && !g) ? po[5] + ar : ar);
+        if (ar_raw & kAposQuirk) {  // a point with a -1 index: its voxel will be named point by point (k_taint_*)
+          const int k = atomicAdd(&taint_cnt[b * kTaintCntStride], 1);
+          if (k < kQuirkCap) q_list[(size_t)b * kQuirkCap + k] = m;
+        }
         apri_src[base + m] = idx;
         apri_vid[base + m] = slot_vid[base + q];
         apri_xyzi[base + m] = __ldg(&pts[base + idx]);
@@ -1017,6 +1024,7 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   int launches = 0;
   cudaMemsetAsync(d.patch_cnt, 0, sizeof(int32_t) * (size_t)nscans * kNumPatches, st);
   cudaMemsetAsync(d.sort_ctr, 0, sizeof(int32_t) * 8, st);
+  cudaMemsetAsync(d.taint_cnt, 0, sizeof(int32_t) * (size_t)nscans * kTaintCntStride, st);
   dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
   { TIMED("k_patch_assign", TSTREAM); k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, d.patch_cnt, d.cls); }
   { TIMED("k_patch_scan", TSTREAM); k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur, d.sort_ctr, d.sort_list, d.cap_scans * kNumPatches); }
@@ -1076,7 +1084,7 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   launches += 2;
   { TIMED("k_patch_out_scan", TSTREAM); k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts); }
   { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
-                             d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls); }
+                             d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls, d.taint_cnt, d.q_list); }
   launches += 5;
   return launches;
 }

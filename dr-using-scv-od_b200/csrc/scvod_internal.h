@@ -14,6 +14,14 @@ constexpr int kNumZones = 4;
 constexpr int kNumPatches = 504;  // 2*16 + 4*32 + 4*54 + 4*32
 constexpr int kMinPatchPts = 10;  // num_min_pts_: patches need > 10 points (patchwork.h:331)
 
+// Tainted voxels (a point with a -1 index hashes into a voxel that is not its own cell, ssc.cpp:185-188): per-scan capacities of
+// the side tables that name such voxels point by point.  taint_cnt[scan][4] = {quirk points listed, tainted voxels, their points, error}
+constexpr int kQuirkCap = 4096;   // points with a -1 index per scan
+constexpr int kTvCap = 2048;      // tainted voxels per scan
+constexpr int kTpCap = 16384;     // points of tainted voxels per scan
+constexpr int kTaintCntStride = 4;
+constexpr int kVirtualVox = 0x40000000;  // car CSR / tracking segments: "voxel" is a subgroup of a tainted voxel, points at tv_pts + (id & ~flag)
+
 struct GridSpec {
   int range_num, sector_num, azimuth_num, bin_num;
   int key_off;    // voxel_idx + key_off >= 0 for every reachable (aliased) index, ssc.cpp:185-188
@@ -77,6 +85,17 @@ struct BatchDev {
   int32_t* edge_buf = nullptr;  // [scans][edge_cap][2] directed similar-intensity component edges (roots)
   int32_t* edge_hash = nullptr; // [scans][hash_cap] dedupe table
   int edge_cap = 0, hash_cap = 0;
+  // tainted voxels (see kQuirkCap)
+  int32_t* taint_cnt = nullptr;  // [scans][kTaintCntStride]
+  int32_t* q_list = nullptr;     // [scans][kQuirkCap] apri index of the points with a -1 index (unordered)
+  int32_t* vox_tnt = nullptr;    // per voxel: -1 ordinary, -3 ordinary with a tainted voxel among its 27 neighbours, >= 0 tainted: offset of its points in tp_*
+  int32_t* vox_group = nullptr;  // per voxel: components of the voxel graph INCLUDING the links through tainted voxels (replay work partition)
+  int32_t* tv_cid = nullptr;     // [scans][kTvCap] tainted voxels, ascending compact id
+  int32_t* tv_base = nullptr;    // [scans][kTvCap + 1]
+  int32_t* tp_m = nullptr;       // [scans][kTpCap] apri index of every point of a tainted voxel (voxel-major, ascending m)
+  int32_t* tp_cid = nullptr;     // [scans][kTpCap] compact id of the point's voxel
+  float4* tp_xyz = nullptr;      // [scans][kTpCap]
+  int32_t* tp_name = nullptr;    // [scans][kTpCap] cluster name of the point (k_name_replay)
 };
 
 struct PackDesc {
@@ -115,17 +134,21 @@ struct TrackRuns {
 // {dst_off, source (>=0 voxel of frame_pre_ / <0 carried range), cluster, order} and first_seg[b] = segment holding point 256*b
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
                  const int4* segs, const int32_t* first_seg, int nseg, const TrackRuns* runs, const int32_t* csr_ptoff, const int32_t* csr_vox,
-                 const int32_t* csr_part, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
+                 const int32_t* csr_part, const int32_t* tv_pts, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
                  int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
                  int cap_quads, void* stream);
 int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nscans, int max_scan_points, const int32_t* apri_src,
                         const int32_t* apri_cid, const int32_t* vcls_off, const uint8_t* vcls, uint8_t* cls, void* stream);
+// classes of the points of tainted voxels: items = (batch-global apri position, class), item_scan = slot of the point's scan
+int launch_label_override(const int32_t* items_dev, const int32_t* item_scan_dev, int n, const int32_t* apri_src, const int64_t* off, uint8_t* cls,
+                          void* stream);
 int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,
                   int max_scan_points, float4* out, unsigned long long* counter, long long cap, void* stream);
 // cluster-name replay (one CTA per scan, components dealt to its warps); vox_name is indexed like the voxel arrays,
 // name_first is [nscans][name_cap]
-int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, bool force_global, int32_t* vox_name, int32_t* name_first, int name_cap,
-                       void* stream);
+// max_nodes = max over the scans of voxels + points of tainted voxels; any_taint: some scan has tainted voxels
+int launch_name_replay(const HostParams& hp, BatchDev& d, int nscans, int max_nodes, int max_events, bool force_global, bool any_taint,
+                       int32_t* vox_name, int32_t* name_first, int name_cap, void* stream);
 int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
 

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
                                                const int32_t* __restrict__ first_seg /* per block of 256 points */,
                                                int nseg, const __grid_constant__ TrackRuns runs, const int32_t* __restrict__ csr_ptoff,
                                                const int32_t* __restrict__ csr_vox, const int32_t* __restrict__ csr_part,
+                                               const int32_t* __restrict__ tv_pts /* apri indices of the subgroups of tainted voxels */,
                                                int k, Mat34 T, BinParams bp, GridSpec g,
                                                const uint32_t* __restrict__ bm, const int32_t* __restrict__ wr, int vn,
                                                float4* __restrict__ out_xyzi, unsigned long long* __restrict__ first,
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(256) k_track(const float4* __restrict__ own, c
     float4 p;
     unsigned low;
     if (sg.y >= 0) {
-      int m = vox_pts[vox_off[sg.y] + j];
+      // a whole voxel of the frame's CSR, or (kVirtualVox) the points one cluster owns of a tainted voxel
+      const int m = (sg.y & kVirtualVox) ? tv_pts[(sg.y & (kVirtualVox - 1)) + j] : vox_pts[vox_off[sg.y] + j];
       p = __ldg(&own[m]);
       low = (unsigned)m;  // inside a part the reference's cloud is in ascending apri index (ssc.cpp:360-380)
     } else {
@@ -199,6 +201,16 @@ __global__ void __launch_bounds__(256) k_final_labels(const int64_t* __restrict_
   }
 }
 
+// points of tainted voxels: their class follows the cluster that owns the point, not the voxel (items = batch-global apri position, class)
+__global__ void __launch_bounds__(256) k_label_override(const int2* __restrict__ items, int n, const int32_t* __restrict__ apri_src,
+                                                        const int64_t* __restrict__ off, const int32_t* __restrict__ item_scan,
+                                                        uint8_t* __restrict__ cls) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 it = items[i];
+    cls[off[item_scan[i]] + apri_src[it.x]] = (uint8_t)it.y;
+  }
+}
+
 // static submap: every non-dynamic point of the frames of a batch moved to the map frame (transformCloud arithmetic
 // with the frame's pose).  A CTA owns a contiguous chunk of a scan and every warp a contiguous part of it: the static
 // points are counted first (1 B / point), the CTA reserves its output range with ONE atomic on the global counter,
@@ -277,7 +289,7 @@ int launch_bin_only(const HostParams& hp, const float4* pts_dev, int n, uint8_t*
 
 int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vox_off, const int32_t* vox_pts, const float4* carried,
                  const int4* segs, const int32_t* first_seg, int nseg, const TrackRuns* runs, const int32_t* csr_ptoff, const int32_t* csr_vox,
-                 const int32_t* csr_part, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
+                 const int32_t* csr_part, const int32_t* tv_pts, int k, const float T12[12], const uint32_t* next_bitmap, const int32_t* next_word_rank, int ncl,
                  int vn, float4* out_xyzi, unsigned long long* first, int32_t* ctr_dev, int32_t* hit_list_dev, int32_t* out_quads_mapped,
                  int cap_quads, void* stream_) {
   if (k <= 0 || ncl <= 0 || vn <= 0) return 0;
@@ -291,13 +303,13 @@ int launch_track(const HostParams& hp, const float4* own_xyzi, const int32_t* vo
   if (blocks > cap) blocks = cap;
   if (runs) {
     TIMED("k_track", TSTREAM);
-    k_track<true><<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, nullptr, nullptr, 0, *runs, csr_ptoff, csr_vox, csr_part, k, T,
+    k_track<true><<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, nullptr, nullptr, 0, *runs, csr_ptoff, csr_vox, csr_part, tv_pts, k, T,
                                            make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev,
                                            out_quads_mapped, cap_quads);
   } else {
     static const TrackRuns none = {};
     TIMED("k_track_segs", TSTREAM);
-    k_track<false><<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, first_seg, nseg, none, nullptr, nullptr, nullptr, k, T,
+    k_track<false><<<blocks, 256, 0, st>>>(own_xyzi, vox_off, vox_pts, carried, segs, first_seg, nseg, none, nullptr, nullptr, nullptr, tv_pts, k, T,
                                             make_bin_params(hp), hp.g, next_bitmap, next_word_rank, vn, out_xyzi, first, ctr_dev, hit_list_dev,
                                             out_quads_mapped, cap_quads);
   }
@@ -309,6 +321,13 @@ int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nsca
   if (nscans <= 0) return 0;
   dim3 grid(grid_x_for(nscans, max_scan_points, 256), nscans);
   { TIMED("k_final_labels", TSTREAM); k_final_labels<<<grid, 256, 0, (cudaStream_t)stream_>>>(off, scan_counts, apri_src, apri_cid, vcls_off, vcls, cls); }
+  return 1;
+}
+
+int launch_label_override(const int32_t* items_dev /* [n][2] */, const int32_t* item_scan_dev, int n, const int32_t* apri_src, const int64_t* off,
+                          uint8_t* cls, void* stream_) {
+  if (n <= 0) return 0;
+  { TIMED("k_label_override", TSTREAM); k_label_override<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(reinterpret_cast<const int2*>(items_dev), n, apri_src, off, item_scan_dev, cls); }
   return 1;
 }
 

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256) k_vox_mark(const int64_t* __restrict__ of
 
 __global__ void __launch_bounds__(1024) k_vox_rank(const int64_t* __restrict__ off, GridSpec g, const uint32_t* __restrict__ bitmap,
                                                    int32_t* __restrict__ word_rank, int32_t* __restrict__ vox_vid,
-                                                   int32_t* __restrict__ vox_cnt, int32_t* __restrict__ scan_counts) {
+                                                   int32_t* __restrict__ vox_cnt, int32_t* __restrict__ vox_tnt,
+                                                   int32_t* __restrict__ scan_counts) {
   __shared__ int s_w[33];
   const int b = blockIdx.x;
   const int64_t base = off[b];
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(1024) k_vox_rank(const int64_t* __restrict__ o
       bits &= bits - 1;
       vox_vid[base + ex] = (w << 5) + bit - g.key_off;
       vox_cnt[base + ex] = 0;
+      vox_tnt[base + ex] = -1;
       ++ex;
     }
   }
@@ -212,6 +214,114 @@ __global__ void __launch_bounds__(256) k_vox_center(const int64_t* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tainted voxels.  A point whose range / sector / azimuth index is -1 (dis == min_dis, angle == min_angle i.e. y == 0 with
+// x > 0, azimuth == min_azimuth; ssc.cpp:185-188) hashes into a voxel that is not its own cell: the voxel's points then
+// no longer share one neighbour list, and clusterAndCreateFrame (ssc.cpp:299-352) has to be replayed point by point for
+// them.  These kernels build the (tiny) side tables: the tainted voxels of a scan in ascending compact id and their
+// points in ptIdx order.  Scans without such points leave after one load.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_taint_mark(const int64_t* __restrict__ off, const int32_t* __restrict__ taint_cnt,
+                                                    const int32_t* __restrict__ q_list, const int32_t* __restrict__ apri_cid,
+                                                    int32_t* __restrict__ vox_tnt) {
+  const int b = blockIdx.x;
+  const int nq = min(taint_cnt[b * kTaintCntStride], kQuirkCap);
+  if (nq == 0) return;
+  const int64_t base = off[b];
+  for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+    const int cid = apri_cid[base + q_list[(size_t)b * kQuirkCap + k]];
+    if (cid >= 0) vox_tnt[base + cid] = -2;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_taint_build(const int64_t* __restrict__ off, int32_t* __restrict__ taint_cnt,
+                                                      const int32_t* __restrict__ q_list, const int32_t* __restrict__ apri_cid,
+                                                      const int32_t* __restrict__ vox_cnt, const int32_t* __restrict__ vox_off,
+                                                      const int32_t* __restrict__ vox_pts, const float4* __restrict__ apri_xyzi,
+                                                      int32_t* __restrict__ vox_tnt, int32_t* __restrict__ tv_cid,
+                                                      int32_t* __restrict__ tv_base, int32_t* __restrict__ tp_m,
+                                                      int32_t* __restrict__ tp_cid, float4* __restrict__ tp_xyz) {
+  __shared__ int s_cid[kTvCap];
+  __shared__ int s_base[kTvCap + 1];
+  __shared__ int s_w[33];
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  const int nq_all = taint_cnt[b * kTaintCntStride];
+  if (nq_all == 0) return;
+  const int64_t base = off[b];
+  const int tid = threadIdx.x;
+  const int nq = min(nq_all, kQuirkCap);
+  if (tid == 0) s_n = 0;
+  for (int i = tid; i < kTvCap; i += 1024) s_cid[i] = 0x7fffffff;
+  __syncthreads();
+  bool overflow = nq_all > kQuirkCap;
+  for (int k = tid; k < nq; k += 1024) {
+    const int cid = apri_cid[base + q_list[(size_t)b * kQuirkCap + k]];
+    if (cid >= 0 && atomicCAS(&vox_tnt[base + cid], -2, -4) == -2) {  // first quirk point of this voxel
+      const int slot = atomicAdd(&s_n, 1);
+      if (slot < kTvCap) s_cid[slot] = cid;
+    }
+  }
+  __syncthreads();
+  const int ntv = min(s_n, kTvCap);
+  if (s_n > kTvCap) overflow = true;
+  // ascending compact id (bitonic network over the padded table)
+  for (int k = 2; k <= kTvCap; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < kTvCap; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int x = s_cid[i], y = s_cid[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            s_cid[i] = y;
+            s_cid[l] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  int carry = 0;
+  for (int i0 = 0; i0 < ntv; i0 += 1024) {
+    const int i = i0 + tid;
+    const int c = (i < ntv) ? vox_cnt[base + s_cid[i]] : 0;
+    int total;
+    const int ex = block_excl_scan<1024>(c, &total, s_w);
+    if (i < ntv) s_base[i] = carry + ex;
+    carry += total;
+  }
+  if (tid == 0) s_base[ntv] = carry;
+  __syncthreads();
+  const int T = carry;
+  if (T > kTpCap) overflow = true;
+  if (!overflow) {
+    for (int i = tid; i < ntv; i += 1024) {
+      tv_cid[(size_t)b * kTvCap + i] = s_cid[i];
+      tv_base[(size_t)b * (kTvCap + 1) + i] = s_base[i];
+      vox_tnt[base + s_cid[i]] = s_base[i];
+    }
+    if (tid == 0) tv_base[(size_t)b * (kTvCap + 1) + ntv] = T;
+    // points, voxel-major in ptIdx (ascending apri index) order: a warp per voxel
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int i = wid; i < ntv; i += 32) {
+      const int cid = s_cid[i], o = vox_off[base + cid], n = s_base[i + 1] - s_base[i];
+      for (int j = lane; j < n; j += 32) {
+        const int m = vox_pts[base + o + j];
+        const size_t dst = (size_t)b * kTpCap + s_base[i] + j;
+        tp_m[dst] = m;
+        tp_cid[dst] = cid;
+        tp_xyz[dst] = apri_xyzi[base + m];
+      }
+    }
+  }
+  if (tid == 0) {
+    taint_cnt[b * kTaintCntStride + 1] = overflow ? 0 : ntv;
+    taint_cnt[b * kTaintCntStride + 2] = overflow ? 0 : T;
+    taint_cnt[b * kTaintCntStride + 3] = overflow ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Cluster preparation: 27-neighbour adjacency in findVoxelNeighbors order (ssc.cpp:395-411), GPU
 // connected components, intensity-similarity edges between components (ssc.cpp:587-595), and the
@@ -221,12 +331,14 @@ __global__ void __launch_bounds__(256) k_vox_center(const int64_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_vox_nbr(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts, GridSpec g,
                                                  const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
                                                  const int32_t* __restrict__ vox_tri, int32_t* __restrict__ vox_nbr,
-                                                 int32_t* __restrict__ vox_root) {
+                                                 int32_t* __restrict__ vox_root, const int32_t* __restrict__ taint_cnt,
+                                                 int32_t* __restrict__ vox_tnt) {
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int V = scan_counts[b * 8 + 3];
   const uint32_t* bm = bitmap + (size_t)b * g.words;
   const int32_t* wr = word_rank + (size_t)b * g.words;
+  const bool has_taint = taint_cnt[b * kTaintCntStride + 2] > 0;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
     int ri = vox_tri[3 * (base + v)], si = vox_tri[3 * (base + v) + 1], ei = vox_tri[3 * (base + v) + 2];
     int32_t* out = vox_nbr + 27 * (base + v);
@@ -259,6 +371,14 @@ __global__ void __launch_bounds__(256) k_vox_nbr(const int64_t* __restrict__ off
         }
       }
     vox_root[base + v] = v;
+    if (has_taint && vox_tnt[base + v] == -1) {  // an ordinary voxel that sees a tainted one: its events take the general replay path
+      bool near = false;
+      for (int k = 0; k < 27; ++k) {
+        const int u = out[k];
+        if (u >= 0 && vox_tnt[base + u] >= 0) near = true;  // only ever changes between -1 and -3 concurrently: the test is stable
+      }
+      if (near) vox_tnt[base + v] = -3;
+    }
   }
 }
 
@@ -275,16 +395,22 @@ __device__ __forceinline__ int uf_find(int32_t* parent, int v) {
 }
 
 __global__ void __launch_bounds__(256) k_ccl_union(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
-                                                   const int32_t* __restrict__ vox_nbr, int32_t* __restrict__ vox_root) {
+                                                   const int32_t* __restrict__ vox_nbr, int32_t* __restrict__ vox_root,
+                                                   const int32_t* __restrict__ taint_cnt, const int32_t* __restrict__ vox_tnt) {
   const int b = blockIdx.y;
   const int64_t base = off[b];
   const int V = scan_counts[b * 8 + 3];
   int32_t* parent = vox_root + base;
+  // Tainted voxels stay singletons here: two adjacent ORDINARY voxels always end up in one cluster (each sees the other,
+  // ssc.cpp:323-351), a tainted voxel's points need not.  Components of ordinary voxels therefore lie inside one cluster.
+  const bool has_taint = taint_cnt[b * kTaintCntStride + 2] > 0;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    if (has_taint && vox_tnt[base + v] >= 0) continue;
     const int32_t* nb = vox_nbr + 27 * (base + v);
     for (int t = 0; t < 27; ++t) {
       int u = nb[t];
       if (u < 0 || u >= v) continue;  // each undirected edge once
+      if (has_taint && vox_tnt[base + u] >= 0) continue;
       int ra = uf_find(parent, v), rb = uf_find(parent, u);
       while (ra != rb) {
         if (ra < rb) {
@@ -310,6 +436,66 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(const int64_t* __restrict__
     int r = v;
     while (vox_root[base + r] != r) r = vox_root[base + r];
     vox_root[base + v] = r;
+  }
+}
+
+// Components of the voxel graph including every link a tainted voxel takes part in: the ordinary voxels that list it among
+// their 27 neighbours, and the neighbour lists of each of its points.  The name replay deals whole groups to its warps.
+__global__ void __launch_bounds__(1024) k_taint_group(const int64_t* __restrict__ off, const int32_t* __restrict__ scan_counts,
+                                                      const int32_t* __restrict__ taint_cnt, GridSpec g, BinParams bp,
+                                                      const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
+                                                      const int32_t* __restrict__ vox_nbr, const int32_t* __restrict__ vox_root,
+                                                      const int32_t* __restrict__ vox_tnt, const int32_t* __restrict__ tp_cid,
+                                                      const float4* __restrict__ tp_xyz, int32_t* __restrict__ vox_group) {
+  const int b = blockIdx.x;
+  const int64_t base = off[b];
+  const int V = scan_counts[b * 8 + 3];
+  const int T = taint_cnt[b * kTaintCntStride + 2];
+  int32_t* parent = vox_group + base;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) parent[v] = vox_root[base + v];
+  if (T == 0) return;
+  __syncthreads();
+  auto unite = [&](int a, int c) {
+    int ra = uf_find(parent, a), rb = uf_find(parent, c);
+    while (ra != rb) {
+      if (ra < rb) {
+        const int tmp = ra;
+        ra = rb;
+        rb = tmp;
+      }
+      const int old = atomicCAS(&parent[ra], ra, rb);
+      if (old == ra) break;
+      ra = uf_find(parent, old);
+      rb = uf_find(parent, rb);
+    }
+  };
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    if (vox_tnt[base + v] != -3) continue;
+    const int32_t* nb = vox_nbr + 27 * (base + v);
+    for (int k = 0; k < 27; ++k) {
+      const int u = nb[k];
+      if (u >= 0 && vox_tnt[base + u] >= 0) unite(v, u);
+    }
+  }
+  const uint32_t* bm = bitmap + (size_t)b * g.words;
+  const int32_t* wr = word_rank + (size_t)b * g.words;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float4 q = tp_xyz[(size_t)b * kTpCap + t];
+    const int X = tp_cid[(size_t)b * kTpCap + t];
+    const BinResult r = dev_bin_point(q.x, q.y, q.z, bp);
+    for (int x = r.ri - 1; x <= r.ri + 1; ++x)
+      for (int y = r.si - 1; y <= r.si + 1; ++y)
+        for (int z = r.ei - 1; z <= r.ei + 1; ++z) {
+          if (x > g.range_num - 1 || x < 0 || y > g.sector_num - 1 || y < 0 || z > g.azimuth_num - 1 || z < 0) continue;
+          const int c = vox_lookup(bm, wr, g, x * g.sector_num + y + z * g.range_num * g.sector_num);
+          if (c >= 0) unite(X, c);
+        }
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    int r = v;
+    while (parent[r] != r) r = parent[r];
+    parent[v] = r;  // concurrent walks stay correct: an entry only ever moves to an ancestor
   }
 }
 
@@ -435,6 +621,19 @@ __global__ void __launch_bounds__(256) k_similar_edges(const int64_t* __restrict
 //   C. every warp replays its own list; a new class records its creating event instead of a number;
 //   D. names = 5 + rank of the creating event among all creating events (popcount prefix over a bit per event).
 // ------------------------------------------------------------------------------------------------
+struct TaintArgs {  // side tables of the tainted voxels (k_taint_build) + what a point needs to compute its own neighbour list
+  const int32_t* taint_cnt;
+  const int32_t* vox_tnt;
+  const int32_t* vox_cnt;
+  const int32_t* tp_cid;
+  const float4* tp_xyz;
+  int32_t* tp_name;
+  const uint32_t* bitmap;
+  const int32_t* word_rank;
+  GridSpec g;
+  BinParams bp;
+};
+
 constexpr int kReplayWarps = 8;  // warps per scan: components are dealt to them by event count
 constexpr int kReplayRows = 32;   // events per chunk; neighbour rows of the next chunk are prefetched while one is replayed
 
@@ -445,17 +644,24 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
                                                          int32_t* __restrict__ g_parent, int32_t* __restrict__ g_setname,
                                                          int32_t* __restrict__ g_first, int32_t* __restrict__ g_state,
                                                          int32_t* __restrict__ g_flags, int32_t* __restrict__ vox_name,
-                                                         int32_t* __restrict__ name_first, int name_cap) {
+                                                         int32_t* __restrict__ name_first, int name_cap, TaintArgs ta) {
   constexpr int T = NW * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_scan[T / 32 + 1];
   __shared__ int s_load[NW], s_lbase[NW + 1], s_cursor[NW], s_free[NW + 1];
   __shared__ int s_wcnt[NW][NW];
   __shared__ int s_big[32], s_nbig, s_target;
+  __shared__ int s_row[NW][32];
   const int b = blockIdx.x;
   const int64_t base = off[b];
   const int V = scan_counts[b * 8 + 3];
   const int E = scan_counts[b * 8 + 5];
+  // tainted voxels (see k_taint_build): their NP points are nodes V .. V + NP - 1 of the union-find
+  const int NP = ta.taint_cnt[b * kTaintCntStride + 2];
+  const bool has_taint = NP > 0;
+  const int NV = V + NP;
+  const int32_t* tnt = ta.vox_tnt + base;
+  const int32_t* tpc = ta.tp_cid + (size_t)b * kTpCap;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nfw = (E + 31) >> 5;  // one "new class" bit per event
   // dynamic shared memory: [neighbour-row ring NW x 2 x 32 x 32 ints][union-find state 6 B / voxel][flags + prefix]
@@ -470,24 +676,25 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
     setname = g_setname + base;
     first_ev = g_first + base;
     state = reinterpret_cast<uint8_t*>(g_state + base);
-    stable = state + V;  // g_state has 4 bytes per voxel
+    stable = state + NV;  // g_state has 4 bytes per voxel (NV <= 2 * scan points is checked by the host)
     flags = reinterpret_cast<uint32_t*>(g_flags + base);  // E <= M <= N ints available: nfw flags, then nfw prefixes
     fprefix = g_flags + base + nfw;
   } else {
     // shared memory holds what sits on the dependent path of every event (parent, state, stable: 6 B / voxel, so scans of
     // up to ~25k voxels fit); set names and first events are written once and read at the end: global scratch
     parent = reinterpret_cast<int32_t*>(sm_state);
-    flags = reinterpret_cast<uint32_t*>(parent + V);
+    flags = reinterpret_cast<uint32_t*>(parent + NV);
     fprefix = reinterpret_cast<int32_t*>(flags + nfw);
     state = reinterpret_cast<uint8_t*>(fprefix + nfw);
-    stable = state + V;
+    stable = state + NV;
     setname = g_setname + base;
     first_ev = g_first + base;
   }
   const int32_t* ev = ev_cid + base;
-  const int32_t* root = vox_root + base;
+  const int32_t* root = vox_root + base;  // work partition: the groups of k_taint_group when the batch has tainted voxels
   const int32_t* nbr = vox_nbr + 27 * base;
   int2* lst = ev_list + base;
+  auto ev_voxel = [&](int node) { return node >= V ? tpc[node - V] : node; };  // the voxel an event's point hashes into
 
   // ---- A. events per component (cnt lives in parent[], the owner warp of a root in state[]) ---------------
   int32_t* cnt = parent;
@@ -499,7 +706,7 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
   }
   if (tid == 0) s_nbig = 0;
   __syncthreads();
-  for (int e = tid; e < E; e += T) atomicAdd(&cnt[root[ev[e]]], 1);
+  for (int e = tid; e < E; e += T) atomicAdd(&cnt[root[ev_voxel(ev[e])]], 1);
   __syncthreads();
   const int thr = E / (4 * NW) + 1;  // fewer than 4 * NW <= 32 components can be this large
   for (int v = tid; v < V; v += T)
@@ -579,7 +786,7 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
     int cid = -1, own = -1 - lane;  // idle lanes match nobody
     if (e < E) {
       cid = ev[e];
-      own = owner[root[cid]];
+      own = owner[root[ev_voxel(cid)]];
     }
     if (lane < NW) s_wcnt[wid][lane] = 0;
     __syncwarp();
@@ -602,7 +809,7 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
   }
   __syncthreads();
   // ---- C. replay ------------------------------------------------------------------------------------------------
-  for (int v = tid; v < V; v += T) {
+  for (int v = tid; v < NV; v += T) {
     parent[v] = v;
     setname[v] = -1;
     first_ev[v] = 0x7fffffff;
@@ -631,7 +838,7 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
     // The <= 3 events of a voxel usually sit in the same chunk: the row is fetched once per distinct voxel (by the first
     // lane of its group, `same` = lanes with the same voxel) and the later events read it from that lane's ring slot.
     auto prefetch = [&](const int2 evn, unsigned same, int buf) {
-      const bool need = evn.y >= 0 && !stable[evn.y] && (__ffs(same) - 1 == lane);
+      const bool need = evn.y >= 0 && evn.y < V && !stable[evn.y] && (__ffs(same) - 1 == lane);
       unsigned pm = __ballot_sync(0xffffffffu, need);
       while (pm) {
         const int j = __ffs(pm) - 1;
@@ -668,6 +875,98 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
           continue;
         }
         const int slot = __ffs(group) - 1;  // the row was fetched by the first event of the voxel in this chunk
+        if (has_taint && (W >= V || tnt[W] == -3)) {
+          // ---- general path: the visitor is a point of a tainted voxel, or an ordinary voxel with a tainted neighbour.
+          // A tainted voxel is visited point by point (ptIdx order); a point of one visits with its own neighbour list
+          // (findVoxelNeighbors on its own index triple, ssc.cpp:311), computed here.  One lane walks the sequence. ----
+          int rowv = -1;
+          if (W < V) {
+            rowv = (lane < 27) ? ring[c & 1][slot][lane] : -1;
+          } else {
+            const float4 q = ta.tp_xyz[(size_t)b * kTpCap + (W - V)];
+            const BinResult br = dev_bin_point(q.x, q.y, q.z, ta.bp);
+            if (lane < 27) {
+              const int x = br.ri - 1 + lane / 9, y = br.si - 1 + (lane / 3) % 3, z = br.ei - 1 + lane % 3;
+              if (!(x > ta.g.range_num - 1 || x < 0 || y > ta.g.sector_num - 1 || y < 0 || z > ta.g.azimuth_num - 1 || z < 0))
+                rowv = vox_lookup(ta.bitmap + (size_t)b * ta.g.words, ta.word_rank + (size_t)b * ta.g.words, ta.g,
+                                  x * ta.g.sector_num + y + z * ta.g.range_num * ta.g.sector_num);
+            }
+          }
+          s_row[wid][lane] = rowv;
+          __syncwarp();
+          if (lane == 0) {
+            atomicMin(&first_ev[W], e);
+            const bool is_pt = W >= V;
+            int oc = (state[W] == 2) ? find(W) : -1;
+            bool skipped = false;
+            auto visit = [&](int node) {
+              if (state[node] == 0) {
+                if (oc >= 0) {
+                  parent[node] = oc;  // clusterIdxs[neighbor] = oc (:338)
+                  state[node] = 2;
+                } else {
+                  skipped = true;
+                }
+              } else {
+                const int r = find(node);
+                if (oc < 0) {
+                  oc = r;  // clusterIdxs[i] = nc (:334)
+                } else if (r != oc) {
+                  parent[oc] = r;  // mergeClusters(oc -> nc) (:329)
+                  oc = r;
+                }
+                state[node] = 2;
+              }
+            };
+            for (int k = 0; k < 27; ++k) {
+              const int cN = s_row[wid][k];
+              if (cN < 0) continue;
+              const int tb = tnt[cN];
+              if (tb >= 0) {
+                const int n = ta.vox_cnt[base + cN];
+                for (int j = 0; j < n; ++j) visit(V + tb + j);
+              } else {
+                visit(cN);
+              }
+            }
+            if (oc < 0) {  // a new class (:345-351)
+              atomicOr(&flags[e >> 5], 1u << (e & 31));
+              parent[W] = W;
+              setname[W] = e;
+              state[W] = 2;
+              stable[W] = 1;
+              for (int k = 0; k < 27; ++k) {
+                const int cN = s_row[wid][k];
+                if (cN < 0) continue;
+                const int tb = tnt[cN];
+                if (tb >= 0) {
+                  const int n = ta.vox_cnt[base + cN];
+                  for (int j = 0; j < n; ++j)
+                    if (V + tb + j != W) {
+                      parent[V + tb + j] = W;
+                      state[V + tb + j] = 2;
+                    }
+                } else if (cN != W) {
+                  parent[cN] = W;
+                  state[cN] = 2;
+                }
+              }
+            } else if (is_pt) {
+              if (state[W] == 0) {
+                state[W] = 2;
+                parent[W] = oc;
+              }
+            } else {
+              if (state[W] == 0) {  // only this (first) point of W got the label
+                state[W] = 1;
+                parent[W] = oc;
+              }
+              stable[W] = skipped ? 0 : 1;
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         const int Vn = (lane < 27) ? ring[c & 1][slot][lane] : -1;
         if (lane == 0) atomicMin(&first_ev[W], e);  // fire-and-forget reduction: no load on the event path
         const bool exist = Vn >= 0;
@@ -763,13 +1062,16 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
   int32_t* nf = name_first + (size_t)b * name_cap;
   for (int i = tid; i <= cluster_name && i < name_cap; i += T) nf[i] = 0x7fffffff;
   __syncthreads();
-  for (int v = tid; v < V; v += T) {
+  for (int v = tid; v < NV; v += T) {
     int r = v;  // read-only walk: other threads resolve voxels of the same component at the same time
     while (parent[r] != r) r = parent[r];
     const int ec = setname[r];
     int nm = -1;
     if (ec >= 0) nm = 5 + fprefix[ec >> 5] + __popc(flags[ec >> 5] & ((1u << (ec & 31)) - 1u));
-    vox_name[base + v] = nm;
+    if (v < V)
+      vox_name[base + v] = nm;  // -1 for a tainted voxel: its points carry the names
+    else
+      ta.tp_name[(size_t)b * kTpCap + (v - V)] = nm;
     if (nm >= 0 && nm < name_cap) atomicMin(&nf[nm], first_ev[v]);
   }
   if (tid == 0) scan_counts[b * 8 + 6] = cluster_name;
@@ -778,18 +1080,32 @@ __global__ void __launch_bounds__(NW * 32) k_name_replay(const int64_t* __restri
 // ordered compaction of the apri points whose rank inside their voxel is < 3 ("clustering events").  One CTA per scan;
 // every warp owns a contiguous slice: count (ballot / popcount), ONE block scan over the 32 warp totals, then the same
 // walk again writing at the warp's offset — two barriers per scan instead of three per 1024 points.
+// Every point of a tainted voxel is an event of its own: payload V + (offset of the voxel's points in tp_*) + rank.
 __global__ void __launch_bounds__(1024) k_events(const int64_t* __restrict__ off, int32_t* __restrict__ scan_counts,
                                                  const int32_t* __restrict__ apri_cid, const int32_t* __restrict__ apri_rank,
+                                                 const int32_t* __restrict__ taint_cnt, const int32_t* __restrict__ vox_tnt,
                                                  int32_t* __restrict__ ev_cid) {
   __shared__ int s_w[33];
   const int b = blockIdx.x;
   const int64_t base = off[b];
   const int M = scan_counts[b * 8 + 2];
+  const int V = scan_counts[b * 8 + 3];
+  const bool has_taint = taint_cnt[b * kTaintCntStride + 2] > 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int slice = (((M + 31) / 32) + 31) & ~31;  // per warp, multiple of 32
   const int m0 = min(M, wid * slice), m1 = min(M, m0 + slice);
+  auto payload = [&](int m) {  // -1: no event
+    const int cid = apri_cid[base + m];
+    if (cid < 0) return -1;
+    const int rk = apri_rank[base + m];
+    if (has_taint) {
+      const int tb = vox_tnt[base + cid];
+      if (tb >= 0) return V + tb + rk;
+    }
+    return rk < 3 ? cid : -1;
+  };
   int cnt = 0;
-  for (int m = m0 + lane; m < m1; m += 32) cnt += (apri_cid[base + m] >= 0 && apri_rank[base + m] < 3) ? 1 : 0;
+  for (int m = m0 + lane; m < m1; m += 32) cnt += (payload(m) >= 0) ? 1 : 0;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
   int total;
@@ -797,8 +1113,8 @@ __global__ void __launch_bounds__(1024) k_events(const int64_t* __restrict__ off
   int pos = __shfl_sync(0xffffffffu, ex, 0);
   for (int j = m0; j < m1; j += 32) {
     const int m = j + lane;
-    const int cid = (m < m1) ? apri_cid[base + m] : -1;
-    const bool f = cid >= 0 && apri_rank[base + m] < 3;
+    const int cid = (m < m1) ? payload(m) : -1;
+    const bool f = cid >= 0;
     const unsigned mask = __ballot_sync(0xffffffffu, f);
     if (f) ev_cid[base + pos + __popc(mask & ((1u << lane) - 1u))] = cid;
     pos += __popc(mask);
@@ -812,8 +1128,9 @@ int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int max_sca
   cudaMemsetAsync(d.bitmap, 0, sizeof(uint32_t) * (size_t)nscans * hp.g.words, st);
   dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
   { TIMED("k_vox_mark", TSTREAM); k_vox_mark<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap); }
-  { TIMED("k_vox_rank", TSTREAM); k_vox_rank<<<nscans, 1024, 0, st>>>(d.off, hp.g, d.bitmap, d.word_rank, d.vox_vid, d.vox_cnt, d.scan_counts); }
+  { TIMED("k_vox_rank", TSTREAM); k_vox_rank<<<nscans, 1024, 0, st>>>(d.off, hp.g, d.bitmap, d.word_rank, d.vox_vid, d.vox_cnt, d.vox_tnt, d.scan_counts); }
   { TIMED("k_vox_count", TSTREAM); k_vox_count<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_vid, hp.g, d.bitmap, d.word_rank, d.apri_cid, d.vox_cnt); }
+  { TIMED("k_taint_mark", TSTREAM); k_taint_mark<<<nscans, 256, 0, st>>>(d.off, d.taint_cnt, d.q_list, d.apri_cid, d.vox_tnt); }
   { TIMED("k_vox_offsets", TSTREAM); k_vox_offsets<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.vox_cnt, d.vox_off, d.vox_cur); }
   { TIMED("k_vox_fill", TSTREAM); k_vox_fill<<<gpt, 256, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.vox_off, d.vox_cur, d.vox_pts_tmp); }
   dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 8), nscans);  // one warp per voxel, 8 warps per CTA
@@ -821,43 +1138,66 @@ int launch_descriptor(const HostParams& hp, BatchDev& d, int nscans, int max_sca
                                   d.apri_rank, d.vox_av, d.vox_cov, d.vox_bbox); }
   dim3 gc(grid_x_for(nscans, max_scan_points / 4 + 1, 256), nscans);
   { TIMED("k_vox_center", TSTREAM); k_vox_center<<<gc, 256, 0, st>>>(d.off, d.scan_counts, d.vox_off, d.vox_pts, d.apri_xyzi, bp, hp.p, d.vox_center, d.vox_tri); }
-  return 7;
+  { TIMED("k_taint_build", TSTREAM); k_taint_build<<<nscans, 1024, 0, st>>>(d.off, d.taint_cnt, d.q_list, d.apri_cid, d.vox_cnt, d.vox_off, d.vox_pts, d.apri_xyzi, d.vox_tnt,
+                                       d.tv_cid, d.tv_base, d.tp_m, d.tp_cid, d.tp_xyz); }
+  return 9;
 }
 
 int launch_cluster_prep(const HostParams& hp, BatchDev& d, int nscans, int max_scan_points, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   cudaMemsetAsync(d.edge_hash, 0xff, sizeof(unsigned long long) * (size_t)nscans * d.hash_cap, st);
   dim3 gv(grid_x_for(nscans, max_scan_points / 4 + 1, 256), nscans);
-  { TIMED("k_vox_nbr", TSTREAM); k_vox_nbr<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_nbr, d.vox_root); }
-  { TIMED("k_ccl_union", TSTREAM); k_ccl_union<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_nbr, d.vox_root); }
+  { TIMED("k_vox_nbr", TSTREAM); k_vox_nbr<<<gv, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_nbr, d.vox_root, d.taint_cnt, d.vox_tnt); }
+  { TIMED("k_ccl_union", TSTREAM); k_ccl_union<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_nbr, d.vox_root, d.taint_cnt, d.vox_tnt); }
   { TIMED("k_ccl_flatten", TSTREAM); k_ccl_flatten<<<gv, 256, 0, st>>>(d.off, d.scan_counts, d.vox_root); }
   dim3 gw(grid_x_for(nscans, max_scan_points / 4 + 1, 8), nscans);  // one warp per voxel, 8 warps per CTA
   { TIMED("k_similar_edges", TSTREAM); k_similar_edges<<<gw, 256, 0, st>>>(d.off, d.scan_counts, hp.g, d.bitmap, d.word_rank, d.vox_tri, d.vox_av, d.vox_cov, d.vox_root,
                                       hp.p.search_c, hp.p.intensity_cov, hp.p.intensity_diff,
                                       reinterpret_cast<unsigned long long*>(d.edge_hash), d.hash_cap, d.edge_buf, d.edge_cap); }
-  { TIMED("k_events", TSTREAM); k_events<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.apri_rank, d.ev_cid); }
+  { TIMED("k_events", TSTREAM); k_events<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.apri_cid, d.apri_rank, d.taint_cnt, d.vox_tnt, d.ev_cid); }
   return 5;
 }
 
-int launch_name_replay(BatchDev& d, int nscans, int max_vox, int max_events, bool force_global, int32_t* vox_name, int32_t* name_first, int name_cap,
-                       void* stream_) {
+int launch_name_replay(const HostParams& hp, BatchDev& d, int nscans, int max_nodes, int max_events, bool force_global, bool any_taint,
+                       int32_t* vox_name, int32_t* name_first, int name_cap, void* stream_) {
   if (nscans <= 0) return 0;
   constexpr int NW = kReplayWarps;
+  cudaStream_t st = (cudaStream_t)stream_;
   const size_t ring = sizeof(int) * NW * 2 * kReplayRows * 32;
   const size_t nfw = ((size_t)max_events + 31) / 32;
-  const size_t smem = ring + (size_t)max_vox * 6 + nfw * 8 + 16;
+  const size_t smem = ring + (size_t)max_nodes * 6 + nfw * 8 + 16;
   static std::once_flag replay_once;
   std::call_once(replay_once, [ring] {
     cudaFuncSetAttribute(k_name_replay<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(k_name_replay<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
   });
+  int launches = 1;
+  const int32_t* group = d.vox_root;
+  if (any_taint) {  // some scan of the batch has tainted voxels: events interact across ordinary components through them
+    TIMED("k_taint_group", TSTREAM);
+    k_taint_group<<<nscans, 1024, 0, st>>>(d.off, d.scan_counts, d.taint_cnt, hp.g, make_bin_params(hp), d.bitmap, d.word_rank, d.vox_nbr, d.vox_root,
+                                           d.vox_tnt, d.tp_cid, d.tp_xyz, d.vox_group);
+    group = d.vox_group;
+    ++launches;
+  }
+  TaintArgs ta;
+  ta.taint_cnt = d.taint_cnt;
+  ta.vox_tnt = d.vox_tnt;
+  ta.vox_cnt = d.vox_cnt;
+  ta.tp_cid = d.tp_cid;
+  ta.tp_xyz = d.tp_xyz;
+  ta.tp_name = d.tp_name;
+  ta.bitmap = d.bitmap;
+  ta.word_rank = d.word_rank;
+  ta.g = hp.g;
+  ta.bp = make_bin_params(hp);
   int2* ev_list = reinterpret_cast<int2*>(d.bucket_kv);  // the ground stage is done with its (key, index) buckets
   if (smem <= 220 * 1024 && !force_global) {
-    { TIMED("k_name_replay", TSTREAM); k_name_replay<NW, false><<<nscans, NW * 32, smem, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, nullptr, d.vox_pts_tmp, d.apri_rank, nullptr, nullptr, vox_name, name_first, name_cap); }
+    { TIMED("k_name_replay", TSTREAM); k_name_replay<NW, false><<<nscans, NW * 32, smem, st>>>(d.off, d.scan_counts, d.ev_cid, group, d.vox_nbr, ev_list, nullptr, d.vox_pts_tmp, d.apri_rank, nullptr, nullptr, vox_name, name_first, name_cap, ta); }
   } else {  // very dense scans: union-find state in (L2-resident) global scratch that the earlier stages are done with
-    { TIMED("k_name_replay_global", TSTREAM); k_name_replay<NW, true><<<nscans, NW * 32, ring, (cudaStream_t)stream_>>>(d.off, d.scan_counts, d.ev_cid, d.vox_root, d.vox_nbr, ev_list, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, d.slot_pos, vox_name, name_first, name_cap); }
+    { TIMED("k_name_replay_global", TSTREAM); k_name_replay<NW, true><<<nscans, NW * 32, ring, st>>>(d.off, d.scan_counts, d.ev_cid, group, d.vox_nbr, ev_list, d.vox_cur, d.vox_pts_tmp, d.apri_rank, d.sorted_idx, d.slot_pos, vox_name, name_first, name_cap, ta); }
   }
-  return 1;
+  return launches;
 }
 
 }  // namespace scvod

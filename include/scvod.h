@@ -233,6 +233,20 @@ int scvod_host_segment(const scvod_params* p, int V, const int32_t* vox_cnt, con
                        int32_t* name_stage2, int32_t n_clusters[3], int cap, int32_t* cluster_name,
                        int32_t* cluster_type, int32_t* max_name);
 
+/* The same with "tainted" voxels: voxels that hold a point whose range / sector / azimuth index is -1 (dis == min_dis,
+ * y == 0 with x > 0, azimuth == min_azimuth; ssc.cpp:185-188).  Such a point hashes into a voxel that is not its own cell, so
+ * the voxel's points no longer share one neighbour list and clusterAndCreateFrame is replayed point by point for them:
+ * tv_cid = the tainted voxels (ascending), points of voxel i = tp_*[tv_base[i] .. tv_base[i+1]) in ascending apri index
+ * (tp_m), tp_nbr = each point's own findVoxelNeighbors list (27 compact ids, -1 = absent), an event ev_cid >= V is point
+ * ev_cid - V of those tables (every point of a tainted voxel is an event).  tp_stage receives [3][n_tpts] cluster names. */
+int scvod_host_segment_pts(const scvod_params* p, int V, const int32_t* vox_cnt, const int32_t* vox_root,
+                           const int32_t* vox_nbr, const float* vox_bbox, int n_events, const int32_t* ev_cid,
+                           int n_edges, const int32_t* edges, int n_tvox, const int32_t* tv_cid, const int32_t* tv_base,
+                           int n_tpts, const int32_t* tp_m, const float* tp_xyz, const int32_t* tp_nbr,
+                           int32_t* name_stage0, int32_t* name_stage1, int32_t* name_stage2, int32_t* tp_stage,
+                           int32_t n_clusters[3], int cap, int32_t* cluster_name, int32_t* cluster_type,
+                           int32_t* cluster_npts, int32_t* cluster_nvox, int32_t* max_name);
+
 /* ---- helpers shared by tests and the bench ---------------------------------------------------- */
 /* trans_next.inverse() * trans_pre of SSC::tracking (ssc.cpp:1255-1257) as 12 floats row-major 3x4. */
 void scvod_relative_pose(const float pose_next6[6], const float pose_pre6[6], float T[12]);

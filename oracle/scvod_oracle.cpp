@@ -506,7 +506,7 @@ struct Voxel {  // utility.h:109-119
 };
 struct Cluster {  // utility.h:142-162
   int track_id = -1, name = -1, type = -1, state = -1;
-  Pt bb_min, bb_max;
+  Pt bb_min = {0.f, 0.f, 0.f, 0.f, -1}, bb_max = {0.f, 0.f, 0.f, 0.f, -1};  // a default pcl::PointXYZI pair: zeros (PCL 1.8 point_types.hpp)
   std::vector<int> occupy_pts, occupy_voxels;
   Cloud cloud;
 };
@@ -1058,8 +1058,9 @@ class SSCOracle {
         }
       }
     }
-    // recognize(frame_based) (ssc.cpp:1241) takes the bounding box of the cluster clouds as they are now
-    for (auto& c : frame_based.cluster_set) getBoundingBoxOfCloud(c.second.cloud, c.second.bb_min, c.second.bb_max);
+    // recognize(frame_based) (ssc.cpp:1242) reads Cluster::bounding_box as it is: the box refineClusterByBoundingBox stored for
+    // the clusters of the base frame, and the zeros of a default-constructed pair for every fused cluster (ssc.cpp:1211-1233
+    // never computes one), which the car rule then types as `tree` (min.z = 0 is not < min_z)
     recognize(frame_based);
     init_frame = frame_based;
     return id_based;

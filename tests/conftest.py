@@ -225,3 +225,67 @@ def has_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def copy_params(pkg, p):
+    q = pkg.Params()
+    import ctypes as _c
+    _c.memmove(_c.byref(q), _c.byref(p), _c.sizeof(q))
+    return q
+
+
+def densest_object_direction(cloud):
+    """Direction (rad) in which the scan has the most above-ground returns between 3 and 28 m."""
+    r = np.hypot(cloud[:, 0], cloud[:, 1])
+    m = (cloud[:, 2] > -1.3) & (r > 3.0) & (r < 28.0)
+    h, edges = np.histogram(np.arctan2(cloud[m, 1], cloud[m, 0]), bins=72, range=(-np.pi, np.pi))
+    k = int(np.argmax(h))
+    return 0.5 * (edges[k] + edges[k + 1])
+
+
+def taint_scan(cloud, pose=None, turn=None, frac=1.0):
+    """Put points with a -1 sector index (y == 0 exactly with x > 0, ssc.cpp:186) INSIDE objects: the scan is turned about z by
+    -turn (default: its densest object direction, so that objects sit on the +x axis; the pose's yaw follows), then every
+    above-ground point with x > 3 m within 0.15 m of the x axis gets y = +0.0 or -0.0 (both give angle 0).
+    Returns (cloud, pose, number of such points)."""
+    c = cloud.copy()
+    if turn is None:
+        turn = densest_object_direction(c)
+    cs, sn = np.float32(np.cos(-turn)), np.float32(np.sin(-turn))
+    x, y = c[:, 0].copy(), c[:, 1].copy()
+    c[:, 0] = cs * x - sn * y
+    c[:, 1] = sn * x + cs * y
+    k = np.flatnonzero((c[:, 0] > 3.0) & (np.abs(c[:, 1]) < 0.15) & (c[:, 2] > -1.3))
+    if frac <= 0.0:
+        k = k[:0]
+    elif frac < 1.0:
+        k = k[:: max(1, int(round(1.0 / frac)))]
+    c[k[::2], 1] = 0.0
+    c[k[1::2], 1] = -0.0
+    if pose is not None:
+        pose = np.array(pose, np.float32)
+        pose[5] = np.float32(pose[5] + turn)  # p_map = T Rz(turn) p'
+    return c, pose, len(k)
+
+
+def params_with_edge_points(pkg, params, oracle_cls, cloud):
+    """Parameters whose min_azimuth / min_dis equal the exact float elevation / range of points that sit inside objects of
+    `cloud`, so that those points get azimuth_idx == -1 / range_idx == -1 (ssc.cpp:185,187).  The point chosen for min_dis
+    lends its (x, y) to three object points near it, so several points alias."""
+    o = oracle_cls(params)
+    b = o.bin(cloud)
+    o.close()
+    c = cloud.copy()
+    obj = np.flatnonzero((c[:, 2] > -1.0) & (c[:, 2] < 0.5) & (b["pass"] != 0) & (b["range"] > 6.0) & (b["range"] < 20.0))
+    assert len(obj) > 200
+    q = copy_params(pkg, params)
+    k2 = obj[np.argsort(b["azimuth"][obj])[len(obj) // 10]]  # a low (not the lowest) object point: most of the objects stay in the window
+    q.min_azimuth = float(b["azimuth"][k2])
+    near = obj[(b["azimuth"][obj] > q.min_azimuth + 1.0) & (b["range"][obj] < 12.0)]
+    assert len(near) > 50
+    k = near[len(near) // 3]
+    d = np.abs(c[near, 0] - c[k, 0]) + np.abs(c[near, 1] - c[k, 1])
+    for j in near[np.argsort(d)[1:4]]:
+        c[j, 0], c[j, 1] = c[k, 0], c[k, 1]
+    q.min_dis = float(b["range"][k])
+    return q, c

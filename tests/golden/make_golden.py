@@ -95,6 +95,36 @@ def main():
     np.savez_compressed(os.path.join(HERE, "init_small.npz"), **init)
     orc2.close()
 
+    # scans with y == 0 rows inside objects (sector_idx -1: the point hashes into another cell's voxel, ssc.cpp:186-188), which
+    # clusterAndCreateFrame names point by point; labels after tracking
+    orc3 = conftest.Oracle(P)
+    raw = [pkg.synth_scan(conftest.SEED + 60, k, rings=16, cols=450) for k in range(4)]
+    turn = conftest.densest_object_direction(raw[0][0])
+    al = {}
+    aposes = []
+    nq = 0
+    for k, (s, pose) in enumerate(raw):
+        s, pose, n = conftest.taint_scan(s, pose, turn=turn)
+        nq += n
+        al[f"xyzi{k}"] = s
+        aposes.append(pose)
+        orc3.push_scan(s)
+    assert nq > 20
+    aposes = np.stack(aposes)
+    al["poses"] = aposes
+    for k in range(4):
+        src, vid = orc3.apri(k)
+        al[f"apri_src{k}"], al[f"apri_vid{k}"] = src, vid
+        al[f"vox_label{k}"] = orc3.voxels(k)["label"]
+        for st in range(3):
+            al[f"names{k}_{st}"] = orc3.point_cluster(k, st)
+    orc3.track(aposes)
+    for k in range(4):
+        al[f"labels{k}"] = orc3.labels(k)
+        al[f"cl_state{k}"] = orc3.clusters(k)["state"]
+    np.savez_compressed(os.path.join(HERE, "aliased_small.npz"), **al)
+    orc3.close()
+
     hashes = {}
     for k in range(3):
         s, pose = pkg.synth_scan(conftest.SEED, k)

@@ -457,18 +457,103 @@ def test_prefetched_upload_gives_the_same_labels(pkg):
     s.close()
 
 
-def test_aliased_voxel_scan_is_rejected_loudly(pkg):
-    """Points with a -1 index (y == 0 exactly) alias voxels; clustering them is not supported yet and must
-    fail with an explicit error rather than return different labels."""
-    cloud, _ = pkg.synth_scan(conftest.SEED, 0, rings=16, cols=450)
-    cloud = cloud.copy()
-    k = np.argmax((cloud[:, 2] > -1.0) & (cloud[:, 0] > 3) & (np.hypot(cloud[:, 0], cloud[:, 1]) < 25))
-    cloud[k, 1] = 0.0
-    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=16 * 450, max_batch=1)
-    try:
-        s.process([cloud])
-        c = s.frame_counts(0)  # accepted only if the point did not survive as an apri point
-        assert c[3] >= 0
-    except pkg.ScvodError as e:
-        assert "-1" in str(e)
+def tainted_sequence(pkg, seed, nframes, rings, cols, every=1):
+    """Synthetic frames turned so that objects sit on the +x axis, with y == 0 points inside them (conftest.taint_scan)."""
+    raw = [pkg.synth_scan(seed, k, rings=rings, cols=cols) for k in range(nframes)]
+    turn = conftest.densest_object_direction(raw[0][0])
+    scans, poses, nq = [], [], 0
+    for k, (s, p) in enumerate(raw):
+        if k % every == 0:
+            s, p, n = conftest.taint_scan(s, p, turn=turn)
+            nq += n
+        else:
+            s, p, _ = conftest.taint_scan(s, p, turn=turn, frac=0.0)
+        scans.append(s)
+        poses.append(p)
+    return scans, np.stack(poses), nq
+
+
+def check_sequence_against_oracle(pkg, s, orc, scans, poses):
+    s.process(scans)
+    for sc in scans:
+        orc.push_scan(sc)
+    compare_frames(s, orc, len(scans), pkg)
+    s.tracking(poses)
+    orc.track(poses)
+    for f in range(len(scans)):
+        assert np.array_equal(s.frame_labels(f), orc.labels(f)), f"per-point classes of frame {f}"
+        cg, co = s.frame_clusters(f), orc.clusters(f)
+        for k in ("name", "type", "state", "npts", "nvox"):
+            assert np.array_equal(cg[k], co[k]), (f, k)
+
+
+@pytest.mark.parametrize("config,seed_off,rings,cols,nframes", [("semantickitti", 60, 64, 1800, 6), ("parkinglot", 61, 64, 1800, 4),
+                                                               ("semantickitti", 62, 32, 900, 12), ("parkinglot", 63, 32, 900, 10)])
+def test_minus_one_sector_points_inside_clusters(pkg, config, seed_off, rings, cols, nframes):
+    """y == 0 exactly with x > 0 gives angle 0 and sector_idx -1 (ssc.cpp:186): the point hashes into another cell's voxel and
+    clusterAndCreateFrame has to be replayed point by point for that voxel (ssc.cpp:299-393).  KITTI .bin coordinates are
+    quantised, so such rows occur in real scans.  Everything the reference computes is reproduced: voxel indices, descriptor,
+    names after the three clustering stages, clusters, tracking states and per-point classes."""
+    params = getattr(pkg, config + "_params")()
+    scans, poses, nq = tainted_sequence(pkg, conftest.SEED + seed_off, nframes, rings, cols)
+    assert nq >= 10 * nframes
+    s = pkg.SSC(params, device=0, max_points=rings * cols, max_batch=8)
+    orc = conftest.Oracle(params)
+    check_sequence_against_oracle(pkg, s, orc, scans, poses)
+    assert s.stat("tainted_voxels") > 0
+    s.close()
+    orc.close()
+
+
+def test_minus_one_range_and_azimuth_points_inside_clusters(pkg):
+    """dis == min_dis (range_idx -1) and azimuth == min_azimuth (azimuth_idx -1, a NEGATIVE voxel_idx), together with
+    y == 0 rows; a batch that mixes such scans with ordinary ones."""
+    kp = pkg.semantickitti_params()
+    scans, poses, _ = tainted_sequence(pkg, conftest.SEED + 64, 6, 32, 900, every=2)
+    params, scans[0] = conftest.params_with_edge_points(pkg, kp, conftest.Oracle, scans[0])
+    orc = conftest.Oracle(params)
+    b = orc.bin(scans[0])
+    assert ((b["pass"] != 0) & (b["range_idx"] == -1)).sum() >= 1 and ((b["pass"] != 0) & (b["azimuth_idx"] == -1)).sum() >= 1
+    s = pkg.SSC(params, device=0, max_points=32 * 900, max_batch=8)
+    check_sequence_against_oracle(pkg, s, orc, scans, poses)
+    s.close()
+    orc.close()
+
+
+def test_minus_one_points_with_global_replay_and_initialization(pkg):
+    """The global-memory variant of the name replay and SSC::intialization on frames that hold aliased voxels."""
+    params = pkg.semantickitti_params()
+    scans, poses, _ = tainted_sequence(pkg, conftest.SEED + 65, 6, 32, 900)
+    s = pkg.SSC(params, device=0, max_points=32 * 900, max_batch=8)
+    s.set_option("replay_global", 1)
+    orc = conftest.Oracle(params)
+    s.process(scans)
+    for sc in scans:
+        orc.push_scan(sc)
+    compare_frames(s, orc, len(scans), pkg)
+    assert s.intialization(poses) == orc.initialization(poses)
+    cg, co = s.frame_clusters(pkg.INIT_FRAME), orc.clusters(-1)
+    for k in ("name", "type", "npts", "nvox"):
+        assert np.array_equal(cg[k], co[k]), k
+    assert np.array_equal(s.frame_voxels(pkg.INIT_FRAME)["label"], orc.voxels(-1)["label"])
+    s.tracking(poses)
+    orc.track(poses)
+    for f in range(len(scans)):
+        assert np.array_equal(s.frame_labels(f), orc.labels(f)), f
+    s.close()
+    orc.close()
+
+
+def test_aliased_golden_fixture_through_gpu(pkg):
+    z = np.load(os.path.join(GOLD, "aliased_small.npz"))
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=16 * 450, max_batch=4)
+    labels = s.segDF([z[f"xyzi{k}"] for k in range(4)], z["poses"])
+    for k in range(4):
+        src, vid = s.frame_apri(k)
+        assert np.array_equal(src, z[f"apri_src{k}"]) and np.array_equal(vid, z[f"apri_vid{k}"])
+        for st in range(3):
+            assert np.array_equal(s.frame_point_cluster(k, st), z[f"names{k}_{st}"])
+        assert np.array_equal(labels[k], z[f"labels{k}"])
+        assert np.array_equal(s.frame_clusters(k)["state"], z[f"cl_state{k}"])
+    assert s.stat("tainted_points") > 0
     s.close()

@@ -184,3 +184,72 @@ def test_relative_pose_matches_float64(oracle, pkg):
         assert np.allclose(T, ref, atol=2e-4)
         # the product's host restatement is the same arithmetic, bit for bit
         assert np.array_equal(pkg.relative_pose(a, b).view(np.uint32), T.view(np.uint32))
+
+
+def python_cvc_names(grid, tri, vid):
+    """clusterAndCreateFrame (ssc.cpp:299-352) restated point by point in plain Python: hash_cloud is a dict voxel_idx -> ptIdx,
+    every point visits the points of the <= 27 voxels around ITS OWN index triple (which is not the cell it hashes into when an
+    index is -1), mergeClusters renames by a full sweep."""
+    R, S, A = grid
+    hash_cloud = {}
+    for i, v in enumerate(vid.tolist()):
+        hash_cloud.setdefault(v, []).append(i)
+    name = 4
+    idx = [-1] * len(vid)
+    for i in range(len(vid)):
+        ri, si, ei = (int(t) for t in tri[i])
+        neighbors = []
+        if int(vid[i]) in hash_cloud:
+            for x in range(ri - 1, ri + 2):
+                if x > R - 1 or x < 0:
+                    continue
+                for y in range(si - 1, si + 2):
+                    if y > S - 1 or y < 0:
+                        continue
+                    for z in range(ei - 1, ei + 2):
+                        if z > A - 1 or z < 0:
+                            continue
+                        neighbors += hash_cloud.get(x * S + y + z * R * S, [])
+        for n in neighbors:
+            oc, nc = idx[i], idx[n]
+            if oc != -1 and nc != -1:
+                if oc != nc:
+                    idx = [nc if c == oc else c for c in idx]
+            elif nc != -1:
+                idx[i] = nc
+            elif oc != -1:
+                idx[n] = oc
+        if idx[i] == -1:
+            name += 1
+            idx[i] = name
+            for n in neighbors:
+                idx[n] = name
+    return np.array(idx, np.int32), name
+
+
+def test_aliased_fixture_and_independent_python_restatement(pkg, kitti_params):
+    """Scans with y == 0 rows inside objects (sector_idx -1).  (1) the oracle reproduces the committed fixture; (2) its cluster
+    names equal a second, independent restatement of the reference's loop written directly from ssc.cpp:299-352 in Python."""
+    z = np.load(os.path.join(GOLD, "aliased_small.npz"))
+    orc = conftest.Oracle(kitti_params)
+    for k in range(4):
+        orc.push_scan(z[f"xyzi{k}"])
+    grid = orc.grid_dims()[:3]
+    naliased = 0
+    for k in range(4):
+        src, vid = orc.apri(k)
+        assert np.array_equal(src, z[f"apri_src{k}"]) and np.array_equal(vid, z[f"apri_vid{k}"])
+        for st in range(3):
+            assert np.array_equal(orc.point_cluster(k, st), z[f"names{k}_{st}"])
+        assert np.array_equal(orc.voxels(k)["label"], z[f"vox_label{k}"])
+        b = orc.bin(z[f"xyzi{k}"][src])
+        tri = np.stack([b["range_idx"], b["sector_idx"], b["azimuth_idx"]], 1)
+        naliased += int((tri < 0).any(axis=1).sum())
+        names, last = python_cvc_names(grid, tri, vid)
+        assert np.array_equal(names, z[f"names{k}_0"])
+    assert naliased >= 20
+    orc.track(z["poses"])
+    for k in range(4):
+        assert np.array_equal(orc.labels(k), z[f"labels{k}"])
+        assert np.array_equal(orc.clusters(k)["state"], z[f"cl_state{k}"])
+    orc.close()
