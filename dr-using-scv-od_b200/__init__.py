@@ -17,6 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscvod_b200.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libscvod_synth.so")  # scan generator + parameter sets, no CUDA (csrc/Makefile)
 
 # enum scvod_point_class (include/scvod.h)
 PT_DROPPED_LOW, PT_DROPPED_RANGE, PT_DROPPED_SPARSE, PT_GROUND, PT_GATED_OUT, PT_UNCLUSTERED, PT_STATIC, PT_DYNAMIC = range(8)
@@ -93,6 +94,23 @@ def load_library() -> ctypes.CDLL:
     return _lib
 
 
+_synth = None
+
+
+def load_synth_library() -> ctypes.CDLL:
+    """libscvod_synth.so: the deterministic scan generator and the two YAML parameter sets, host-only C++.  The CPU reference
+    arm of bench.py and the oracle-side tools use nothing else of this package, so they never map the CUDA library."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise RuntimeError(f"{SYNTH_LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}`")
+        lib = ctypes.CDLL(SYNTH_LIB_PATH)
+        lib.scvod_params_semantickitti.restype = None
+        lib.scvod_params_parkinglot.restype = None
+        _synth = lib
+    return _synth
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
@@ -109,13 +127,13 @@ def _check(rc: int):
 
 def semantickitti_params() -> Params:
     p = Params()
-    load_library().scvod_params_semantickitti(ctypes.byref(p))
+    load_synth_library().scvod_params_semantickitti(ctypes.byref(p))
     return p
 
 
 def parkinglot_params() -> Params:
     p = Params()
-    load_library().scvod_params_parkinglot(ctypes.byref(p))
+    load_synth_library().scvod_params_parkinglot(ctypes.byref(p))
     return p
 
 
@@ -130,7 +148,8 @@ def synth_scan(seed: int, scan_id: int, rings: int = 64, cols: int = 1800):
     buf = np.empty((rings * cols, 4), np.float32)
     n = ctypes.c_int(0)
     pose = np.zeros(6, np.float32)
-    _check(load_library().scvod_synth_scan(ctypes.c_uint64(seed), int(scan_id), int(rings), int(cols), _ptr(buf), ctypes.byref(n), _ptr(pose)))
+    if load_synth_library().scvod_synth_scan(ctypes.c_uint64(seed), int(scan_id), int(rings), int(cols), _ptr(buf), ctypes.byref(n), _ptr(pose)) < 0:
+        raise ScvodError("scvod_synth_scan: bad arguments")
     return np.ascontiguousarray(buf[: n.value]), pose
 
 

@@ -20,6 +20,7 @@
 // behaviour = no FMA).
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -1330,6 +1331,46 @@ double orc_run_sequence(const scvod_params* p, const float* xyzi, const int64_t*
     for (int f = 0; f < nscans; ++f) s.frameLabels(f, labels + offsets[f]);
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+
+// The GPU arm's decomposition on the host cores: `nchunks` independent sequences (chunk c = scans [c*chunk, (c+1)*chunk) of the
+// input, which may repeat: chunk c reads input chunk c % in_chunks), each one run like the reference runs a sequence (per-scan
+// stages, then tracking(k, k+1) as soon as both frames exist) by ONE thread; threads pull chunks from a queue.  A frame is
+// dropped once it has been `pre`, so a thread holds two frames at a time.  labels (may be null) = [nchunks * points of a chunk].
+double orc_run_chunks(const scvod_params* p, const float* xyzi, const int64_t* offsets, int in_chunks, int chunk, const float* poses6,
+                      int nchunks, int nthreads, uint8_t* labels) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (nthreads < 1) nthreads = 1;
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) {
+    th.emplace_back([&]() {
+      for (;;) {
+        const int c = next.fetch_add(1);
+        if (c >= nchunks) break;
+        const int ic = c % in_chunks;
+        const int64_t* off = offsets + (size_t)ic * chunk;
+        const float* poses = poses6 + 6 * (size_t)ic * chunk;
+        SSCOracle w(*p);
+        for (int k = 0; k < chunk; ++k) {
+          w.id = k;
+          w.pushScan(xyzi + 4 * off[k], (int)(off[k + 1] - off[k]));
+          if (k > 0) {
+            w.tracking(w.frame_set[k - 1], w.frame_set[k], poses + 6 * (k - 1), poses + 6 * k);
+            if (labels) w.frameLabels(k - 1, labels + (off[k - 1] - offsets[0]));  // only meaningful when nchunks <= in_chunks
+            Frame& done = w.frame_set[k - 1];
+            Frame().hash_cloud.swap(done.hash_cloud);
+            Frame().cluster_set.swap(done.cluster_set);
+            Cloud().swap(done.cloud_use);
+          }
+        }
+        if (labels && chunk > 0) w.frameLabels(chunk - 1, labels + (off[chunk - 1] - offsets[0]));
+      }
+    });
+  }
+  for (auto& t : th) t.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

@@ -201,6 +201,20 @@ class Oracle:
         secs = self.lib.orc_run_sequence(ctypes.byref(self.params), _ptr(flat), _ptr(off), len(scans), _ptr(poses), int(nthreads), _ptr(labels))
         return secs, (labels[: off[-1]] if want_labels else None), off
 
+    def run_chunks(self, flat, off, poses, chunk, nchunks, nthreads=1, want_labels=False):
+        """nchunks independent sequences of `chunk` scans (chunk c reads input chunk c % in_chunks), one thread per chunk at a
+        time: the decomposition the GPU arm of bench.py uses.  Returns (seconds, labels or None)."""
+        off = np.ascontiguousarray(off, np.int64)
+        flat = np.ascontiguousarray(flat, np.float32)
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        in_chunks = (len(off) - 1) // chunk
+        assert in_chunks >= 1 and len(poses) >= in_chunks * chunk
+        labels = np.zeros(max(int(off[in_chunks * chunk] - off[0]), 1), np.uint8) if want_labels else None
+        self.lib.orc_run_chunks.restype = ctypes.c_double
+        secs = self.lib.orc_run_chunks(ctypes.byref(self.params), _ptr(flat), _ptr(off), in_chunks, int(chunk), _ptr(poses), int(nchunks),
+                                       int(nthreads), _ptr(labels))
+        return secs, labels
+
 
 @pytest.fixture(scope="session")
 def pkg():

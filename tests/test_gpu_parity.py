@@ -557,3 +557,33 @@ def test_aliased_golden_fixture_through_gpu(pkg):
         assert np.array_equal(s.frame_clusters(k)["state"], z[f"cl_state{k}"])
     assert s.stat("tainted_points") > 0
     s.close()
+
+
+def test_benchmarked_chunk_matches_oracle(pkg):
+    """The exact shape bench.py times: one 64-frame chunk of 64x1800 scans (its batches[0]: generator seed SEED, scans 0..63,
+    carried clouds growing over 63 tracked pairs).  Per-point classes, cluster names and states of every frame equal the oracle's."""
+    n = 64
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED, k) for k in range(n)])
+    poses = np.stack(poses)
+    s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=n)
+    labels = s.segDF(scans, poses)
+    orc = conftest.Oracle(pkg.semantickitti_params())
+    secs, olab, off = orc.run_sequence(scans, poses, nthreads=8)
+    ndyn = 0
+    for f in range(n):
+        assert np.array_equal(labels[f], olab[off[f]:off[f + 1]]), f"frame {f}"
+        ndyn += int((labels[f] == pkg.PT_DYNAMIC).sum())
+    assert ndyn > 0 and s.stat("track_pairs") == n - 1
+    # cluster tables of a few frames deep in the chain (the step-by-step oracle keeps them)
+    for sc in scans[:24]:
+        orc.push_scan(sc)
+    orc.track(poses[:24])
+    t = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=24)
+    t.segDF(scans[:24], poses[:24])
+    for f in (5, 14, 22, 23):
+        cg, co = t.frame_clusters(f), orc.clusters(f)
+        for k in ("name", "type", "state", "npts", "nvox"):
+            assert np.array_equal(cg[k], co[k]), (f, k)
+    s.close()
+    t.close()
+    orc.close()
