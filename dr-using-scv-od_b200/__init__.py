@@ -70,6 +70,7 @@ EXPORTS = (
     "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_host_segment_pts", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
     "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
+    "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states",
 )
 
 _lib = None
@@ -289,6 +290,29 @@ class SSC:
     def tracking(self, poses: np.ndarray):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
         _check(self._lib.scvod_track(self._ctx, _ptr(poses), len(poses)))
+
+    # -- one unbroken chain over a sequence cut into chunks (include/scvod.h "chain hand-off") ----
+    def export_tail(self) -> np.ndarray:
+        """The last frame as tracking() sees a frame_pre_ (car clusters in cluster_set order with their clouds): host bytes."""
+        n = ctypes.c_size_t(0)
+        _check(self._lib.scvod_export_tail(self._ctx, None, ctypes.c_size_t(0), ctypes.byref(n)))
+        buf = np.zeros(int(n.value), np.uint8)
+        _check(self._lib.scvod_export_tail(self._ctx, _ptr(buf), ctypes.c_size_t(buf.size), ctypes.byref(n)))
+        return buf
+
+    def track_from_tail(self, tail: np.ndarray, pose_pre: np.ndarray, pose_next: np.ndarray) -> np.ndarray:
+        """tracking(tail of the previous chunk, this context's frame 0); returns (state, type) per exported car cluster."""
+        tail = np.ascontiguousarray(tail, np.uint8)
+        ncars = int(tail[4:8].view(np.int32)[0]) if tail.size >= 16 else 0
+        st = np.zeros((max(ncars, 1), 2), np.int32)
+        a = np.ascontiguousarray(pose_pre, np.float32)
+        b = np.ascontiguousarray(pose_next, np.float32)
+        n = _check(self._lib.scvod_track_from_tail(self._ctx, _ptr(tail), ctypes.c_size_t(tail.size), _ptr(a), _ptr(b), _ptr(st), len(st)))
+        return st[:n]
+
+    def apply_tail_states(self, state_type: np.ndarray):
+        st = np.ascontiguousarray(state_type, np.int32).reshape(-1, 2)
+        _check(self._lib.scvod_apply_tail_states(self._ctx, _ptr(st), len(st)))
 
     def intialization(self, poses: np.ndarray) -> int:
         """SSC::intialization (reference src/ssc.cpp:1148-1248, spelling as in the reference): fuses the clusters of the base frame

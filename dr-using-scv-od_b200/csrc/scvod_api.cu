@@ -238,6 +238,7 @@ struct scvod_ctx {
   std::vector<std::unique_ptr<PersistBatch>> batch_pool;  // released batches kept for reuse (no cudaMalloc in steady state)
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
+  bool head_tracked = false;  // frame 0 has been frame_next_ of an imported tail (scvod_track_from_tail)
   cudaEvent_t sync_event = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning (see wait_stream)
   // scvod_prefetch_scans: upload of the next batch on a private stream, consumed by the next scvod_push_scans of the same buffer
   cudaStream_t copy_stream = nullptr;
@@ -918,6 +919,7 @@ extern "C" int scvod_reset_frames(scvod_ctx* c) {
   c->batches.clear();
   c->frames.clear();
   c->tracked = 0;
+  c->head_tracked = false;
   c->track_name = 0;
   c->tout_cur = 0;
   c->have_init = false;
@@ -1179,18 +1181,9 @@ static void build_remap(scvod_ctx* c, size_t ci, const std::vector<int>& nlabel,
   }
 }
 
-static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float* pose_pre, const float* pose_next) {
-  PROF("track_pair total");
+// tracking(frame_pre_, frame_next_) for the car clusters `cars` of frame_pre_, given in cluster_set iteration order
+static int track_cars(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float T[12], std::vector<HCluster*>& cars) {
   const scvod_params& P = c->hp.p;
-  float T[12];
-  relative_pose(pose_next, pose_pre, T);
-  // car clusters of frame_pre_ in cluster_set order (ssc.cpp:1261-1264)
-  std::vector<HCluster*> cars;
-  {
-    PROF("  track: prepare");
-    for (auto& cs : pre.fc.cluster_set)
-      if (cs.second.type == P.car) cars.push_back(&cs.second);
-  }
   std::vector<size_t> cstart;
   const int out_buf = 1 - c->tout_cur;
   {
@@ -1301,6 +1294,20 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
   return SCVOD_OK;
 }
 
+static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float* pose_pre, const float* pose_next) {
+  PROF("track_pair total");
+  float T[12];
+  relative_pose(pose_next, pose_pre, T);
+  // car clusters of frame_pre_ in cluster_set order (ssc.cpp:1261-1264)
+  std::vector<HCluster*> cars;
+  {
+    PROF("  track: prepare");
+    for (auto& cs : pre.fc.cluster_set)
+      if (cs.second.type == c->hp.p.car) cars.push_back(&cs.second);
+  }
+  return track_cars(c, pre, next, T, cars);
+}
+
 extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
   if (!c || !poses6) return fail(SCVOD_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
@@ -1310,6 +1317,155 @@ extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
     if (rc) return rc;
     c->tracked = i + 1;
   }
+  return SCVOD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain hand-off between contexts: tracking(k, k+1) only reads, of frame k, the clouds of its car clusters in
+// cluster_set order (ssc.cpp:1261-1275) and writes their state / type back.  A sequence that is cut into chunks owned by different
+// contexts (workers, GPUs, processes) therefore keeps ONE unbroken chain (ssc.cpp:1450-1452) if the tail of chunk i is exported,
+// tracked into the head of chunk i+1 by that chunk's context, and the resulting states are applied to the tail.
+// Tail layout (host bytes): int32 {magic, ncars, npts, SSC::name}, ncars x int32 {name, track_id, npts, 0}, npts x float4.
+// ---------------------------------------------------------------------------------------------
+static const int32_t kTailMagic = 0x5C7A11;
+
+extern "C" int scvod_export_tail(scvod_ctx* c, void* buf, size_t cap, size_t* nbytes) {
+  if (!c || !nbytes) return fail(SCVOD_ERR_ARG, "null argument");
+  if (c->frames.empty()) return fail(SCVOD_ERR_STATE, "no frames");
+  if (c->tracked + 1 != (int)c->frames.size()) return fail(SCVOD_ERR_STATE, "scvod_export_tail: track the context's own frames first");
+  CU(cudaSetDevice(c->device));
+  FrameHost& fr = c->frames.back();
+  PersistBatch& pb = *c->batches[fr.batch];
+  std::vector<HCluster*> cars;
+  for (auto& cs : fr.fc.cluster_set)
+    if (cs.second.type == c->hp.p.car) cars.push_back(&cs.second);
+  size_t npts = 0;
+  for (HCluster* cl : cars) npts += (size_t)std::max(0, cl->npts) + (size_t)std::max(0, cl->n_carried);
+  const size_t need = sizeof(int32_t) * 4 * (1 + cars.size()) + sizeof(float) * 4 * npts;
+  *nbytes = need;
+  if (!buf) return SCVOD_OK;  // size query
+  if (cap < need) return fail(SCVOD_ERR_CAPACITY, "scvod_export_tail: buffer too small");
+  int32_t* hdr = (int32_t*)buf;
+  hdr[0] = kTailMagic;
+  hdr[1] = (int32_t)cars.size();
+  hdr[2] = (int32_t)npts;
+  hdr[3] = c->track_name;
+  float* out = (float*)(hdr + 4 * (1 + cars.size()));
+  // the frame's apri points and voxel CSR (one scan: ~1 MB) come to the host once
+  std::vector<float> xyzi((size_t)std::max(1, fr.n_apri) * 4);
+  std::vector<int32_t> vox_off((size_t)std::max(1, fr.n_vox)), vox_pts((size_t)std::max(1, fr.n_apri));
+  CU(cudaStreamSynchronize(c->stream));
+  if (fr.n_apri > 0) {
+    CU(cudaMemcpy(xyzi.data(), pb.apri_xyzi.p + fr.base, sizeof(float4) * fr.n_apri, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vox_pts.data(), pb.vox_pts.p + fr.base, sizeof(int32_t) * fr.n_apri, cudaMemcpyDeviceToHost));
+  }
+  if (fr.n_vox > 0) CU(cudaMemcpy(vox_off.data(), pb.vox_off.p + fr.base, sizeof(int32_t) * fr.n_vox, cudaMemcpyDeviceToHost));
+  const bool taint = !fr.fc.tvox.empty();
+  size_t pos = 0;
+  std::vector<int> ms;
+  for (size_t i = 0; i < cars.size(); ++i) {
+    HCluster& cl = *cars[i];
+    const size_t pos0 = pos;
+    // own points: part by part (the concatenation order of fusions, ssc.cpp:617,1409), ascending apri index inside a part (:360-380)
+    const int nparts = (int)cl.part_end.size();
+    int vi = 0;
+    for (int part = 0; part < nparts; ++part) {
+      ms.clear();
+      for (; vi < cl.part_end[part]; ++vi) {
+        const int v = cl.occupy_voxels[vi];
+        if (taint && fr.fc.tainted(v)) continue;
+        for (int j = 0; j < fr.vox_cnt[v]; ++j) ms.push_back(vox_pts[vox_off[v] + j]);
+      }
+      for (auto& tu : cl.tunits)
+        if (tu.part == part) ms.insert(ms.end(), fr.fc.subgroups[tu.sg].pts.begin(), fr.fc.subgroups[tu.sg].pts.end());
+      std::sort(ms.begin(), ms.end());
+      for (int m : ms) {
+        std::memcpy(out + 4 * pos, xyzi.data() + 4 * (size_t)m, sizeof(float) * 4);
+        ++pos;
+      }
+    }
+    if ((int)(pos - pos0) != std::max(0, cl.npts)) return fail(SCVOD_ERR_STATE, "internal: cluster point count disagrees with its voxels");
+    for (auto& cr : cl.carried) {  // clouds appended by tracking (ssc.cpp:1382), device resident
+      if (cr.second <= 0) continue;
+      CU(cudaMemcpy(out + 4 * pos, c->d_tout[c->tout_cur].p + cr.first, sizeof(float4) * cr.second, cudaMemcpyDeviceToHost));
+      pos += cr.second;
+    }
+    int32_t* rec = hdr + 4 * (1 + i);
+    rec[0] = cl.name;
+    rec[1] = cl.track_id;
+    rec[2] = (int32_t)(pos - pos0);
+    rec[3] = 0;
+  }
+  if (pos != npts) return fail(SCVOD_ERR_STATE, "internal: exported point count");
+  return SCVOD_OK;
+}
+
+extern "C" int scvod_track_from_tail(scvod_ctx* c, const void* tail, size_t nbytes, const float pose_pre6[6], const float pose_next6[6],
+                                     int32_t* state_type, int cap) {
+  if (!c || !tail || !pose_pre6 || !pose_next6) return fail(SCVOD_ERR_ARG, "null argument");
+  if (c->frames.empty()) return fail(SCVOD_ERR_STATE, "scvod_track_from_tail: push the chunk's scans first");
+  if (c->tracked != 0 || c->head_tracked) return fail(SCVOD_ERR_STATE, "scvod_track_from_tail: the head frame has already been tracked");
+  const int32_t* hdr = (const int32_t*)tail;
+  if (nbytes < sizeof(int32_t) * 4 || hdr[0] != kTailMagic || hdr[1] < 0 || hdr[2] < 0) return fail(SCVOD_ERR_ARG, "not a tail buffer");
+  const int ncars = hdr[1], npts = hdr[2];
+  if (nbytes < sizeof(int32_t) * 4 * (1 + (size_t)ncars) + sizeof(float) * 4 * (size_t)npts) return fail(SCVOD_ERR_ARG, "truncated tail buffer");
+  if (state_type && cap < ncars) return fail(SCVOD_ERR_CAPACITY, "state buffer too small");
+  CU(cudaSetDevice(c->device));
+  c->track_name = hdr[3];  // SSC::name runs on along the chain (ssc.cpp:1267-1271)
+  const float* pts = (const float*)(hdr + 4 * (1 + (size_t)ncars));
+  // the imported clouds become "carried" ranges of a stand-in frame_pre_
+  const int in_buf = c->tout_cur;
+  CU(c->d_tout[in_buf].alloc((size_t)std::max(1, npts)));
+  if (npts > 0) CU(cudaMemcpyAsync(c->d_tout[in_buf].p, pts, sizeof(float4) * (size_t)npts, cudaMemcpyHostToDevice, c->stream));
+  FrameHost& next = c->frames[0];
+  FrameHost pre;
+  pre.batch = next.batch;
+  pre.slot = next.slot;
+  pre.base = next.base;
+  pre.csr_base = 0;
+  std::vector<HCluster> store((size_t)ncars);
+  std::vector<HCluster*> cars;
+  int off = 0;
+  for (int i = 0; i < ncars; ++i) {
+    const int32_t* rec = hdr + 4 * (1 + (size_t)i);
+    HCluster& cl = store[i];
+    cl.name = rec[0];
+    cl.track_id = rec[1];
+    cl.type = c->hp.p.car;
+    cl.npts = 0;
+    if (rec[2] > 0) cl.carried.push_back(std::make_pair(off, rec[2]));
+    cl.n_carried = rec[2];
+    off += rec[2];
+    cars.push_back(&cl);
+  }
+  if (off != npts) return fail(SCVOD_ERR_ARG, "tail buffer: point counts disagree");
+  float T[12];
+  relative_pose(pose_next6, pose_pre6, T);
+  int rc = track_cars(c, pre, next, T, cars);
+  CU(cudaStreamSynchronize(c->stream));  // the caller may free `tail` now
+  if (rc) return rc;
+  c->head_tracked = true;
+  if (state_type)
+    for (int i = 0; i < ncars; ++i) {
+      state_type[2 * i] = store[i].state;
+      state_type[2 * i + 1] = store[i].type;
+    }
+  return ncars;
+}
+
+extern "C" int scvod_apply_tail_states(scvod_ctx* c, const int32_t* state_type, int n) {
+  if (!c || (!state_type && n > 0)) return fail(SCVOD_ERR_ARG, "null argument");
+  if (c->frames.empty()) return fail(SCVOD_ERR_STATE, "no frames");
+  FrameHost& fr = c->frames.back();
+  std::vector<HCluster*> cars;
+  for (auto& cs : fr.fc.cluster_set)
+    if (cs.second.type == c->hp.p.car) cars.push_back(&cs.second);
+  if ((int)cars.size() != n) return fail(SCVOD_ERR_STATE, "scvod_apply_tail_states: the tail frame changed since it was exported");
+  for (int i = 0; i < n; ++i) {
+    cars[i]->state = state_type[2 * i];
+    cars[i]->type = state_type[2 * i + 1];
+  }
+  c->batches[fr.batch]->labels_current = false;
   return SCVOD_OK;
 }
 

@@ -28,11 +28,63 @@ def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
 def chunk_sequence(n_scans: int, chunk: int) -> List[Tuple[int, int]]:
     """Cuts a sequence of n_scans frames into chunks of at most ``chunk`` consecutive frames.
 
-    The tracking chain runs inside a chunk; at a cut the first frame of the next chunk is tracked only against its
-    own successor (documented deviation from one unbroken chain)."""
+    Chunks are units of work (one context each).  For ONE sequence the chain is kept unbroken across them with the tail hand-off
+    (``track_chunks_as_one_chain`` / ``ChainLink``); treating every chunk as its own sequence instead drops one tracking(k, k+1)
+    per cut (DESIGN.md §6 has the measured label difference)."""
     if chunk <= 0:
         raise ValueError("chunk must be positive")
     return [(s, min(n_scans, s + chunk)) for s in range(0, n_scans, chunk)]
+
+
+def track_chunks_as_one_chain(contexts: Sequence, poses: Sequence) -> None:
+    """One unbroken tracking chain (reference src/ssc.cpp:1450-1452) over consecutive chunks that live in different contexts of
+    this process: ``contexts[i]`` holds chunk i's frames (pushed, not yet tracked), ``poses[i]`` its [n_i, 6] poses.  The pair
+    that straddles a cut is tracked by the later chunk's context from the exported tail of the earlier one."""
+    for i, ssc in enumerate(contexts):
+        if i > 0:
+            st = ssc.track_from_tail(contexts[i - 1].export_tail(), poses[i - 1][-1], poses[i][0])
+            contexts[i - 1].apply_tail_states(st)
+        ssc.tracking(poses[i])
+
+
+class ChainLink:
+    """The same hand-off between ranks (one process per GPU): the tail of rank r's last chunk goes to rank r + 1, the (state, type)
+    pairs come back.  Two point-to-point messages per cut (a length, then the bytes; < 4 MB: a frame's car clusters), so the
+    chain stays a chain — ranks do their per-scan stages concurrently and their tracking in rank order.  Works over ``gloo`` (CPU
+    tensors) and ``nccl`` (the bytes are staged through a CUDA tensor)."""
+
+    def __init__(self, device: torch.device = torch.device("cpu"), group=None):
+        self.device = device
+        self.group = group
+
+    def _send(self, arr, dst: int):
+        t = torch.from_numpy(arr.view("uint8").reshape(-1).copy())
+        n = torch.tensor([t.numel()], dtype=torch.int64)
+        dist.send(n.to(self.device), dst, group=self.group)
+        if t.numel():
+            dist.send(t.to(self.device), dst, group=self.group)
+
+    def _recv(self, src: int):
+        n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        dist.recv(n, src, group=self.group)
+        t = torch.empty(int(n.item()), dtype=torch.uint8, device=self.device)
+        if t.numel():
+            dist.recv(t, src, group=self.group)
+        return t.cpu().numpy()
+
+    def send_tail(self, tail, dst: int):
+        self._send(tail, dst)
+
+    def recv_tail(self, src: int):
+        return self._recv(src)
+
+    def send_states(self, state_type, dst: int):
+        import numpy as np
+
+        self._send(np.ascontiguousarray(state_type, np.int32), dst)
+
+    def recv_states(self, src: int):
+        return self._recv(src).view("int32").reshape(-1, 2)
 
 
 def shard_chunks(n_scans: int, chunk: int, world: int, rank: int) -> List[Tuple[int, int]]:

@@ -21,6 +21,7 @@
 #ifndef SCVOD_H_
 #define SCVOD_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -246,6 +247,23 @@ int scvod_host_segment_pts(const scvod_params* p, int V, const int32_t* vox_cnt,
                            int32_t* name_stage0, int32_t* name_stage1, int32_t* name_stage2, int32_t* tp_stage,
                            int32_t n_clusters[3], int cap, int32_t* cluster_name, int32_t* cluster_type,
                            int32_t* cluster_npts, int32_t* cluster_nvox, int32_t* max_name);
+
+/* ---- chain hand-off between contexts (one unbroken tracking chain over a sequence cut into chunks) ------------------------
+ * SSC::segDF tracks a whole sequence as ONE chain: tracking(frame_set[i], frame_set[i+1]) for every i (ssc.cpp:1450-1452).  When the
+ * sequence is cut into chunks owned by different contexts (workers of one GPU, GPUs of a box, processes), the pair that straddles a
+ * cut is run by the context that owns the later chunk: tracking() only reads, of frame_pre_, the clouds of its car clusters in
+ * cluster_set order and writes their state / type back (ssc.cpp:1261-1275, 1324-1397).
+ *   scvod_export_tail      serialises that view of the context's LAST frame (after its own frames have been tracked) into host memory:
+ *                          int32 {magic, ncars, npts, SSC::name}, ncars x int32 {name, track_id, npts, 0}, npts x float4 xyzi
+ *                          (own points part by part, then the clouds carried along the chain).  buf == NULL: size query.
+ *   scvod_track_from_tail  runs tracking(tail, frame 0) in the context that holds the next chunk (before its own scvod_track): frame 0 is
+ *                          mutated exactly as in the unbroken chain (splits, fusions, carried clouds, track ids, SSC::name).  Writes
+ *                          (state, type) of every exported car cluster to state_type[2 * ncars]; returns ncars.
+ *   scvod_apply_tail_states stores those back into the exporting context's last frame (its labels are refreshed on the next read). */
+int scvod_export_tail(scvod_ctx* ctx, void* buf, size_t cap, size_t* nbytes);
+int scvod_track_from_tail(scvod_ctx* ctx, const void* tail, size_t nbytes, const float pose_pre6[6], const float pose_next6[6],
+                          int32_t* state_type, int cap);
+int scvod_apply_tail_states(scvod_ctx* ctx, const int32_t* state_type, int n);
 
 /* ---- helpers shared by tests and the bench ---------------------------------------------------- */
 /* trans_next.inverse() * trans_pre of SSC::tracking (ssc.cpp:1255-1257) as 12 floats row-major 3x4. */

@@ -587,3 +587,61 @@ def test_benchmarked_chunk_matches_oracle(pkg):
     s.close()
     t.close()
     orc.close()
+
+
+def test_chunked_sequence_with_tail_handoff_is_one_chain(pkg, oracle):
+    """A 40-frame sequence cut into chunks of 7 frames held by different contexts: with the tail hand-off (scvod_export_tail ->
+    scvod_track_from_tail -> scvod_apply_tail_states) labels, cluster states and track ids equal the oracle's ONE unbroken chain
+    (ssc.cpp:1450-1452); without it, every cut loses the labels of one frame pair."""
+    par = conftest.load_parallel()
+    n, chunk = 40, 7
+    scans, poses = zip(*[pkg.synth_scan(conftest.SEED + 1, k, rings=32, cols=900) for k in range(n)])
+    poses = np.stack(poses)
+    for sc in scans:
+        oracle.push_scan(sc)
+    oracle.track(poses)
+    cuts = par.chunk_sequence(n, chunk)
+    ctxs = [pkg.SSC(pkg.semantickitti_params(), device=0, max_points=32 * 900, max_batch=chunk) for _ in cuts]
+    for (a, b), s in zip(cuts, ctxs):
+        s.process(scans[a:b])
+    par.track_chunks_as_one_chain(ctxs, [poses[a:b] for a, b in cuts])
+    for (a, b), s in zip(cuts, ctxs):
+        for f in range(a, b):
+            assert np.array_equal(s.frame_labels(f - a), oracle.labels(f)), f"frame {f}"
+            cg, co = s.frame_clusters(f - a), oracle.clusters(f)
+            for k in ("name", "type", "state", "npts", "nvox"):
+                assert np.array_equal(cg[k], co[k]), (f, k)
+    # the cut chain, for the record: only frames next to a cut may differ, and at least one does in this sequence
+    differ = []
+    for (a, b), s in zip(cuts, ctxs):
+        s.reset()
+        lab = s.segDF(scans[a:b], poses[a:b])
+        differ += [f for f in range(a, b) if not np.array_equal(lab[f - a], oracle.labels(f))]
+    assert len(differ) > 0
+    for s in ctxs:
+        s.close()
+
+
+def test_tail_handoff_with_aliased_voxels_and_errors(pkg):
+    params = pkg.semantickitti_params()
+    scans, poses, _ = tainted_sequence(pkg, conftest.SEED + 62, 9, 32, 900)
+    orc = conftest.Oracle(params)
+    for sc in scans:
+        orc.push_scan(sc)
+    orc.track(poses)
+    par = conftest.load_parallel()
+    a = pkg.SSC(params, device=0, max_points=32 * 900, max_batch=8)
+    b = pkg.SSC(params, device=0, max_points=32 * 900, max_batch=8)
+    a.process(scans[:5])
+    b.process(scans[5:])
+    with pytest.raises(pkg.ScvodError):
+        a.export_tail()  # its own frames are not tracked yet
+    par.track_chunks_as_one_chain([a, b], [poses[:5], poses[5:]])
+    with pytest.raises(pkg.ScvodError):
+        b.track_from_tail(a.export_tail(), poses[4], poses[5])  # head already tracked
+    for f in range(9):
+        s, g = (a, f) if f < 5 else (b, f - 5)
+        assert np.array_equal(s.frame_labels(g), orc.labels(f)), f
+    a.close()
+    b.close()
+    orc.close()

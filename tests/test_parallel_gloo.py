@@ -93,3 +93,38 @@ def test_single_process_gather_and_label_merge():
     assert counts.tolist() == [5] and torch.equal(g.compact(), sub[:5])
     labels = par.merge_labels_host([[np.array([1]), np.array([2])], [np.array([3])]], [(0, 0, 0), (0, 1, 1), (1, 0, 2)])
     assert [int(a[0]) for a in labels] == [1, 2, 3]
+
+
+def _link_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = load_parallel()
+    link = par.ChainLink()
+    rng = np.random.default_rng(5)
+    tail = rng.integers(0, 255, 4 * 4 * 3 + 16 * 1000, dtype=np.uint8)  # header + 2 clusters + 1000 points worth of bytes
+    states = np.array([[1, 2], [0, 1]], np.int32)
+    ok = True
+    if rank == 0:  # owner of the earlier chunk: sends its tail, waits for the states
+        link.send_tail(tail, 1)
+        ok &= np.array_equal(link.recv_states(1), states)
+        link.send_tail(np.zeros(0, np.uint8), 1)  # an empty tail travels too
+    else:
+        ok &= np.array_equal(link.recv_tail(0), tail)
+        link.send_states(states, 0)
+        ok &= link.recv_tail(0).size == 0
+    results[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_chain_link_world_size_2_gloo():
+    """Transport of the chain hand-off between ranks (the tail of rank r's last frame -> rank r + 1, states back)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_link_worker, args=(2, port, results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
