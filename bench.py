@@ -237,6 +237,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="stream", choices=["stream", "sequence", "parkinglot_gicp", "stress"],
+                    help="stream = BASELINE configs[1] (default, the headline); sequence = configs[3]; parkinglot_gicp = configs[2]; stress = configs[4] "
+                         "(tools/bench_workloads.py)")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e, roofline, cpu_baseline and parity legs; prints value only")
+    ap.add_argument("--skip-tracking", action="store_true", help="ablation: per-scan stages only (INVALID as a bench number)")
+    ap.add_argument("--seq-scans", type=int, default=1000, help="--workload sequence: scans in the sequence")
     ap.add_argument("--scans-per-step", type=int, default=64, help="scans per sequence chunk; a step is one chunk per worker")
     ap.add_argument("--pool", type=int, default=3, help="distinct input batches rotated through (pool > L2)")
     ap.add_argument("--workers", type=int, default=0, help="independent sequence chunks processed side by side per GPU")
@@ -249,6 +255,11 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "stream":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_workloads
+
+        return bench_workloads.run(args, sys.modules[__name__])
 
     import torch
     import torch.distributed as dist
@@ -316,7 +327,8 @@ def main():
                 ssc.prefetch_host_ptr(nb["host"].data_ptr(), nb["off"])
         else:
             ssc.process_device(b["dev"].data_ptr(), b["off"])
-        ssc.tracking(b["poses"])
+        if not args.skip_tracking:
+            ssc.tracking(b["poses"])
         if host_io:
             ssc.labels_into(0, S, wk.labels_host.data_ptr(), wk.labels_host.numel())
         else:
@@ -401,6 +413,16 @@ def main():
         return par.max_over_ranks(secs, dev), sum(wk.ssc.kernel_launches for wk in workers) - l0, clocks, rep
 
     secs_dev, launches, clocks, _ = timed(False, False)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": world * W * S * args.steps / secs_dev, "unit": UNIT, "workers": W, "ms_per_step": 1000.0 * secs_dev / args.steps,
+                              "skip_tracking": args.skip_tracking, "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        for wk in workers:
+            wk.ssc.close()
+        return 0
     secs_e2e, _, clocks_e2e, _ = timed(True, False)
     # roofline block: per-kernel CUDA-event durations need launches that do not overlap with other streams, so
     # they are measured in a dedicated pass of the same steps on ONE worker (events on that worker's stream)

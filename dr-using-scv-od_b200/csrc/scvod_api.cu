@@ -25,7 +25,14 @@
 using namespace scvod;
 
 static thread_local std::string g_err;
-static std::atomic<int> g_live_contexts(0);  // contexts alive in this process: sizes the footprint of the latency-bound tracking kernel
+static std::atomic<int> g_live_contexts(0);  // contexts alive in this process
+// contexts that are inside a tracking chain right now: sizes the footprint of the latency-bound tracking kernel (a lone chain may
+// fill the GPU for the shortest round trip; many concurrent chains take one CTA per SM each so that their kernels co-run)
+static std::atomic<int> g_tracking_now(0);
+struct TrackingScope {
+  TrackingScope() { g_tracking_now.fetch_add(1); }
+  ~TrackingScope() { g_tracking_now.fetch_sub(1); }
+};
 static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -1079,7 +1086,8 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
     PROF("    track: enqueue+wait+read");
     if (!use_runs) CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->stream));
     // one context: the kernel may fill the GPU (shortest latency); many contexts: one CTA per SM so that their kernels co-run
-    c->hp.track_ctas_per_sm = g_live_contexts.load() <= 2 ? 16 : g_live_contexts.load() <= 6 ? 4 : 1;
+    const int chains = g_tracking_now.load();
+    c->hp.track_ctas_per_sm = chains <= 2 ? 16 : chains <= 6 ? 4 : 1;
     c->launches += launch_track(c->hp, pbp.apri_xyzi.p + pre.base, pbp.vox_off.p + pre.base, pbp.vox_pts.p + pre.base, c->d_tout[in_buf].p,
                                 use_runs ? nullptr : reinterpret_cast<const int4*>(c->d_treq.p), use_runs ? nullptr : c->d_treq.p + si * 4,
                                 (int)si, use_runs ? &runs : nullptr, pbp.csr.p, pbp.csr.p + pbp.csr_n, pbp.csr.p + 2 * pbp.csr_n,
@@ -1311,6 +1319,7 @@ static int track_pair(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
 extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
   if (!c || !poses6) return fail(SCVOD_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
+  TrackingScope in_chain;
   int nf = std::min<int>((int)c->frames.size(), nposes);
   for (int i = c->tracked; i + 1 < nf; ++i) {
     int rc = track_pair(c, c->frames[i], c->frames[i + 1], poses6 + 6 * i, poses6 + 6 * (i + 1));
@@ -1441,6 +1450,7 @@ extern "C" int scvod_track_from_tail(scvod_ctx* c, const void* tail, size_t nbyt
   if (off != npts) return fail(SCVOD_ERR_ARG, "tail buffer: point counts disagree");
   float T[12];
   relative_pose(pose_next6, pose_pre6, T);
+  TrackingScope in_chain;
   int rc = track_cars(c, pre, next, T, cars);
   CU(cudaStreamSynchronize(c->stream));  // the caller may free `tail` now
   if (rc) return rc;
