@@ -70,7 +70,7 @@ EXPORTS = (
     "scvod_atan2f_device", "scvod_relative_pose", "scvod_synth_scan", "scvod_host_segment", "scvod_host_segment_pts", "scvod_set_stream", "scvod_kernel_timing", "scvod_kernel_timing_report", "scvod_get_stat",
     "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
-    "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states",
+    "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states", "scvod_load_kitti", "scvod_load_kitti_dev",
 )
 
 _lib = None
@@ -290,6 +290,26 @@ class SSC:
     def tracking(self, poses: np.ndarray):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
         _check(self._lib.scvod_track(self._ctx, _ptr(poses), len(poses)))
+
+    # -- loader front end (SSC::getCloud, reference src/ssc.cpp:1060-1111) ----------------------
+    def load_kitti(self, raw_scans: Sequence[np.ndarray], labels: Optional[Sequence[np.ndarray]] = None, leaf: float = 0.08,
+                   max_intensity: float = 255.0) -> List[np.ndarray]:
+        """Label mask (semantic label 0 / 1 dropped), intensity x max_intensity, 0.08 m VoxelGrid on the device.  raw_scans are
+        the .bin contents ([n, 4] float32), labels the .label contents ([n] uint32) or None.  Returns the clouds process() takes."""
+        raw = [np.ascontiguousarray(r, np.float32).reshape(-1, 4) for r in raw_scans]
+        off = np.zeros(len(raw) + 1, np.int64)
+        off[1:] = np.cumsum([len(r) for r in raw])
+        flat = np.ascontiguousarray(np.concatenate(raw, axis=0)) if raw else np.zeros((0, 4), np.float32)
+        lab = None
+        if labels is not None:
+            lab = np.ascontiguousarray(np.concatenate([np.asarray(l, np.uint32).reshape(-1) for l in labels])) if raw else np.zeros(0, np.uint32)
+            if len(lab) != len(flat):
+                raise ValueError("labels and points disagree in length")
+        out = np.zeros((max(len(flat), 1), 4), np.float32)
+        ooff = np.zeros(len(raw) + 1, np.int64)
+        _check(self._lib.scvod_load_kitti(self._ctx, _ptr(flat), _ptr(lab), _ptr(off), len(raw), ctypes.c_float(leaf), ctypes.c_float(max_intensity),
+                                          _ptr(out), _ptr(ooff)))
+        return [out[ooff[b]:ooff[b + 1]].copy() for b in range(len(raw))]
 
     # -- one unbroken chain over a sequence cut into chunks (include/scvod.h "chain hand-off") ----
     def export_tail(self) -> np.ndarray:

@@ -248,6 +248,24 @@ int scvod_host_segment_pts(const scvod_params* p, int V, const int32_t* vox_cnt,
                            int32_t n_clusters[3], int cap, int32_t* cluster_name, int32_t* cluster_type,
                            int32_t* cluster_npts, int32_t* cluster_nvox, int32_t* max_name);
 
+/* ---- loader front end on the device ------------------------------------------------------------------
+ * What SSC::getCloud does to a SemanticKITTI scan before process() sees it (reference src/ssc.cpp:1060-1111): points whose label
+ * (low 16 bits) is 0 or 1 are dropped (:1063), intensity is multiplied by max_intensity (:1071), and the cloud goes through
+ * pcl::VoxelGrid<PointXYZI> with leaf 0.08 m (:1108-1111; PCL 1.8 voxel_grid.hpp: one centroid per occupied leaf, in ascending
+ * leaf index).  raw_xyzi = the .bin file contents (x, y, z, intensity in [0, 1]), labels = the .label file contents (NULL: keep
+ * every point, as for PCD input).  Mask, leaf indices, output order and leaf populations are exact; a centroid is the float sum
+ * of its leaf's points in ascending input index (the reference leaves that order to std::sort, which is unstable), so leaves
+ * with >= 3 points may differ from the reference in the last bits.
+ *   scvod_load_kitti      host buffers; out_xyzi (room for every input point) receives the scans packed one after the other and
+ *                         out_offsets[nscans + 1] their boundaries: both can be handed to scvod_push_scans as they are.
+ *   scvod_load_kitti_dev  device buffers; scan b is written at out + (offsets[b] - offsets[0]); counts4[4 b] = output points,
+ *                         [4 b + 1] = points that passed the mask, [4 b + 2] = 1 if the leaf grid overflowed an int and the
+ *                         masked scan was passed through unchanged (PCL's "leaf size is too small" path). */
+int scvod_load_kitti(scvod_ctx* ctx, const float* raw_xyzi, const uint32_t* labels, const int64_t* offsets, int nscans, float leaf,
+                     float max_intensity, float* out_xyzi, int64_t* out_offsets);
+int scvod_load_kitti_dev(scvod_ctx* ctx, const void* raw_xyzi_dev, const uint32_t* labels_dev, const int64_t* offsets, int nscans,
+                         float leaf, float max_intensity, void* out_xyzi_dev, int32_t* counts4);
+
 /* ---- chain hand-off between contexts (one unbroken tracking chain over a sequence cut into chunks) ------------------------
  * SSC::segDF tracks a whole sequence as ONE chain: tracking(frame_set[i], frame_set[i+1]) for every i (ssc.cpp:1450-1452).  When the
  * sequence is cut into chunks owned by different contexts (workers of one GPU, GPUs of a box, processes), the pair that straddles a
