@@ -57,6 +57,23 @@ class GicpResult(ctypes.Structure):
                 "iterations": int(self.iterations), "n_corr": int(self.n_corr), "converged": bool(self.converged)}
 
 
+class EvalResult(ctypes.Structure):
+    """scvod_eval_result (tool/analysis.py:124-194)."""
+
+    _fields_ = ([(n, ctypes.c_int64) for n in ("gt_static", "gt_dynamic", "est_static", "est_dynamic", "preserved", "static_preserved", "dynamic_preserved")]
+                + [(n, ctypes.c_double) for n in ("preservation_rate", "rejection_rate", "f1")]
+                + [("gt_per_class", ctypes.c_int64 * 8), ("est_per_class", ctypes.c_int64 * 8)])
+
+    def as_dict(self) -> dict:
+        d = {n: getattr(self, n) for n, _ in self._fields_[:10]}
+        d["gt_per_class"] = list(self.gt_per_class)
+        d["est_per_class"] = list(self.est_per_class)
+        return d
+
+
+DYNAMIC_CLASSES = (252, 253, 254, 255, 256, 257, 258, 259)  # tool/analysis.py:6, config/semantickitti.yaml dynamic_label_
+
+
 class Grid(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("range_num", "sector_num", "azimuth_num", "bin_num")]
 
@@ -71,6 +88,7 @@ EXPORTS = (
     "scvod_gicp_default_params", "scvod_gicp_set_target", "scvod_gicp_set_target_dev", "scvod_gicp_align", "scvod_gicp_align_dev",
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
     "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states", "scvod_load_kitti", "scvod_load_kitti_dev",
+    "scvod_evaluate_map", "scvod_evaluate_confusion", "scvod_synth_scan_labeled",
 )
 
 _lib = None
@@ -152,6 +170,17 @@ def synth_scan(seed: int, scan_id: int, rings: int = 64, cols: int = 1800):
     if load_synth_library().scvod_synth_scan(ctypes.c_uint64(seed), int(scan_id), int(rings), int(cols), _ptr(buf), ctypes.byref(n), _ptr(pose)) < 0:
         raise ScvodError("scvod_synth_scan: bad arguments")
     return np.ascontiguousarray(buf[: n.value]), pose
+
+
+def synth_scan_labeled(seed: int, scan_id: int, rings: int = 64, cols: int = 1800):
+    """synth_scan plus a SemanticKITTI-style label per point (252 in the low 16 bits = moving car).  Returns (xyzi, pose6, labels)."""
+    buf = np.empty((rings * cols, 4), np.float32)
+    lab = np.zeros(rings * cols, np.uint32)
+    n = ctypes.c_int(0)
+    pose = np.zeros(6, np.float32)
+    if load_synth_library().scvod_synth_scan_labeled(ctypes.c_uint64(seed), int(scan_id), int(rings), int(cols), _ptr(buf), ctypes.byref(n), _ptr(pose), _ptr(lab)) < 0:
+        raise ScvodError("scvod_synth_scan_labeled: bad arguments")
+    return np.ascontiguousarray(buf[: n.value]), pose, np.ascontiguousarray(lab[: n.value])
 
 
 def relative_pose(pose_next: np.ndarray, pose_pre: np.ndarray) -> np.ndarray:
@@ -310,6 +339,31 @@ class SSC:
         _check(self._lib.scvod_load_kitti(self._ctx, _ptr(flat), _ptr(lab), _ptr(off), len(raw), ctypes.c_float(leaf), ctypes.c_float(max_intensity),
                                           _ptr(out), _ptr(ooff)))
         return [out[ooff[b]:ooff[b + 1]].copy() for b in range(len(raw))]
+
+    # -- quality measures (tool/analysis.py:124-194, src/evaluate.cpp:79-145) --------------------
+    def evaluate_map(self, gt_xyzl: np.ndarray, est_xyzl: np.ndarray, voxelsize: float = 0.2, dynamic_classes: Sequence[int] = DYNAMIC_CLASSES,
+                     want_nn: bool = False):
+        """Preservation / rejection rate of an estimated static map against the ground-truth map (labels as floats in column 3)."""
+        gt = np.ascontiguousarray(gt_xyzl, np.float32).reshape(-1, 4)
+        est = np.ascontiguousarray(est_xyzl, np.float32).reshape(-1, 4)
+        dc = np.ascontiguousarray(dynamic_classes, np.int32)
+        res = EvalResult()
+        nn = np.zeros(max(len(gt), 1), np.int32) if want_nn else None
+        _check(self._lib.scvod_evaluate_map(self._ctx, _ptr(gt), ctypes.c_int64(len(gt)), _ptr(est), ctypes.c_int64(len(est)), ctypes.c_float(voxelsize),
+                                            _ptr(dc), len(dc), ctypes.byref(res), _ptr(nn)))
+        d = res.as_dict()
+        return (d, nn[: len(gt)]) if want_nn else d
+
+    def evaluate_confusion(self, pred_xyzs: np.ndarray, static_gt: np.ndarray, dynamic_gt: np.ndarray, r_hit: float = 0.15, r_miss: float = 0.1):
+        """TP / FN / TN / FN / not-shown counts and the per-point class (src/evaluate.cpp:79-145)."""
+        p = np.ascontiguousarray(pred_xyzs, np.float32).reshape(-1, 4)
+        s = np.ascontiguousarray(static_gt, np.float32).reshape(-1, 4)
+        d = np.ascontiguousarray(dynamic_gt, np.float32).reshape(-1, 4)
+        counts = np.zeros(5, np.int64)
+        per = np.zeros(max(len(p), 1), np.uint8)
+        _check(self._lib.scvod_evaluate_confusion(self._ctx, _ptr(p), ctypes.c_int64(len(p)), _ptr(s), ctypes.c_int64(len(s)), _ptr(d), ctypes.c_int64(len(d)),
+                                                  ctypes.c_float(r_hit), ctypes.c_float(r_miss), _ptr(counts), _ptr(per)))
+        return counts, per[: len(p)]
 
     # -- one unbroken chain over a sequence cut into chunks (include/scvod.h "chain hand-off") ----
     def export_tail(self) -> np.ndarray:

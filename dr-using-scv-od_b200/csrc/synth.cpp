@@ -60,13 +60,15 @@ void det_sincos(double a, double* s, double* c) {
 struct Box {
   double cx, cy, cyaw_c, cyaw_s, hx, hy, z0, z1;
   float base_intensity, noise_amp;
+  uint32_t sem;  // SemanticKITTI-style class of the object (scvod_synth_scan_labeled)
 };
 
 const double kGroundZ = -1.73;
 
 void add_box(std::vector<Box>& v, double cx, double cy, double yaw, double lx, double ly, double z0, double z1, float inten,
-             float amp) {
+             float amp, uint32_t sem = 0) {
   Box b;
+  b.sem = sem;
   b.cx = cx;
   b.cy = cy;
   det_sincos(yaw, &b.cyaw_s, &b.cyaw_c);
@@ -94,7 +96,7 @@ void build_scene(uint64_t seed, int k, double ex, std::vector<Box>& out) {
           double x = c * cell + 5.0 + 10.0 * j + r.sym() * 1.5;
           double y = sg * (5.2 + r.sym() * 0.4);
           add_box(out, x, y, r.sym() * 0.08, 4.2 + r.sym() * 0.3, 1.8 + r.sym() * 0.1, kGroundZ, kGroundZ + 1.5 + r.sym() * 0.1,
-                  90.f + (float)(r.sym() * 3.0), 1.0f);
+                  90.f + (float)(r.sym() * 3.0), 1.0f, 10u);
         }
       }
       // building wall segment
@@ -103,7 +105,7 @@ void build_scene(uint64_t seed, int k, double ex, std::vector<Box>& out) {
         if (r.uni() < 0.85) {
           double y = sg * (9.5 + r.uni() * 4.0);
           add_box(out, c * cell + 10.0, y, r.sym() * 0.03, 16.0 + r.uni() * 4.0, 0.3, kGroundZ, kGroundZ + 6.0 + r.uni() * 4.0,
-                  60.f + (float)(r.sym() * 3.0), (r.uni() < 0.5) ? 1.0f : 2.5f);
+                  60.f + (float)(r.sym() * 3.0), (r.uni() < 0.5) ? 1.0f : 2.5f, 50u);
         }
       }
       // pole
@@ -111,7 +113,7 @@ void build_scene(uint64_t seed, int k, double ex, std::vector<Box>& out) {
         Rng r(hash4(seed, uc, 30 + side, 0));
         if (r.uni() < 0.5) {
           add_box(out, c * cell + r.uni() * cell, sg * (7.5 + r.sym() * 0.3), 0.0, 0.3, 0.3, kGroundZ, kGroundZ + 5.0,
-                  150.f + (float)(r.sym() * 3.0), 1.0f);
+                  150.f + (float)(r.sym() * 3.0), 1.0f, 80u);
         }
       }
       // tree: trunk + crown
@@ -119,9 +121,9 @@ void build_scene(uint64_t seed, int k, double ex, std::vector<Box>& out) {
         Rng r(hash4(seed, uc, 35 + side, 0));
         if (r.uni() < 0.45) {
           double x = c * cell + r.uni() * cell, y = sg * (7.0 + r.uni() * 1.5);
-          add_box(out, x, y, 0.0, 0.4, 0.4, kGroundZ, kGroundZ + 2.6, 45.f + (float)(r.sym() * 3.0), 1.0f);
+          add_box(out, x, y, 0.0, 0.4, 0.4, kGroundZ, kGroundZ + 2.6, 45.f + (float)(r.sym() * 3.0), 1.0f, 71u);
           add_box(out, x, y, r.sym() * 0.7, 2.5 + r.uni(), 2.5 + r.uni(), kGroundZ + 2.5, kGroundZ + 5.0 + r.uni() * 2.0,
-                  30.f + (float)(r.sym() * 3.0), 5.0f);
+                  30.f + (float)(r.sym() * 3.0), 5.0f, 70u);
         }
       }
       // low bush / clutter
@@ -129,7 +131,7 @@ void build_scene(uint64_t seed, int k, double ex, std::vector<Box>& out) {
         Rng r(hash4(seed, uc, 40 + side, 0));
         if (r.uni() < 0.4) {
           add_box(out, c * cell + r.uni() * cell, sg * (8.5 + r.uni() * 1.5), r.sym() * 0.5, 1.0 + r.uni(), 0.8 + r.uni() * 0.6,
-                  kGroundZ, kGroundZ + 0.9 + r.uni() * 0.5, 35.f + (float)(r.sym() * 3.0), 4.0f);
+                  kGroundZ, kGroundZ + 0.9 + r.uni() * 0.5, 35.f + (float)(r.sym() * 3.0), 4.0f, 70u);
         }
       }
     }
@@ -144,7 +146,8 @@ void build_scene(uint64_t seed, int k, double ex, std::vector<Box>& out) {
     double x = m * 45.0 + r.uni() * 20.0 + v * k;
     if (std::fabs(x - ex) > 95.0) continue;
     double y = oncoming ? 1.9 : -1.9;
-    add_box(out, x, y, oncoming ? 3.14159265358979323846 : 0.0, 4.3, 1.8, kGroundZ, kGroundZ + 1.5, 95.f + (float)(r.sym() * 3.0), 1.0f);
+    add_box(out, x, y, oncoming ? 3.14159265358979323846 : 0.0, 4.3, 1.8, kGroundZ, kGroundZ + 1.5, 95.f + (float)(r.sym() * 3.0), 1.0f,
+            252u | ((uint32_t)((m % 60000 + 60000) % 60000 + 1) << 16));
   }
 }
 
@@ -160,7 +163,7 @@ inline float next_up(float f) {
 
 }  // namespace
 
-extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n, float* pose6) {
+static int synth_scan_impl(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n, float* pose6, uint32_t* labels) {
   if (!xyzi || !n || rings <= 0 || cols <= 0) return SCVOD_ERR_ARG;
   const double DEG = 3.14159265358979323846 / 180.0;
   // ego pose (world): +x at 1 m/scan, slow lateral and yaw drift
@@ -216,11 +219,13 @@ extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols,
       double best = 1e30;
       float inten = 0.f, amp = 0.f;
       bool ground = false;
+      uint32_t sem = 0;
       if (dz < 0.0) {
         best = kGroundZ / dz;
         inten = 20.f;
         amp = 1.0f;
         ground = true;
+        sem = 40u;
       }
       const std::vector<int>& cand = col_objs[c];
       for (size_t q = 0; q < cand.size(); ++q) {
@@ -247,6 +252,7 @@ extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols,
           inten = B.base_intensity;
           amp = B.noise_amp;
           ground = false;
+          sem = B.sem;
         }
       }
       if (best > 80.0) continue;
@@ -255,7 +261,11 @@ extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols,
       // reference include/patchwork.h:302-310) and ego-body returns inside min_range (patchwork.h:436)
       double uo = rng.uni();
       bool mirror = ground && uo < 0.0008;
-      if (uo > 0.9990) t = 1.2 + 1.4 * rng.uni();
+      if (uo > 0.9990) {
+        t = 1.2 + 1.4 * rng.uni();
+        sem = 1u;
+      }
+      if (mirror) sem = 1u;
       double px = t * dh * ac, py = t * dh * as, pz = t * dz;
       if (ground) pz += 0.02 * rng.gauss();
       if (mirror) pz = -3.2 - rng.uni();
@@ -266,6 +276,7 @@ extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols,
       xyzi[4 * cnt + 1] = (float)py;
       xyzi[4 * cnt + 2] = (float)pz;
       xyzi[4 * cnt + 3] = fi;
+      if (labels) labels[cnt] = sem;
       ++cnt;
     }
   }
@@ -284,4 +295,13 @@ extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols,
   }
   *n = cnt;
   return SCVOD_OK;
+}
+
+extern "C" int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n, float* pose6) {
+  return synth_scan_impl(seed, scan_id, rings, cols, xyzi, n, pose6, nullptr);
+}
+
+extern "C" int scvod_synth_scan_labeled(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n, float* pose6, uint32_t* labels) {
+  if (!labels) return SCVOD_ERR_ARG;
+  return synth_scan_impl(seed, scan_id, rings, cols, xyzi, n, pose6, labels);
 }

@@ -266,6 +266,26 @@ int scvod_load_kitti(scvod_ctx* ctx, const float* raw_xyzi, const uint32_t* labe
 int scvod_load_kitti_dev(scvod_ctx* ctx, const void* raw_xyzi_dev, const uint32_t* labels_dev, const int64_t* offsets, int nscans,
                          float leaf, float max_intensity, void* out_xyzi_dev, int32_t* counts4);
 
+/* ---- quality measures on the device ---------------------------------------------------------------------
+ * Clouds are host arrays of float[4] points.  For scvod_evaluate_map the 4th float is the SemanticKITTI label stored as a float (what
+ * the reference writes into PCD intensity, src/ssc.cpp:1079; low 16 bits = semantic class), dynamic_classes the moving classes
+ * (DYNAMIC_CLASSES of tool/analysis.py:6 = the YAML's dynamic_label_).  gt = ground-truth map, est = estimated static map.
+ * Restates evaluate() + calc_naive_preservation() (tool/analysis.py:124-194): nearest neighbour of every gt point in est; preserved
+ * when closer than voxelsize * sqrt(3) / 2.  nn_index (may be NULL) receives that neighbour's index per gt point, -1 if none. */
+typedef struct scvod_eval_result {
+  int64_t gt_static, gt_dynamic, est_static, est_dynamic;
+  int64_t preserved, static_preserved, dynamic_preserved;
+  double preservation_rate, rejection_rate, f1; /* PR %, RR %, F1 (tool/analysis.py:186-188) */
+  int64_t gt_per_class[8], est_per_class[8];    /* points of every dynamic class (the "R. R" table, :158-165) */
+} scvod_eval_result;
+int scvod_evaluate_map(scvod_ctx* ctx, const float* gt_xyzl, int64_t n_gt, const float* est_xyzl, int64_t n_est, float voxelsize,
+                       const int32_t* dynamic_classes, int n_classes, scvod_eval_result* out, int32_t* nn_index);
+/* evaluate() of src/evaluate.cpp:79-145.  pred = xyz + "predicted static" flag (4th float != 0, the reference's ori.g != 0), the two
+ * ground-truth clouds are searched with r_hit (0.15) first and r_miss (0.1) second.  counts5 = {TP, FN (predicted static, dynamic
+ * point nearby), TN, FN (predicted dynamic, static point nearby), not shown}; per_point (may be NULL) the class of every point. */
+int scvod_evaluate_confusion(scvod_ctx* ctx, const float* pred_xyzs, int64_t n, const float* static_gt_xyz, int64_t ns,
+                             const float* dynamic_gt_xyz, int64_t nd, float r_hit, float r_miss, int64_t counts5[5], uint8_t* per_point);
+
 /* ---- chain hand-off between contexts (one unbroken tracking chain over a sequence cut into chunks) ------------------------
  * SSC::segDF tracks a whole sequence as ONE chain: tracking(frame_set[i], frame_set[i+1]) for every i (ssc.cpp:1450-1452).  When the
  * sequence is cut into chunks owned by different contexts (workers of one GPU, GPUs of a box, processes), the pair that straddles a
@@ -292,6 +312,9 @@ void scvod_relative_pose(const float pose_next6[6], const float pose_pre6[6], fl
  * pose in pose6 (may be NULL). No libm calls: identical bytes on every host. */
 int scvod_synth_scan(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n,
                      float* pose6);
+/* The same scan with a SemanticKITTI-style label per point (low 16 bits: 40 road, 10 car, 50 building, 80 pole, 71 trunk,
+ * 70 vegetation, 252 moving car, 1 outlier; high 16 bits: object id): ground truth for the quality measures. */
+int scvod_synth_scan_labeled(uint64_t seed, int scan_id, int rings, int cols, float* xyzi, int* n, float* pose6, uint32_t* labels);
 
 #ifdef __cplusplus
 }
