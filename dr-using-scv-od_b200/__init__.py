@@ -89,6 +89,7 @@ EXPORTS = (
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
     "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states", "scvod_load_kitti", "scvod_load_kitti_dev",
     "scvod_evaluate_map", "scvod_evaluate_confusion", "scvod_synth_scan_labeled",
+    "scvod_knn_normals", "scvod_calibrate_intensity", "scvod_region_growing",
 )
 
 _lib = None
@@ -339,6 +340,32 @@ class SSC:
         _check(self._lib.scvod_load_kitti(self._ctx, _ptr(flat), _ptr(lab), _ptr(off), len(raw), ctypes.c_float(leaf), ctypes.c_float(max_intensity),
                                           _ptr(out), _ptr(ooff)))
         return [out[ooff[b]:ooff[b + 1]].copy() for b in range(len(raw))]
+
+    # -- k-NN normals / intensity calibration / region growing (src/ssc.cpp:98-153, 797-832) -------
+    def knn_normals(self, cloud: np.ndarray, k: int = 10):
+        """(normals [n,3], curvature [n], neighbours [n,k]) of pcl::NormalEstimation with setKSearch(k) on the cloud itself."""
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+        n = len(cloud)
+        nm = np.zeros((max(n, 1), 3), np.float32)
+        cv = np.zeros(max(n, 1), np.float32)
+        nb = np.zeros((max(n, 1), k), np.int32)
+        _check(self._lib.scvod_knn_normals(self._ctx, _ptr(cloud), n, int(k), _ptr(nm), _ptr(cv), _ptr(nb)))
+        return nm[:n], cv[:n], nb[:n]
+
+    def intensityCalibrationByCurvature(self, cloud: np.ndarray, search_num: int = 10, max_intensity: float = 255.0) -> np.ndarray:
+        """SSC::intensityCalibrationByCurvature (reference src/ssc.cpp:98-153); returns the calibrated copy."""
+        out = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4).copy()
+        _check(self._lib.scvod_calibrate_intensity(self._ctx, _ptr(out), len(out), int(search_num), ctypes.c_float(max_intensity)))
+        return out
+
+    def regionGrowing(self, cluster_cloud: np.ndarray):
+        """SSC::regionGrowing (reference src/ssc.cpp:797-832): (is_building, segment of every point, points in planar segments)."""
+        cloud = np.ascontiguousarray(cluster_cloud, np.float32).reshape(-1, 4)
+        n = len(cloud)
+        flag, planar = ctypes.c_int32(0), ctypes.c_int32(0)
+        seg = np.zeros(max(n, 1), np.int32)
+        _check(self._lib.scvod_region_growing(self._ctx, _ptr(cloud), n, ctypes.byref(flag), _ptr(seg), ctypes.byref(planar)))
+        return bool(flag.value), seg[:n], int(planar.value)
 
     # -- quality measures (tool/analysis.py:124-194, src/evaluate.cpp:79-145) --------------------
     def evaluate_map(self, gt_xyzl: np.ndarray, est_xyzl: np.ndarray, voxelsize: float = 0.2, dynamic_classes: Sequence[int] = DYNAMIC_CLASSES,

@@ -286,6 +286,19 @@ int scvod_evaluate_map(scvod_ctx* ctx, const float* gt_xyzl, int64_t n_gt, const
 int scvod_evaluate_confusion(scvod_ctx* ctx, const float* pred_xyzs, int64_t n, const float* static_gt_xyz, int64_t ns,
                              const float* dynamic_gt_xyz, int64_t nd, float r_hit, float r_miss, int64_t counts5[5], uint8_t* per_point);
 
+/* ---- k-NN normals, intensity calibration, region growing ---------------------------------------------
+ * scvod_knn_normals          exact k nearest neighbours (1 <= k <= 16, the point itself included, sorted by distance) of every point
+ *                            of a host cloud in the cloud itself, the PCA normal of the neighbourhood turned towards the origin and
+ *                            its curvature lambda_min / trace: what pcl::NormalEstimation with setKSearch(k) computes.  Any output
+ *                            may be NULL.  Normals are checked by tolerance (PCL's float eigen33 is not reproduced bit for bit).
+ * scvod_calibrate_intensity  SSC::intensityCalibrationByCurvature (src/ssc.cpp:98-153) in place on a host cloud (float[4] points).
+ * scvod_region_growing       SSC::regionGrowing (src/ssc.cpp:797-832) on a cluster cloud: *is_building = 1 when the planar segments hold
+ *                            >= 20 % of the points; segment_of (may be NULL) = segment of every point, planar_points (may be NULL) =
+ *                            points in segments of >= 20 points.  recognize() needs it only to tell building from tree (:845-856). */
+int scvod_knn_normals(scvod_ctx* ctx, const float* xyzi, int n, int k, float* normals3, float* curvature, int32_t* neighbors);
+int scvod_calibrate_intensity(scvod_ctx* ctx, float* xyzi, int n, int search_num, float max_intensity);
+int scvod_region_growing(scvod_ctx* ctx, const float* xyzi, int n, int32_t* is_building, int32_t* segment_of, int32_t* planar_points);
+
 /* ---- chain hand-off between contexts (one unbroken tracking chain over a sequence cut into chunks) ------------------------
  * SSC::segDF tracks a whole sequence as ONE chain: tracking(frame_set[i], frame_set[i+1]) for every i (ssc.cpp:1450-1452).  When the
  * sequence is cut into chunks owned by different contexts (workers of one GPU, GPUs of a box, processes), the pair that straddles a
