@@ -36,11 +36,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
+def env_int_early(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
 METRIC = "scans/sec (64-beam ~120k pts) full SCV-OD removal"
 UNIT = "scans/s"
 WORKLOAD = ("configs[1]: SemanticKITTI-shape streams (config/semantickitti.yaml), full PatchWork+SSC+tracking labelling; a step = W independent "
             "64-scan sequences (one per worker), each tracked as one unbroken chain")
-RINGS, COLS = 64, 1800
+RINGS, COLS = env_int_early("SCVOD_BENCH_RINGS", 64), env_int_early("SCVOD_BENCH_COLS", 1800)  # tuning only: the metric is quoted on 64 x 1800
 SEED = 0x5C0D0000
 # algorithmic (compulsory) bytes per unit for the stage each kernel dominates
 ALGO_BYTES = {
@@ -62,6 +69,43 @@ def host_cores():
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def bind_to_gpu_numa_node(local_rank, local_world):
+    """One process per GPU: run this rank (its worker threads and, through first touch, its pinned staging buffers) on the host
+    cores of its GPU's NUMA node; ranks whose GPUs share a node split that node's cores evenly.  Returns a short description."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout
+        bus = {}
+        for ln in out.strip().splitlines():
+            idx, b = [t.strip() for t in ln.split(",")]
+            bus[int(idx)] = b.lower()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = [int(t) for t in vis.split(",")] if vis and all(t.strip().isdigit() for t in vis.split(",")) else list(range(len(bus)))
+
+        def node_of(lr):
+            b = bus[phys[lr]]  # 00000000:1b:00.0 -> sysfs name 0000:1b:00.0
+            name = b[-12:] if len(b) > 12 else b
+            return int(open(f"/sys/bus/pci/devices/{name}/numa_node").read())
+
+        nodes = [node_of(lr) for lr in range(local_world)]
+        node = nodes[local_rank]
+        allowed = sorted(os.sched_getaffinity(0))
+        cores = allowed
+        if node >= 0:
+            node_cores = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                node_cores.update(range(int(a), int(b or a) + 1))
+            cores = [c for c in allowed if c in node_cores] or allowed
+        peers = [lr for lr in range(local_world) if nodes[lr] == node] if cores != allowed else list(range(local_world))
+        per = max(1, len(cores) // len(peers))
+        k = peers.index(local_rank)
+        mine = cores[k * per:(k + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return f"numa node {node}: cores {mine[0]}-{mine[-1]} ({len(mine)} of {len(allowed)} allowed)"
+    except Exception as e:  # noqa: BLE001
+        return f"not pinned ({type(e).__name__}: {e})"
 
 
 def env_int(name, default):
@@ -241,12 +285,24 @@ def main():
                     help="stream = BASELINE configs[1] (default, the headline); sequence = configs[3]; parkinglot_gicp = configs[2]; stress = configs[4] "
                          "(tools/bench_workloads.py)")
     ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e, roofline, cpu_baseline and parity legs; prints value only")
+    ap.add_argument("--concurrent-timing", action="store_true",
+                    help="tuning runs (with --quick): per-kernel CUDA-event durations measured INSIDE the multi-worker run (kernels of different "
+                         "workers overlap, so the durations are not additive; a kernel stretched against its single-stream time is contended)")
+    ap.add_argument("--trace", default="", help="tuning runs (with --quick): after the timed region, record a CUPTI kernel timeline of 2 more steps "
+                                                 "with torch.profiler and write it to this chrome-trace file (tools/trace_gaps.py reads it)")
     ap.add_argument("--skip-tracking", action="store_true", help="ablation: per-scan stages only (INVALID as a bench number)")
     ap.add_argument("--seq-scans", type=int, default=1000, help="--workload sequence: scans in the sequence")
     ap.add_argument("--scans-per-step", type=int, default=64, help="scans per sequence chunk; a step is one chunk per worker")
     ap.add_argument("--pool", type=int, default=3, help="distinct input batches rotated through (pool > L2)")
     ap.add_argument("--workers", type=int, default=0, help="independent sequence chunks processed side by side per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans for the cpu_baseline leg (0 = auto)")
+    ap.add_argument("--gather", default="exact", choices=["exact", "padded", "off"],
+                    help="N > 1: static-submap all-gather per chunk: rows = largest count of the call (default), capacity-sized (round-1 behaviour), "
+                         "or none (ablation, INVALID as a bench number)")
+    ap.add_argument("--submap", default="instance", choices=["instance", "all"],
+                    help="what a chunk contributes to the merged map: the points of its non-dynamic clusters (reference saveSegCloud mode 3, default) or "
+                         "every non-dynamic input point")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not bind the rank to the host cores of its GPU's NUMA node")
     ap.add_argument("--prefetch", action="store_true",
                     help="e2e leg: scvod_prefetch_scans the worker's next chunk during the tracking chain (measured slower with 16 workers: "
                          "a saturated PCIe link delays the launches of every tracking chain)")
@@ -267,6 +323,8 @@ def main():
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the SCV-OD path has no CPU fallback")
+    cores_total = host_cores()  # before the rank binds itself to its share of them
+    pin_note = bind_to_gpu_numa_node(local_rank, env_int("LOCAL_WORLD_SIZE", world)) if (world > 1 and not args.no_pin) else "not pinned"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -280,7 +338,7 @@ def main():
     # workers per GPU: 16 when there are at least 4 host cores per GPU, else 4 per core.  A worker that waits for the GPU sleeps
     # (blocking-sync events) or yields (tracking poll), so workers share cores: measured on one B200 restricted to 4 cores,
     # 4 / 8 / 12 / 16 workers give 18.6k / 22.2k / 24.5k / 26.5k scans/s
-    W = args.workers if args.workers > 0 else max(4, min(16, 4 * (host_cores() // max(1, local_world))))
+    W = args.workers if args.workers > 0 else max(4, min(16, 4 * (cores_total // max(1, local_world))))
     # each rank owns its own sequence chunks (scan-sharding, no data-path collective before the submap merge)
     batches = []
     for b in range(args.pool):
@@ -301,17 +359,22 @@ def main():
             self.stream = torch.cuda.Stream(device=dev)
             self.ssc = pkg.SSC(params, device=local_rank, max_points=RINGS * COLS, max_batch=S)
             self.ssc.set_option("inspect", 0)
-            self.ssc.set_option("host_threads", max(1, host_cores() // (W * max(1, local_world))))
+            self.ssc.set_option("host_threads", max(1, cores_total // (W * max(1, local_world))))
+            self.ssc.set_option("submap_all_static", 1 if args.submap == "all" else 0)
             self.ssc.set_stream(self.stream.cuda_stream)
             self.labels_host = torch.empty(max_pts, dtype=torch.uint8).pin_memory()
-            self.submap = torch.empty((max_pts, 4), dtype=torch.float32, device=dev)
-            self.submap_free = threading.Event()
-            self.submap_free.set()
+            # two send buffers per worker: the all-gather of chunk i runs while the worker already fills the other one for chunk i+1
+            self.submaps = [torch.empty((max_pts, 4), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
+            self.submap_free = [threading.Event() for _ in self.submaps]
+            for ev in self.submap_free:
+                ev.set()
             self.count = 0
 
     workers = [Worker(w) for w in range(W)]
     par = entry._load_parallel()
-    gatherer = par.SubmapGatherer(max_pts, dev) if world > 1 else None  # one NCCL all-gather of the static submaps per step
+    gatherer = par.SubmapGatherer(max_pts, dev) if world > 1 else None  # one NCCL all-gather of the static submaps per chunk
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_count = [0]
 
     def step(wk, i, host_io, prefetch_next=False):
         # every worker cycles through the whole pool (so its buffers reach their steady-state sizes during warm-up) and
@@ -333,10 +396,11 @@ def main():
             ssc.labels_into(0, S, wk.labels_host.data_ptr(), wk.labels_host.numel())
         else:
             ssc.refresh_labels(0, S)
+        k = wk.count % len(wk.submaps)
         if world > 1:
-            wk.submap_free.wait()  # the comm thread may still be gathering this worker's previous submap
-            wk.submap_free.clear()
-        return ssc.static_submap_device(0, S, b["poses"], wk.submap.data_ptr(), max_pts)
+            wk.submap_free[k].wait()  # the comm thread may still be gathering the submap this buffer held two chunks ago
+            wk.submap_free[k].clear()
+        return k, ssc.static_submap_device(0, S, b["poses"], wk.submaps[k].data_ptr(), max_pts)
 
     def barrier():
         if world > 1:
@@ -355,9 +419,9 @@ def main():
                 with torch.cuda.stream(wk.stream):
                     mine = list(range(first_step + wk.wid, first_step + nsteps, W))
                     for i in mine:
-                        n_static = step(wk, i, host_io, prefetch_next=(i != mine[-1]))
+                        k, n_static = step(wk, i, host_io, prefetch_next=(i != mine[-1]))
                         with cv:
-                            done[i] = (wk, n_static)
+                            done[i] = (wk, k, n_static)
                             cv.notify_all()
             except Exception as e:  # noqa: BLE001
                 with cv:
@@ -365,16 +429,30 @@ def main():
                     cv.notify_all()
 
         def comm():
-            for i in range(first_step, first_step + nsteps):
-                with cv:
-                    while i not in done and not errors:
-                        cv.wait()
-                    if errors:
-                        return
-                    wk, n_static = done.pop(i)
-                gatherer.gather(wk.submap, n_static)
-                torch.cuda.current_stream().synchronize()
-                wk.submap_free.set()
+            # One communication thread issues the gathers in chunk order (the same order on every rank) on its own stream.  It never
+            # blocks a worker: a send buffer is handed back once the event recorded after its gather has completed, which is checked
+            # when the next chunks come by (and drained at the end).
+            inflight = []
+            with torch.cuda.stream(comm_stream):
+                for i in range(first_step, first_step + nsteps):
+                    with cv:
+                        while i not in done and not errors:
+                            cv.wait()
+                        if errors:
+                            break
+                        wk, k, n_static = done.pop(i)
+                    if args.gather != "off":
+                        gatherer.gather(wk.submaps[k], n_static, padded=(args.gather == "padded"))
+                        gather_count[0] += 1
+                    ev = torch.cuda.Event()
+                    ev.record(comm_stream)
+                    inflight.append((ev, wk, k))
+                    while inflight and inflight[0][0].query():
+                        _, w2, k2 = inflight.pop(0)
+                        w2.submap_free[k2].set()
+                for ev, w2, k2 in inflight:
+                    ev.synchronize()
+                    w2.submap_free[k2].set()
 
         threads = [threading.Thread(target=work, args=(wk,)) for wk in workers]
         if world > 1:
@@ -391,32 +469,52 @@ def main():
         barrier()
         if with_kernel_timing:
             pkg.kernel_timing(True)
+        if os.environ.get("SCVOD_PROFILE"):
+            workers[0].ssc.set_option("profile_reset", 1)  # host-side section timers: steady state only
         l0 = sum(wk.ssc.kernel_launches for wk in workers)
+        a0 = workers[0].ssc.stat("reallocs")
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
+        c0 = time.process_time()
         run_steps(1000 * W, args.steps * W, host_io)
         for wk in workers:
             torch.cuda.current_stream().wait_stream(wk.stream)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
+        cpu_busy[0] = (time.process_time() - c0) / max(wall, 1e-9)  # host cores this rank kept busy (user + system), polling included
         ev = e0.elapsed_time(e1) / 1000.0
         clocks = sampler.stop() if rank == 0 else None
         rep = pkg.kernel_timing_report() if with_kernel_timing else None
         if with_kernel_timing:
             pkg.kernel_timing(False)
         secs = max(ev, wall)  # every step ends with host-side bookkeeping, so wall >= device time
+        reallocs[0] += workers[0].ssc.stat("reallocs") - a0  # buffer (re)allocations inside the timed regions: 0 in steady state
         return par.max_over_ranks(secs, dev), sum(wk.ssc.kernel_launches for wk in workers) - l0, clocks, rep
 
-    secs_dev, launches, clocks, _ = timed(False, False)
+    reallocs = [0]
+    cpu_busy = [0.0]
+    secs_dev, launches, clocks, crep = timed(False, args.concurrent_timing)
     if args.quick:
+        if args.trace and rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                run_steps(5000 * W, 2 * W, False)
+                torch.cuda.synchronize()
+            prof.export_chrome_trace(args.trace)
         if rank == 0:
+            if crep:
+                for k, (ms, cnt) in sorted(crep.items(), key=lambda kv: -kv[1][0]):
+                    print(f"  {k:26s} {ms / (W * args.steps):8.4f} ms/chunk under concurrency ({cnt // (W * args.steps)} launches/chunk)", file=sys.stderr)
             print(json.dumps({"quick": True, "value": world * W * S * args.steps / secs_dev, "unit": UNIT, "workers": W, "ms_per_step": 1000.0 * secs_dev / args.steps,
-                              "skip_tracking": args.skip_tracking, "gpu_launches": int(launches)}))
+                              "skip_tracking": args.skip_tracking, "gpu_launches": int(launches), "reallocs_in_timed_region": int(reallocs[0]), "host_cores_busy": round(cpu_busy[0], 2), "host_cores": host_cores(), "n_gpus": world, "gather": args.gather if world > 1 else None,
+                              "submap": args.submap, "host_binding": pin_note,
+                              "gather_mb_per_chunk": (gatherer.bytes_moved / max(1, gather_count[0]) / 1e6) if gatherer else None}))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -431,9 +529,9 @@ def main():
         pkg.kernel_timing(True)
         with torch.cuda.stream(workers[0].stream):
             for i in range(args.steps):
-                step(workers[0], 2000 + i, False)
+                k, _ = step(workers[0], 2000 + i, False)
                 if world > 1:
-                    workers[0].submap_free.set()
+                    workers[0].submap_free[k].set()
         torch.cuda.synchronize()
         rep = pkg.kernel_timing_report()
         pkg.kernel_timing(False)
@@ -443,6 +541,7 @@ def main():
     if rank == 0:
         value = world * W * S * args.steps / secs_dev
         e2e_value = world * W * S * args.steps / secs_e2e
+        gather_calls = gather_count[0]
         avg_pts = float(np.mean([b["npts"] for b in batches])) / S
         peak, peak_src = measured_peak()
         # dominant kernel by total device time inside the timed region
@@ -509,11 +608,16 @@ def main():
                        "l2": f"inputs rotate over a pool of {args.pool} batches ({args.pool * b0['npts'] * 16 / 1e6:.0f} MB) larger than the 126 MB L2; "
                              "per-step workspace (>1 GB) is rewritten every step",
                        "workers_per_gpu": W,
-                       "sharding": ("scan-sharded: independent sequence chunks per rank and per worker; one NCCL all-gather of static submaps per step"
-                                    if world > 1 else "single GPU; independent sequence chunks per worker")},
+                       "sharding": ("scan-sharded: independent sequence chunks per rank and per worker; one NCCL all-gather of static submaps per chunk "
+                                    f"(--gather {args.gather}: {gatherer.bytes_moved / max(1, gather_calls) / 1e6:.1f} MB received per rank and chunk)"
+                                    if world > 1 else "single GPU; independent sequence chunks per worker"),
+                       "submap": ("instance map: points of the non-dynamic clusters (reference saveSegCloud mode 3)" if args.submap == "instance"
+                                  else "every non-dynamic input point"),
+                       "host_binding": pin_note},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(W * (b0["npts"] * 16 + (S + 1) * 8)), "d2h_bytes_per_step": int(W * b0["npts"]),
                     "ms_per_step": 1000.0 * secs_e2e / args.steps},
             "gpu_launches": int(launches),
+            "reallocs_in_timed_region": int(reallocs[0]),
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": min(nchunks, ncores), "kind": "port",
                              "sample": f"{nchunks} independent {S}-scan chunks of the same workload in {cpu_secs:.2f} s, one host thread per chunk (per-scan "

@@ -89,7 +89,7 @@ EXPORTS = (
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
     "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states", "scvod_load_kitti", "scvod_load_kitti_dev",
     "scvod_evaluate_map", "scvod_evaluate_confusion", "scvod_synth_scan_labeled",
-    "scvod_knn_normals", "scvod_calibrate_intensity", "scvod_region_growing",
+    "scvod_knn_normals", "scvod_calibrate_intensity", "scvod_region_growing", "scvod_bin_filter_check",
 )
 
 _lib = None
@@ -308,6 +308,17 @@ class SSC:
         _check(self._lib.scvod_bin(self._ctx, _ptr(cloud), n, _ptr(out["pass"]), _ptr(out["voxel_idx"]), _ptr(out["range_idx"]),
                                    _ptr(out["sector_idx"]), _ptr(out["azimuth_idx"]), _ptr(out["range"]), _ptr(out["angle"]), _ptr(out["azimuth"])))
         return out
+
+    def bin_filter_check(self, n: int, seed: int = 1, extent: float = 60.0, cloud: Optional[np.ndarray] = None) -> dict:
+        """Soundness probe of the in-kernel binning filter: dict(points, exact, mismatches, max_dq_sector, max_dq_azimuth)."""
+        st = np.zeros(7, np.uint64)
+        if cloud is not None:
+            cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+            n = len(cloud)
+        _check(self._lib.scvod_bin_filter_check(self._ctx, _ptr(cloud) if cloud is not None else None, ctypes.c_int64(n), ctypes.c_uint32(seed),
+                                                ctypes.c_float(extent), _ptr(st)))
+        return {"points": int(st[0]), "exact": int(st[1]), "mismatches": int(st[2]), "max_dq_sector": float(st[3]) * 1e-9,
+                "max_dq_azimuth": float(st[4]) * 1e-9, "patch_exact": int(st[5]), "patch_mismatches": int(st[6])}
 
     def atan2f_device(self, y: np.ndarray, x: np.ndarray) -> np.ndarray:
         y = np.ascontiguousarray(y, np.float32)

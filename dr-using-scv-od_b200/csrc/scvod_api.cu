@@ -45,37 +45,64 @@ static int fail(int code, const std::string& msg) {
 
 namespace {
 
-// host-side section timer (SCVOD_PROFILE=1 prints the accumulated breakdown at scvod_destroy)
+// host-side section timer (SCVOD_PROFILE=1 prints the accumulated breakdown at scvod_destroy): wall time and the CPU time of the
+// calling thread per section (a section that waits for the GPU asleep has wall >> cpu; one that spins has wall == cpu)
+static double thread_cpu_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 struct HostProf {
   bool on = getenv("SCVOD_PROFILE") != nullptr;
-  std::vector<std::pair<std::string, double>> acc;
+  struct Acc {
+    std::string name;
+    double wall = 0, cpu = 0;
+    long long calls = 0;
+  };
+  std::vector<Acc> acc;
   std::mutex mu;
-  void add(const char* name, double ms) {
+  void add(const char* name, double ms, double cpu_ms = 0) {
     std::lock_guard<std::mutex> lk(mu);
     for (auto& a : acc)
-      if (a.first == name) {
-        a.second += ms;
+      if (a.name == name) {
+        a.wall += ms;
+        a.cpu += cpu_ms;
+        a.calls++;
         return;
       }
-    acc.push_back(std::make_pair(std::string(name), ms));
+    Acc a;
+    a.name = name;
+    a.wall = ms;
+    a.cpu = cpu_ms;
+    a.calls = 1;
+    acc.push_back(a);
+  }
+  void reset() {
+    std::lock_guard<std::mutex> lk(mu);
+    acc.clear();
   }
   void dump() {
     if (!on) return;
-    for (auto& a : acc) fprintf(stderr, "[scvod profile] %-28s %10.3f ms\n", a.first.c_str(), a.second);
+    for (auto& a : acc)
+      fprintf(stderr, "[scvod profile] %-28s wall %10.3f ms  cpu %10.3f ms  calls %lld\n", a.name.c_str(), a.wall, a.cpu, a.calls);
   }
 };
 HostProf g_prof;
 struct ProfScope {
   const char* name;
   std::chrono::steady_clock::time_point t0;
-  explicit ProfScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  double c0;
+  explicit ProfScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()), c0(g_prof.on ? thread_cpu_ms() : 0) {}
   ~ProfScope() {
-    if (g_prof.on) g_prof.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (g_prof.on)
+      g_prof.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), thread_cpu_ms() - c0);
   }
 };
 #define PROF_CAT2(a, b) a##b
 #define PROF_CAT(a, b) PROF_CAT2(a, b)
 #define PROF(name) ProfScope PROF_CAT(prof_scope__, __COUNTER__)(name)
+
+std::atomic<long long> g_reallocs(0);  // device / pinned (re)allocations so far in this process (scvod_get_stat "reallocs")
 
 template <typename T>
 struct DevBuf {
@@ -83,6 +110,7 @@ struct DevBuf {
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     if (count <= n && p) return cudaSuccess;
+    g_reallocs.fetch_add(1, std::memory_order_relaxed);
     if (p) {
       cudaFree(p);
       count += count / 2 + 1024;  // geometric growth: buffers that grow step by step are not re-allocated every time
@@ -106,6 +134,7 @@ struct PinBuf {
   size_t n = 0;
   cudaError_t alloc(size_t count) {
     if (count <= n && p) return cudaSuccess;
+    g_reallocs.fetch_add(1, std::memory_order_relaxed);
     if (p) {
       cudaFreeHost(p);
       count += count / 2 + 1024;
@@ -196,6 +225,7 @@ struct scvod_ctx {
   int host_threads = 1;
   bool inspect = true;
   bool replay_global = false;  // test hook: force the global-memory variant of k_name_replay
+  bool submap_all_static = false;  // scvod_static_submap_dev: every non-dynamic input point instead of the instance map (cluster points)
 
   BatchDev ws;  // transient workspace (pointers into the DevBufs below and into the current PersistBatch)
   DevBuf<int64_t> d_off;
@@ -246,6 +276,11 @@ struct scvod_ctx {
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
   bool head_tracked = false;  // frame 0 has been frame_next_ of an imported tail (scvod_track_from_tail)
+  // The tracking chain runs on its own stream of the HIGHEST priority: a k_track launch is tiny and latency critical (the host
+  // waits for its answer before it can decide the pair), while the per-scan kernels of the other contexts are bulk work; the
+  // block scheduler hands freed CTA slots to the higher priority first, so a pair no longer queues behind whole grids.
+  cudaStream_t tstream = nullptr;
+  cudaEvent_t tlink = nullptr;
   cudaEvent_t sync_event = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning (see wait_stream)
   // scvod_prefetch_scans: upload of the next batch on a private stream, consumed by the next scvod_push_scans of the same buffer
   cudaStream_t copy_stream = nullptr;
@@ -277,6 +312,20 @@ static cudaError_t wait_stream(scvod_ctx* c, cudaStream_t st) {
 
 namespace scvod {
 void* ctx_stream(scvod_ctx* c) { return (void*)c->stream; }
+// the tracking stream joins the context's stream on entry (everything queued so far happens before the chain) and hands back on
+// exit (everything queued afterwards sees the chain's results)
+struct TrackStreamScope {
+  scvod_ctx* c;
+  explicit TrackStreamScope(scvod_ctx* ctx) : c(ctx) {
+    cudaEventRecord(c->tlink, c->stream);
+    cudaStreamWaitEvent(c->tstream, c->tlink, 0);
+  }
+  ~TrackStreamScope() {
+    cudaEventRecord(c->tlink, c->tstream);
+    cudaStreamWaitEvent(c->stream, c->tlink, 0);
+  }
+};
+
 int ctx_device(const scvod_ctx* c) { return c->device; }
 void ctx_add_launches(scvod_ctx* c, int n) { c->launches += n; }
 void** ctx_gicp_slot(scvod_ctx* c) { return &c->gicp; }
@@ -418,6 +467,13 @@ extern "C" int scvod_create(const scvod_params* p, int device, int max_points, i
   unsigned hc = std::thread::hardware_concurrency();
   c->host_threads = hc ? (int)std::min<unsigned>(hc, 32u) : 4;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    static const bool flat = getenv("SCVOD_TRACK_PRIORITY") && atoi(getenv("SCVOD_TRACK_PRIORITY")) == 0;  // A/B switch
+    CU(cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, flat ? lo : hi));
+    CU(cudaEventCreateWithFlags(&c->tlink, cudaEventDisableTiming));
+  }
   int rc = alloc_workspace(c.get());
   if (rc != SCVOD_OK) return rc;
   g_live_contexts.fetch_add(1);
@@ -427,8 +483,7 @@ extern "C" int scvod_create(const scvod_params* p, int device, int max_points, i
 
 extern "C" int scvod_destroy(scvod_ctx* c) {
   if (!c) return SCVOD_OK;
-  g_live_contexts.fetch_sub(1);
-  g_prof.dump();
+  if (g_live_contexts.fetch_sub(1) == 1) g_prof.dump();  // the last context of the process prints the host-side profile
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->gicp && c->gicp_free) c->gicp_free(c->gicp);
@@ -451,6 +506,11 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_tp_m.release(); c->d_tp_cid.release(); c->d_tp_name.release(); c->d_tp_xyz.release(); c->h_taint_cnt.release();
   c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->tstream) {
+    cudaStreamSynchronize(c->tstream);
+    cudaStreamDestroy(c->tstream);
+  }
+  if (c->tlink) cudaEventDestroy(c->tlink);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
@@ -479,6 +539,7 @@ extern "C" int scvod_get_stat(scvod_ctx* c, const char* key, int64_t* out) {
   else if (k == "voxels") *out = c->stat_voxels;
   else if (k == "tainted_voxels") *out = c->stat_tvox;
   else if (k == "tainted_points") *out = c->stat_tpts;
+  else if (k == "reallocs") *out = g_reallocs.load();  // process-wide: device / pinned buffer (re)allocations so far
   else return fail(SCVOD_ERR_ARG, "unknown stat " + k);
   return SCVOD_OK;
 }
@@ -494,6 +555,10 @@ extern "C" int scvod_set_option(scvod_ctx* c, const char* key, int value) {
     c->replay_global = value != 0;
   else if (k == "chain_tma")
     c->hp.chain_tma = value != 0;
+  else if (k == "submap_all_static")
+    c->submap_all_static = value != 0;
+  else if (k == "profile_reset")  // SCVOD_PROFILE=1: forget what the host-side section timers have accumulated (e.g. after a warm-up)
+    g_prof.reset();
   else
     return fail(SCVOD_ERR_ARG, "unknown option " + k);
   return SCVOD_OK;
@@ -595,6 +660,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   w.vox_center = pb->vox_center.p;
 
   std::chrono::steady_clock::time_point tk0 = std::chrono::steady_clock::now();
+  const double tk0_cpu = g_prof.on ? thread_cpu_ms() : 0;
   CU(cudaMemcpyAsync(w.off, off.data(), sizeof(int64_t) * (nscans + 1), cudaMemcpyHostToDevice, st));
   if (total > 0) {
     const char* src = (const char*)xyzi + sizeof(float) * 4 * offsets[0];
@@ -616,7 +682,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   CU(cudaMemcpyAsync(c->h_scan_counts.p, w.scan_counts, sizeof(int32_t) * ((size_t)w.cap_scans * 8 + 8), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_taint_cnt.p, w.taint_cnt, sizeof(int32_t) * (size_t)nscans * kTaintCntStride, cudaMemcpyDeviceToHost, st));
   CU(wait_stream(c, st));
-  if (g_prof.on) g_prof.add("  h2d + kernels + sync", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count());
+  if (g_prof.on) g_prof.add("  h2d + kernels + sync", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count(), thread_cpu_ms() - tk0_cpu);
   const int32_t* sc = c->h_scan_counts.p;
   if (sc[(size_t)w.cap_scans * 8] & 1) return fail(SCVOD_ERR_CAPACITY, "a PatchWork patch holds more points than the largest fit tile");
 
@@ -646,6 +712,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   }
 
   std::chrono::steady_clock::time_point td0 = std::chrono::steady_clock::now();
+  const double td0_cpu = g_prof.on ? thread_cpu_ms() : 0;
   // cluster names: one warp per scan replays the reference's sequential naming on the device
   int max_vox = 1, max_ev = 1;
   for (int s = 0; s < nscans; ++s) {
@@ -711,8 +778,9 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   const int32_t* hp_nf = c->h_pack.p + o_nf;
   const int32_t* hp_edge = c->h_pack.p + o_edge;
   const int32_t* hp_sc2 = c->h_pack.p + o_max;
-  if (g_prof.on) g_prof.add("  d2h voxel tables", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td0).count());
+  if (g_prof.on) g_prof.add("  d2h voxel tables", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td0).count(), thread_cpu_ms() - td0_cpu);
   std::chrono::steady_clock::time_point th0 = std::chrono::steady_clock::now();
+  const double th0_cpu = g_prof.on ? thread_cpu_ms() : 0;
   // host cluster bookkeeping, one scan per task
   const int batch_id = (int)c->batches.size();
   const size_t f0 = c->frames.size();
@@ -777,7 +845,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     for (int i = 0; i < nt; ++i) th.emplace_back(worker);
     for (auto& t : th) t.join();
   }
-  if (g_prof.on) g_prof.add("  host segment+recognize", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count());
+  if (g_prof.on) g_prof.add("  host segment+recognize", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count(), thread_cpu_ms() - th0_cpu);
   // car CSR of the batch (see PersistBatch::csr): the own voxels of every car cluster, in occupy_voxels order, with running
   // point offsets and part indices; one upload per batch, so that tracking needs no per-pair segment upload.  A tainted voxel
   // contributes only the subgroups the cluster owns, as "virtual voxels" whose points sit in the 4th section (tv_pts).
@@ -786,6 +854,7 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
     return fail(SCVOD_ERR_STATE, "internal: replayed cluster partition differs from the GPU components");
   }
   {
+    PROF("  car csr build");
     size_t csr_n = 0, tv_n = 0;
     for (int s = 0; s < nscans; ++s) {
       FrameHost& fr = c->frames[f0 + s];
@@ -1050,6 +1119,7 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
   if (K == 0 || vn <= 0) return SCVOD_OK;
   c->stat_track_points += (int64_t)K;
   std::chrono::steady_clock::time_point ta0 = std::chrono::steady_clock::now();
+  const double ta0_cpu = g_prof.on ? thread_cpu_ms() : 0;
   const int cap_quads = (int)std::min<size_t>((size_t)ncl * vn, (size_t)1 << 20);
   size_t nblk = 0;
   if (!use_runs) {
@@ -1070,21 +1140,21 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
     const size_t need = (size_t)ncl * vn;
     if (need > c->d_first.n) {  // (re)allocation: the table must start out "empty"; afterwards the epilogue of k_track keeps it so
       CU(c->d_first.alloc(need));
-      CU(cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream));
+      CU(cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->tstream));
     }
   }
   CU(c->h_triples.alloc(4 + 4 * (size_t)cap_quads));
   if (!c->d_track_ctr.p) {
     CU(c->d_track_ctr.alloc(4));
-    CU(cudaMemsetAsync(c->d_track_ctr.p, 0, sizeof(int32_t) * c->d_track_ctr.n, c->stream));
+    CU(cudaMemsetAsync(c->d_track_ctr.p, 0, sizeof(int32_t) * c->d_track_ctr.n, c->tstream));
   }
   CU(c->d_track_list.alloc((size_t)cap_quads));
   *reinterpret_cast<volatile int32_t*>(c->h_triples.p) = -1;
   std::atomic_thread_fence(std::memory_order_release);
-  if (g_prof.on) g_prof.add("    track: buffers", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ta0).count());
+  if (g_prof.on) g_prof.add("    track: buffers", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ta0).count(), thread_cpu_ms() - ta0_cpu);
   {
     PROF("    track: enqueue+wait+read");
-    if (!use_runs) CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->stream));
+    if (!use_runs) CU(cudaMemcpyAsync(c->d_treq.p, c->h_treq.p, sizeof(int32_t) * (si * 4 + nblk + 1), cudaMemcpyHostToDevice, c->tstream));
     // one context: the kernel may fill the GPU (shortest latency); many contexts: one CTA per SM so that their kernels co-run
     const int chains = g_tracking_now.load();
     c->hp.track_ctas_per_sm = chains <= 2 ? 16 : chains <= 6 ? 4 : 1;
@@ -1093,7 +1163,7 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
                                 (int)si, use_runs ? &runs : nullptr, pbp.csr.p, pbp.csr.p + pbp.csr_n, pbp.csr.p + 2 * pbp.csr_n,
                                 pbp.csr.p + 3 * (size_t)pbp.csr_n, (int)K, T,
                                 pbn.bitmap.p + (size_t)next.slot * c->hp.g.words, pbn.word_rank.p + (size_t)next.slot * c->hp.g.words, ncl, vn,
-                                c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads, c->stream);
+                                c->d_tout[out_buf].p, c->d_first.p, c->d_track_ctr.p, c->d_track_list.p, c->h_triples.p, cap_quads, c->tstream);
     CU(cudaGetLastError());
     // The kernel's last CTA writes the hits and then their count straight into this pinned buffer: poll the count
     // instead of paying a stream synchronisation per frame pair (stream order still protects every device buffer).
@@ -1101,7 +1171,7 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
     static const bool sync_wait = getenv("SCVOD_TRACK_SYNC") != nullptr;  // A/B switch: stream synchronisation instead of polling
     if (sync_wait) {
       PROF("    track: wait (sync)");
-      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaStreamSynchronize(c->tstream));
       nt = c->h_triples.p[0];
     } else {
       PROF("    track: wait (poll)");
@@ -1114,7 +1184,7 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
       while ((nt = *flag) < 0) {
         if (++since_query >= 2000) {
           since_query = 0;
-          cudaError_t qe = cudaStreamQuery(c->stream);
+          cudaError_t qe = cudaStreamQuery(c->tstream);
           if (qe == cudaSuccess) {
             nt = *flag;
             if (nt < 0) return fail(SCVOD_ERR_CUDA, "k_track finished without publishing its hit count");
@@ -1133,8 +1203,8 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
       std::atomic_thread_fence(std::memory_order_acquire);
     }
     if (nt > cap_quads) {  // entries past the list were not reset by the kernel epilogue: wipe the table before giving up
-      cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->stream);
-      cudaStreamSynchronize(c->stream);
+      cudaMemsetAsync(c->d_first.p, 0xff, sizeof(unsigned long long) * c->d_first.n, c->tstream);
+      cudaStreamSynchronize(c->tstream);
       return fail(SCVOD_ERR_CAPACITY, "tracking hit table overflow");
     }
     // counting sort of the quads by cluster (no order inside a cluster: the decisions only need, per next-frame
@@ -1320,6 +1390,7 @@ extern "C" int scvod_track(scvod_ctx* c, const float* poses6, int nposes) {
   if (!c || !poses6) return fail(SCVOD_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   TrackingScope in_chain;
+  TrackStreamScope on_tstream(c);
   int nf = std::min<int>((int)c->frames.size(), nposes);
   for (int i = c->tracked; i + 1 < nf; ++i) {
     int rc = track_pair(c, c->frames[i], c->frames[i + 1], poses6 + 6 * i, poses6 + 6 * (i + 1));
@@ -1425,7 +1496,7 @@ extern "C" int scvod_track_from_tail(scvod_ctx* c, const void* tail, size_t nbyt
   // the imported clouds become "carried" ranges of a stand-in frame_pre_
   const int in_buf = c->tout_cur;
   CU(c->d_tout[in_buf].alloc((size_t)std::max(1, npts)));
-  if (npts > 0) CU(cudaMemcpyAsync(c->d_tout[in_buf].p, pts, sizeof(float4) * (size_t)npts, cudaMemcpyHostToDevice, c->stream));
+  if (npts > 0) CU(cudaMemcpyAsync(c->d_tout[in_buf].p, pts, sizeof(float4) * (size_t)npts, cudaMemcpyHostToDevice, c->stream));  // before the scope below joins
   FrameHost& next = c->frames[0];
   FrameHost pre;
   pre.batch = next.batch;
@@ -1451,7 +1522,11 @@ extern "C" int scvod_track_from_tail(scvod_ctx* c, const void* tail, size_t nbyt
   float T[12];
   relative_pose(pose_next6, pose_pre6, T);
   TrackingScope in_chain;
-  int rc = track_cars(c, pre, next, T, cars);
+  int rc;
+  {
+    TrackStreamScope on_tstream(c);
+    rc = track_cars(c, pre, next, T, cars);
+  }
   CU(cudaStreamSynchronize(c->stream));  // the caller may free `tail` now
   if (rc) return rc;
   c->head_tracked = true;
@@ -1501,6 +1576,7 @@ extern "C" int scvod_initialization(scvod_ctx* c, const float* poses6, int npose
   c->init_base = id_based;
   FrameClusters& fb = c->init_fc;
   std::vector<size_t> cstart;
+  TrackStreamScope on_tstream(c);
   for (int i = 0; i < nf; ++i) {
     if (i == id_based) continue;
     FrameHost& fi = c->frames[i];
@@ -1678,7 +1754,8 @@ extern "C" int scvod_static_submap_dev(scvod_ctx* c, int f0, int f1, const float
     while (g < f1 && c->frames[g].batch == fr.batch) ++g;
     PersistBatch& pb = *c->batches[fr.batch];
     c->launches += launch_submap(pb.pts.p, pb.cls.p, pb.off_dev.p, c->d_Ts.p + 12 * (f - f0), fr.slot, g - f, pb.max_n,
-                                 (float4*)out_xyzi_dev, c->d_counter.p, cap_points, c->stream);
+                                 (float4*)out_xyzi_dev, c->d_counter.p, cap_points,
+                                 c->submap_all_static ? (0xffu & ~(1u << SCVOD_PT_DYNAMIC)) : (1u << SCVOD_PT_STATIC), c->stream);
     CU(cudaGetLastError());
     f = g;
   }
@@ -1889,6 +1966,33 @@ extern "C" int scvod_bin(scvod_ctx* c, const float* xyzi, int n, uint8_t* pass, 
   CU(cudaStreamSynchronize(st));
   pts.release(); dpass.release(); dvid.release(); dri.release(); dsi.release(); dei.release(); dr.release(); da_.release(); daz.release();
   return rc ? SCVOD_ERR_CUDA : SCVOD_OK;
+}
+
+// Test hook: soundness of the binning filter (dev_bin_filtered == dev_bin_point) on n generated points (xyzi == NULL: counter-based
+// generator with structured edge cases, coordinates within +-extent) or on n caller points.  stats5: points, points that took the
+// exact chain, mismatches, max |q_approx - q_exact| * 1e9 of the sector and of the azimuth coordinate among filter-decided points,
+// then (generated points only) the same two counts for the patch-assignment filter of the ground stage (dev_patch_filtered).
+extern "C" int scvod_bin_filter_check(scvod_ctx* c, const float* xyzi, int64_t n, uint32_t seed, float extent, uint64_t* stats7) {
+  if (!c || !stats7 || n < 0) return fail(SCVOD_ERR_ARG, "bad arguments to scvod_bin_filter_check");
+  CU(cudaSetDevice(c->device));
+  DevBuf<unsigned long long> st;
+  DevBuf<float4> pts;
+  CU(st.alloc(8));
+  CU(cudaMemsetAsync(st.p, 0, sizeof(unsigned long long) * 8, c->stream));
+  if (xyzi && n > 0) {
+    CU(pts.alloc(n));
+    CU(cudaMemcpyAsync(pts.p, xyzi, sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (n > 0) c->launches += launch_bin_filter_check(c->hp, n, seed, extent, xyzi ? pts.p : nullptr, st.p, c->stream);
+  if (n > 0 && !xyzi) c->launches += launch_patch_filter_check(c->hp, n, seed, extent, st.p, c->stream);  // G1 (pc2czm) filter: stats[5], [6]
+  CU(cudaGetLastError());
+  unsigned long long h[7] = {0, 0, 0, 0, 0, 0, 0};
+  CU(cudaMemcpyAsync(h, st.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 7; ++i) stats7[i] = h[i];
+  st.release();
+  pts.release();
+  return SCVOD_OK;
 }
 
 // device port of glibc atan2f evaluated on the GPU (test hook for the libm-parity check)

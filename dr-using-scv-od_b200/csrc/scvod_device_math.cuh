@@ -142,6 +142,8 @@ __device__ __forceinline__ float dev_deg2rad_f(float d) {
 struct BinParams {
   float min_dis, max_dis, min_angle, max_angle, min_azimuth, max_azimuth, range_res, sector_res, azimuth_res;
   int range_num, sector_num;
+  // filter of dev_bin_filtered (make_bin_params): reciprocal resolutions and guard bands
+  float inv_sector_res, inv_azimuth_res, eps_qs, eps_qe, eps_deg;
 };
 
 struct BinResult {
@@ -172,6 +174,58 @@ __device__ __forceinline__ BinResult dev_bin_point(float x, float y, float z, co
   r.ei = (int)ds(ceilf(dd(ds(r.azimuth, P.min_azimuth), P.azimuth_res)), 1.f);
   r.vid = r.ei * P.range_num * P.sector_num + r.ri * P.sector_num + r.si;
   return r;
+}
+
+// Filtered exact binning: the same index triple, voxel_idx and gate outcome as dev_bin_point, at a fraction of its instruction
+// count (the two exact atan2f restatements with their rad2deg double divisions are ~2/3 of dev_bin_point; every kernel on the path
+// is issue bound, so instructions are what it costs).  Floating-point filter, as used for exact geometric predicates:
+//   * the range index needs no libm call: it is computed with the exact chain;
+//   * polar angle and azimuth are first evaluated approximately (CUDA atan2f + two multiplications).  The approximate and the
+//     exact chain both lie within a small, provable distance of the real-valued angle (a few float ulps of 360 degrees:
+//     < 2e-4 degrees in total, measured < 6e-5, see tests/test_gpu_parity.py::test_filtered_binning_*), so whenever the
+//     approximate bin coordinate q = (angle - min) / res is farther than the guard band (1e-3 degrees, >= 5x that distance) from
+//     every integer and the angle farther than it from both gates, ceil(q) and the gate comparisons of the two chains agree;
+//   * otherwise (about 0.3 % of the points) the point takes dev_bin_point.
+// The result is therefore ALWAYS the exact chain's; the filter only decides how much work that takes.
+struct BinIdx {
+  int ri, si, ei, vid;
+  bool pass;
+};
+
+// out-of-line exact chain for the rare points the filter cannot decide (keeps the callers' register count and code size down)
+static __device__ __noinline__ int4 dev_bin_point_call(float x, float y, float z, const BinParams& P) {
+  const BinResult r = dev_bin_point(x, y, z, P);
+  return make_int4(r.ri, r.si, r.ei, r.pass ? 1 : 0);
+}
+
+__device__ __forceinline__ BinIdx dev_bin_filtered(float x, float y, float z, const BinParams& P, bool* took_exact = nullptr) {
+  BinIdx o;
+  const float dis = __fsqrt_rn(da(dm(x, x), dm(y, y)));
+  float a = atan2f(y, x);
+  if (!(y >= 0.f)) a += 6.283185307179586f;  // same branch as getPolarAngle (utility.h:376-384)
+  const float ang = a * 57.29577951308232f;
+  const float az = atan2f(z, dis) * 57.29577951308232f;
+  const float qs = (ang - P.min_angle) * P.inv_sector_res;
+  const float qe = (az - P.min_azimuth) * P.inv_azimuth_res;
+  const float cs = ceilf(qs), ce = ceilf(qe);
+  const bool safe = (cs - qs > P.eps_qs) && (qs - (cs - 1.f) > P.eps_qs) && (ce - qe > P.eps_qe) && (qe - (ce - 1.f) > P.eps_qe) &&
+                    (fabsf(ang - P.max_angle) > P.eps_deg) && (fabsf(az - P.max_azimuth) > P.eps_deg) &&
+                    (fabsf(qs) < 1.0e6f) && (fabsf(qe) < 1.0e6f) && !(x == 0.f && y == 0.f);  // the origin: angle := 0 (utility.h:377)
+  if (took_exact) *took_exact = !safe;
+  if (safe) {
+    o.ri = (int)ds(ceilf(dd(ds(dis, P.min_dis), P.range_res)), 1.f);
+    o.si = (int)ds(cs, 1.f);
+    o.ei = (int)ds(ce, 1.f);
+    o.pass = !(dis < P.min_dis || dis > P.max_dis || ang < P.min_angle || ang > P.max_angle || az < P.min_azimuth || az > P.max_azimuth);
+  } else {
+    const int4 r = dev_bin_point_call(x, y, z, P);
+    o.ri = r.x;
+    o.si = r.y;
+    o.ei = r.z;
+    o.pass = r.w != 0;
+  }
+  o.vid = o.ei * P.range_num * P.sector_num + o.ri * P.sector_num + o.si;
+  return o;
 }
 
 }  // namespace scvod

@@ -24,7 +24,90 @@ struct GroundConst {
   double seed_thr;  // adaptive_seed_selection_margin_ * sensor_height_ (patchwork.h:247)
   double min_range, max_range, z2, z3, z4;
   double ring_size[4], sector_size[4], rmin[4];
+  // float filter of k_patch_assign (same idea as dev_bin_filtered): approximate ring / sector coordinates decide unless they
+  // are within a guard band of an integer, the exact double chain decides the rest
+  float low_thr_f;  // smallest float >= low_thr: ((double)z < low_thr) == (z < low_thr_f)
+  float max_range_f, z2f, z3f, z4f, rmin_f[4], inv_ring_f[4], inv_sector_f[4];
 };
+
+// pc2czm (patchwork.h:431-459) for one point: patch id, -1 below the height threshold (patchwork.h:304), -2 outside (min_range, max_range]
+__device__ __forceinline__ int dev_patch_exact(float px, float py, float pz, const GroundConst& gc) {
+  if ((double)pz < gc.low_thr) return -1;
+  double x = (double)px, y = (double)py;
+  double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+  if ((r <= gc.max_range) && (r > gc.min_range)) {
+    double theta = (y >= 0) ? atan2(y, x) : __dadd_rn(2.0 * 3.14159265358979323846, atan2(y, x));
+    int k = (r < gc.z2) ? 0 : (r < gc.z3) ? 1 : (r < gc.z4) ? 2 : 3;
+    int ring = min((int)__ddiv_rn(__dsub_rn(r, gc.rmin[k]), gc.ring_size[k]), c_zone_rings[k] - 1);
+    int sector = min((int)__ddiv_rn(theta, gc.sector_size[k]), c_zone_sectors[k] - 1);
+    return c_zone_base[k] + ring * c_zone_sectors[k] + sector;
+  }
+  return -2;
+}
+static __device__ __noinline__ int dev_patch_exact_call(float px, float py, float pz, const GroundConst& gc) { return dev_patch_exact(px, py, pz, gc); }
+
+// The same result through a float filter (the idea of dev_bin_filtered): the float radius and CUDA's atan2f are within ~1e-5 of the
+// exact double ring / sector coordinates (float rounding of a radius <= 80 m over a ring >= 4.8 m; 3 ulp of pi over a sector
+// >= 0.116 rad), so coordinates farther than the guard bands (2e-4 / 5e-4: a 20x margin) from every integer decide at once; the
+// double chain (dsqrt, double atan2, two double divisions: ~4x the instructions) is evaluated only for the rest.
+__device__ __forceinline__ int dev_patch_filtered(float px, float py, float pz, const GroundConst& gc, bool* took_exact = nullptr) {
+  if (took_exact) *took_exact = false;
+  if (pz < gc.low_thr_f) return -1;
+  const float rf = sqrtf(px * px + py * py);
+  const int k = (rf < gc.z2f) ? 0 : (rf < gc.z3f) ? 1 : (rf < gc.z4f) ? 2 : 3;
+  const float qr = (rf - gc.rmin_f[k]) * gc.inv_ring_f[k];
+  float th = atan2f(py, px);
+  if (!(py >= 0.f)) th += 6.283185307179586f;
+  const float qt = th * gc.inv_sector_f[k];
+  const float fr = qr - floorf(qr), ft = qt - floorf(qt);
+  if (qr > 2.0e-4f && qr < (float)c_zone_rings[k] - 2.0e-4f && fr > 2.0e-4f && fr < 1.f - 2.0e-4f && qt > 5.0e-4f && ft > 5.0e-4f &&
+      ft < 1.f - 5.0e-4f && qt < (float)c_zone_sectors[k] + 0.5f)
+    return c_zone_base[k] + (int)qr * c_zone_sectors[k] + min((int)qt, c_zone_sectors[k] - 1);
+  if (rf < gc.rmin_f[0] - 1.0e-3f || rf > gc.max_range_f + 1.0e-3f) return -2;  // clearly outside (min_range, max_range]
+  if (took_exact) *took_exact = true;
+  return dev_patch_exact_call(px, py, pz, gc);
+}
+
+// G1 filter soundness probe (scvod_bin_filter_check): stats[5] points that took the double chain, stats[6] mismatches
+__global__ void __launch_bounds__(256) k_patch_filter_check(long long n, uint32_t seed, GroundConst gc, float extent,
+                                                            unsigned long long* __restrict__ stats) {
+  unsigned long long n_exact = 0, n_bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t h[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      uint32_t v = (uint32_t)i * 3u + (uint32_t)j + seed + (uint32_t)(i >> 32) * 0x9e3779b9u;
+      v ^= v >> 16; v *= 0x7feb352du; v ^= v >> 15; v *= 0x846ca68bu; v ^= v >> 16;
+      h[j] = v;
+    }
+    float x = ((float)h[0] * 2.3283064e-10f - 0.5f) * 2.f * extent;
+    float y = ((float)h[1] * 2.3283064e-10f - 0.5f) * 2.f * extent;
+    const float z = ((float)h[2] * 2.3283064e-10f - 0.5f) * 8.f;
+    const int kind = (int)(i & 7), sub = (int)((i >> 3) & 7);
+    if (kind == 0) {
+      if (sub == 0) y = 0.f;
+      else if (sub == 1) x = 0.f;
+      else if (sub == 2) y = -0.f;
+      else if (sub == 3) { x = 0.f; y = 0.f; }
+      else if (sub == 4) {  // on a sector edge of some zone
+        const int zn = (int)(h[2] & 3);
+        const float r = sqrtf(x * x + y * y) + 0.1f, a = (float)(h[1] % (uint32_t)c_zone_sectors[zn]) * (float)gc.sector_size[zn];
+        x = r * cosf(a); y = r * sinf(a);
+      } else if (sub == 5) {  // on a ring edge
+        const int zn = (int)(h[2] & 3);
+        const float r = fmaxf(sqrtf(x * x + y * y), 1e-6f), rr = (float)(gc.rmin[zn] + (double)(h[1] % 5u) * gc.ring_size[zn]);
+        x *= rr / r; y *= rr / r;
+      } else if (sub == 6) y = -fabsf(y) * 1e-7f;
+    }
+    bool slow;
+    const int f = dev_patch_filtered(x, y, z, gc, &slow);
+    const int e = dev_patch_exact(x, y, z, gc);
+    n_exact += slow ? 1 : 0;
+    n_bad += (f != e) ? 1 : 0;
+  }
+  atomicAdd(&stats[5], n_exact);
+  atomicAdd(&stats[6], n_bad);
+}
 
 // ------------------------------------------------------------------------------------------------
 // G1: per-point patch assignment (pc2czm, patchwork.h:431-459) + per-patch histogram
@@ -40,22 +123,7 @@ __global__ void __launch_bounds__(256) k_patch_assign(const float4* __restrict__
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = __ldg(&pts[base + i]);
-    int pid;
-    if ((double)p.z < gc.low_thr) {
-      pid = -1;
-    } else {
-      double x = (double)p.x, y = (double)p.y;
-      double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
-      if ((r <= gc.max_range) && (r > gc.min_range)) {
-        double theta = (y >= 0) ? atan2(y, x) : __dadd_rn(2.0 * 3.14159265358979323846, atan2(y, x));
-        int k = (r < gc.z2) ? 0 : (r < gc.z3) ? 1 : (r < gc.z4) ? 2 : 3;
-        int ring = min((int)__ddiv_rn(__dsub_rn(r, gc.rmin[k]), gc.ring_size[k]), c_zone_rings[k] - 1);
-        int sector = min((int)__ddiv_rn(theta, gc.sector_size[k]), c_zone_sectors[k] - 1);
-        pid = c_zone_base[k] + ring * c_zone_sectors[k] + sector;
-      } else {
-        pid = -2;
-      }
-    }
+    const int pid = dev_patch_filtered(p.x, p.y, p.z, gc);
     patch_of[base + i] = (int16_t)pid;
     if (pid >= 0)
       atomicAdd(&s_hist[pid], 1);
@@ -833,7 +901,7 @@ __device__ __forceinline__ void rank_one_patch(const FitArgs& a, int p, int b, i
       const float res = da(da(dm(q.x, n0), dm(q.y, n1)), dm(q.z, n2));
       if (res < th) f |= F_G;
       if (rejected || !(f & F_G)) {
-        BinResult r = dev_bin_point(q.x, q.y, q.z, a.bp);
+        const BinIdx r = dev_bin_filtered(q.x, q.y, q.z, a.bp);
         if (r.pass) {
           f |= F_PASS;
           if (r.ri < 0 || r.si < 0 || r.ei < 0) f |= F_QUIRK;
@@ -1014,7 +1082,23 @@ static GroundConst make_ground_const(const HostParams& hp) {
   gc.ring_size[3] = (max_range - gc.z4) / 4;
   const int sectors[4] = {16, 32, 54, 32};
   for (int k = 0; k < 4; ++k) gc.sector_size[k] = 2 * M_PI / sectors[k];
+  gc.low_thr_f = nextafterf((float)gc.low_thr, INFINITY);
+  while ((double)nextafterf(gc.low_thr_f, -INFINITY) >= gc.low_thr) gc.low_thr_f = nextafterf(gc.low_thr_f, -INFINITY);
+  gc.max_range_f = (float)gc.max_range;
+  gc.z2f = (float)gc.z2;
+  gc.z3f = (float)gc.z3;
+  gc.z4f = (float)gc.z4;
+  for (int k = 0; k < 4; ++k) {
+    gc.rmin_f[k] = (float)gc.rmin[k];
+    gc.inv_ring_f[k] = (float)(1.0 / gc.ring_size[k]);
+    gc.inv_sector_f[k] = (float)(1.0 / gc.sector_size[k]);
+  }
   return gc;
+}
+
+int launch_patch_filter_check(const HostParams& hp, long long n, uint32_t seed, float extent, unsigned long long* stats_dev, void* stream_) {
+  { TIMED("k_patch_filter_check", TSTREAM); k_patch_filter_check<<<num_sms() * 8, 256, 0, (cudaStream_t)stream_>>>(n, seed, make_ground_const(hp), extent, stats_dev); }
+  return 1;
 }
 
 int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_points, void* stream_) {

@@ -143,14 +143,17 @@ int launch_final_labels(const int64_t* off, const int32_t* scan_counts, int nsca
 int launch_label_override(const int32_t* items_dev, const int32_t* item_scan_dev, int n, const int32_t* apri_src, const int64_t* off, uint8_t* cls,
                           void* stream);
 int launch_submap(const float4* pts, const uint8_t* cls, const int64_t* off, const float* Ts_dev, int first_scan, int nscans,
-                  int max_scan_points, float4* out, unsigned long long* counter, long long cap, void* stream);
+                  int max_scan_points, float4* out, unsigned long long* counter, long long cap, unsigned keep_mask, void* stream);
 // cluster-name replay (one CTA per scan, components dealt to its warps); vox_name is indexed like the voxel arrays,
 // name_first is [nscans][name_cap]
 // max_nodes = max over the scans of voxels + points of tainted voxels; any_taint: some scan has tainted voxels
 int launch_name_replay(const HostParams& hp, BatchDev& d, int nscans, int max_nodes, int max_events, bool force_global, bool any_taint,
                        int32_t* vox_name, int32_t* name_first, int name_cap, void* stream);
 int launch_pack(const PackDesc* descs_dev, int ndesc, int max_n, int32_t* out, void* stream);
+int launch_patch_filter_check(const HostParams& hp, long long n, uint32_t seed, float extent, unsigned long long* stats_dev, void* stream);
 int launch_atan2f_probe(const float* y, const float* x, float* out, long long n, void* stream);
+int launch_bin_filter_check(const HostParams& hp, long long n, uint32_t seed, float extent, const float4* pts_dev, unsigned long long* stats_dev,
+                            void* stream);
 
 // context accessors for the translation units that do not see struct scvod_ctx (scvod_gicp.cu)
 void* ctx_stream(scvod_ctx* c);

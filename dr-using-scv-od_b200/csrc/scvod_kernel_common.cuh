@@ -78,6 +78,13 @@ inline BinParams make_bin_params(const HostParams& hp) {
   bp.azimuth_res = hp.p.azimuth_res;
   bp.range_num = hp.g.range_num;
   bp.sector_num = hp.g.sector_num;
+  // dev_bin_filtered: guard band of 1e-3 degrees around every bin edge and gate (>= 5x the provable distance between the
+  // approximate and the exact chain), plus the rounding of the bin coordinate itself (a few ulps of its largest magnitude)
+  bp.eps_deg = 1.0e-3f;
+  bp.inv_sector_res = 1.0f / bp.sector_res;
+  bp.inv_azimuth_res = 1.0f / bp.azimuth_res;
+  bp.eps_qs = bp.eps_deg * fabsf(bp.inv_sector_res) + 1.0e-6f * (360.0f + fabsf(bp.min_angle)) * fabsf(bp.inv_sector_res);
+  bp.eps_qe = bp.eps_deg * fabsf(bp.inv_azimuth_res) + 1.0e-6f * (90.0f + fabsf(bp.min_azimuth)) * fabsf(bp.inv_azimuth_res);
   return bp;
 }
 

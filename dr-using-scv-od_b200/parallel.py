@@ -97,23 +97,28 @@ def shard_chunks(n_scans: int, chunk: int, world: int, rank: int) -> List[Tuple[
 class SubmapGatherer:
     """All-gather of variable-length per-rank static submaps ([n_r, 4] float32 xyzi in the map frame).
 
-    One count exchange + one padded ``all_gather_into_tensor`` per call; buffers are allocated once for
-    ``cap_points`` per rank.  ``gather`` returns (merged buffer [world*cap, 4], counts [world]); rank r's points
-    are ``merged[r*cap : r*cap + counts[r]]`` — ``compact`` concatenates them in rank order, which is the
-    reference's concatenation order when ranks own consecutive chunks.
+    One count exchange + one ``all_gather_into_tensor`` per call; buffers are allocated once for ``cap_points`` per rank.
+    The data gather moves ``rows`` = the largest count of the call (rounded up to ``granule`` rows) per rank, not the capacity
+    (``padded=True`` restores the capacity-sized gather: the ablation of DESIGN.md section 6).  ``gather`` returns
+    (merged buffer, counts [world]); rank r's points are ``merged[r*stride : r*stride + counts[r]]`` with ``stride`` = the rows of
+    that call (``self.stride``) - ``compact`` concatenates them in rank order, which is the reference's concatenation order when
+    ranks own consecutive chunks.
     """
 
-    def __init__(self, cap_points: int, device: torch.device, group=None):
+    def __init__(self, cap_points: int, device: torch.device, group=None, granule: int = 4096):
         self.cap = int(cap_points)
         self.device = device
         self.group = group
+        self.granule = max(1, int(granule))
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.merged = torch.empty((self.world * self.cap, 4), dtype=torch.float32, device=device)
         self.counts = torch.zeros(self.world, dtype=torch.int64, device=device)
         self._mine = torch.zeros(1, dtype=torch.int64, device=device)
+        self.stride = self.cap
+        self.bytes_moved = 0  # bytes this rank received from the data gathers so far (diagnostics)
 
-    def gather(self, submap: torch.Tensor, n_points: int):
+    def gather(self, submap: torch.Tensor, n_points: int, padded: bool = False):
         if submap.shape[0] < self.cap or submap.shape[1] != 4 or submap.dtype != torch.float32:
             raise ValueError("submap must be a [>=cap, 4] float32 tensor")
         if n_points > self.cap:
@@ -121,16 +126,24 @@ class SubmapGatherer:
         self._mine.fill_(int(n_points))
         if self.world == 1:
             self.counts.copy_(self._mine)
-            self.merged[: self.cap].copy_(submap[: self.cap])
+            self.stride = self.cap
+            self.merged[: n_points].copy_(submap[: n_points])
             return self.merged, self.counts
         dist.all_gather_into_tensor(self.counts, self._mine, group=self.group)
-        dist.all_gather_into_tensor(self.merged, submap[: self.cap].contiguous(), group=self.group)
+        if padded:
+            rows = self.cap
+        else:  # every rank derives the same row count from the gathered counts (one small device->host read per call)
+            rows = int(self.counts.max().item())
+            rows = min(self.cap, max(self.granule, -(-rows // self.granule) * self.granule))
+        self.stride = rows
+        dist.all_gather_into_tensor(self.merged[: self.world * rows], submap[:rows], group=self.group)
+        self.bytes_moved += (self.world - 1) * rows * 16
         return self.merged, self.counts
 
     def compact(self) -> torch.Tensor:
         """Concatenation of every rank's valid points, in rank order."""
         counts = [int(c) for c in self.counts.tolist()]
-        return torch.cat([self.merged[r * self.cap: r * self.cap + counts[r]] for r in range(self.world)], dim=0)
+        return torch.cat([self.merged[r * self.stride: r * self.stride + counts[r]] for r in range(self.world)], dim=0)
 
 
 def max_over_ranks(seconds: float, device: torch.device, group=None) -> float:

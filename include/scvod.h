@@ -117,6 +117,14 @@ int scvod_bin(scvod_ctx* ctx, const float* xyzi, int n, uint8_t* pass, int32_t* 
               int32_t* range_idx, int32_t* sector_idx, int32_t* azimuth_idx, float* range,
               float* angle, float* azimuth);
 
+/* Test hook for the binning filter used inside the pipeline kernels: the filtered evaluation (approximate angles + guard band,
+ * exact chain for undecided points) must return exactly scvod_bin's indices and gate outcome.  Checks n generated points
+ * (xyzi == NULL; coordinates within +-extent, structured edge cases mixed in) or n caller points on the device.
+ * stats7 = {points, points that took the exact chain, mismatches (0 expected), max |q_approx - q_exact| * 1e9 for the sector and
+ * for the azimuth bin coordinate among the filter-decided points, and for generated points the patch-assignment filter of the
+ * ground stage (pc2czm, patchwork.h:431-459): points that took the double chain, mismatches (0 expected)}. */
+int scvod_bin_filter_check(scvod_ctx* ctx, const float* xyzi, int64_t n, uint32_t seed, float extent, uint64_t* stats7);
+
 /* ---- frame pipeline (the hot path proper) ---------------------------------------------------- */
 
 /* SSC::process + segment + recognize (ssc.cpp:224-251, 637-656, 834-895) for nscans scans in
@@ -175,9 +183,11 @@ int scvod_frame_point_cluster(scvod_ctx* ctx, int frame, int stage, int32_t* nam
 int scvod_frame_clusters(scvod_ctx* ctx, int frame, int cap, int32_t* name, int32_t* type,
                          int32_t* state, int32_t* npts, int32_t* nvox, float* bbox);
 
-/* Static submap of frames [f0,f1): xyz+intensity of every point whose class is not DYNAMIC,
- * transformed to the map frame with the frame's pose (SSC::saveSegCloud mode 3 semantics,
- * ssc.cpp:531-555).  Written to device memory for the NCCL all-gather; returns the point count. */
+/* Static submap of frames [f0,f1) in the map frame (transformCloud arithmetic with the frame's pose), written to device memory
+ * for the NCCL all-gather; returns the point count.  Default = the reference's instance map: the points of every cluster that
+ * is not dynamic (SSC::saveSegCloud mode 3, ssc.cpp:446-555: `*instance_map += *rgb_ptr` concatenates cluster points only), i.e.
+ * class SCVOD_PT_STATIC.  scvod_set_option("submap_all_static", 1) keeps every input point whose class is not DYNAMIC instead
+ * (ground, gated-out and unclustered points included: the dynamic-free scan). */
 int scvod_static_submap_dev(scvod_ctx* ctx, int f0, int f1, const float* poses6, void* out_xyzi_dev,
                             int64_t cap_points, int64_t* n_points);
 

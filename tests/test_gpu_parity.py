@@ -72,6 +72,33 @@ def test_binning_bit_exact(pkg, config):
     o.close()
 
 
+@pytest.mark.parametrize("config", ["semantickitti", "parkinglot"])
+def test_filtered_binning_equals_exact_chain(pkg, config):
+    """The pipeline kernels bin through a floating-point filter (dev_bin_filtered / dev_patch_filtered: approximate angles decide
+    unless they are within a guard band of a bin edge or gate, otherwise the exact glibc-atan2f / double chain).  Soundness: on
+    4 x 2^30 generated points (1/8 of them snapped onto axes, the origin, bin edges, gate radii) plus the oracle-checked edge-case
+    fixture, the filtered result equals the exact chain's in every index and gate outcome, and the filter-decided points keep a
+    >= 4x margin between the measured approximate-vs-exact distance and the guard band."""
+    P = pkg.semantickitti_params() if config == "semantickitti" else pkg.parkinglot_params()
+    s = pkg.SSC(P, device=0, max_points=65536, max_batch=1)
+    worst_s = worst_e = 0.0
+    for seed, extent in [(1, 60.0), (77, 35.0), (1234567, 90.0), (99, 8.0)]:
+        st = s.bin_filter_check(1 << 30, seed=seed, extent=extent)
+        assert st["points"] == 1 << 30
+        assert st["mismatches"] == 0, st
+        assert st["patch_mismatches"] == 0, st
+        assert 0 < st["exact"] < 0.15 * st["points"], st          # the filter decides the bulk (structured cases are 1/8 of the sample)
+        assert 0 < st["patch_exact"] < 0.15 * st["points"], st
+        worst_s, worst_e = max(worst_s, st["max_dq_sector"]), max(worst_e, st["max_dq_azimuth"])
+    # guard bands (scvod_kernel_common.cuh make_bin_params): 1e-3 degrees in bin coordinates + rounding allowance
+    assert worst_s * 4 < 1e-3 / P.sector_res, worst_s
+    assert worst_e * 4 < 1e-3 / P.azimuth_res, worst_e
+    z = np.load(os.path.join(GOLD, "bin_edge_cases.npz"))
+    st = s.bin_filter_check(0, cloud=z["xyzi"])
+    assert st["mismatches"] == 0 and st["points"] == len(z["xyzi"])
+    s.close()
+
+
 # ---- ground ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("scan_id,rings,cols", [(0, 64, 1800), (11, 64, 1800), (2, 16, 450), (4, 128, 2250)])
 def test_ground_order_bit_exact(pkg, oracle, scan_id, rings, cols):
@@ -353,10 +380,15 @@ def test_full_size_batch_properties(pkg):
     l2 = t.segDF(scans[:4], poses[:4])
     for f in range(3):
         assert np.array_equal(l2[f], labels[f])
-    # static submap: one point per non-dynamic input point
+    # static submap: default = the instance map (points of non-dynamic clusters, ssc.cpp:531-555) ...
     import torch
     total = sum(len(x) for x in scans)
     out = torch.empty((total, 4), dtype=torch.float32, device="cuda:0")
+    cnt = s.static_submap_device(0, n, poses, out.data_ptr(), total)
+    assert cnt == sum(int((l == pkg.PT_STATIC).sum()) for l in labels)
+    inst = out[:cnt].cpu().numpy().copy()
+    # ... or, as an option, one point per non-dynamic input point
+    s.set_option("submap_all_static", 1)
     cnt = s.static_submap_device(0, n, poses, out.data_ptr(), total)
     assert cnt == sum(int((l != pkg.PT_DYNAMIC).sum()) for l in labels)
     assert torch.isfinite(out[:cnt]).all()
@@ -375,6 +407,17 @@ def test_full_size_batch_properties(pkg):
     got = out[:cnt].cpu().numpy().view(np.uint32)
     key = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
     assert np.array_equal(key(exp), key(got))
+    # the instance map is the subset of it that belongs to clusters
+    exp_i = []
+    for f in range(n):
+        T = pkg.pose_matrix(poses[f]).astype(np.float32)
+        p = scans[f][labels[f] == pkg.PT_STATIC].astype(np.float32)
+        q = np.empty_like(p)
+        for r in range(3):
+            q[:, r] = ((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3]
+        q[:, 3] = p[:, 3]
+        exp_i.append(q)
+    assert np.array_equal(key(np.concatenate(exp_i).view(np.uint32)), key(inst.view(np.uint32)))
     s.close()
     t.close()
 

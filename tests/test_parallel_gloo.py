@@ -50,13 +50,14 @@ def _worker(rank, world, port, results):
     par = load_parallel()
     dev = torch.device("cpu")
     cap = 1000
-    g = par.SubmapGatherer(cap, dev)
+    g = par.SubmapGatherer(cap, dev, granule=64)
     ok = True
-    for step in range(3):
+    for step in range(4):
         n = 100 * (rank + 1) + 7 * step  # different valid counts per rank and per step
         sub = torch.full((cap, 4), float("nan"))
         sub[:n] = torch.arange(n * 4, dtype=torch.float32).reshape(n, 4) + 10000 * rank + step
-        merged, counts = g.gather(sub, n)
+        merged, counts = g.gather(sub, n, padded=(step == 3))  # exact-size rows (default) and the capacity-sized ablation
+        ok &= g.stride == (cap if step == 3 else -(-max(100 * world + 7 * step, 1) // 64) * 64)
         want_counts = [100 * (r + 1) + 7 * step for r in range(world)]
         ok &= counts.tolist() == want_counts
         comp = g.compact()
