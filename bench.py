@@ -90,6 +90,10 @@ def bind_to_gpu_numa_node(local_rank, local_world):
 
         nodes = [node_of(lr) for lr in range(local_world)]
         node = nodes[local_rank]
+        if node < 0 or len(set(nodes)) < 2:
+            # no NUMA information (containers often report -1) or a single node: leave the threads to the scheduler.  Confining each rank
+            # to its 1/N share of the cores was measured on the 8-GPU box (32 cores, node -1): 158k vs 178k+ scans/s unconfined
+            return f"not pinned (numa nodes of the local GPUs: {sorted(set(nodes))})"
         allowed = sorted(os.sched_getaffinity(0))
         cores = allowed
         if node >= 0:
@@ -288,6 +292,7 @@ def main():
     ap.add_argument("--concurrent-timing", action="store_true",
                     help="tuning runs (with --quick): per-kernel CUDA-event durations measured INSIDE the multi-worker run (kernels of different "
                          "workers overlap, so the durations are not additive; a kernel stretched against its single-stream time is contended)")
+    ap.add_argument("--with-e2e", action="store_true", help="tuning runs (with --quick): also time the host-buffer (e2e) leg")
     ap.add_argument("--trace", default="", help="tuning runs (with --quick): after the timed region, record a CUPTI kernel timeline of 2 more steps "
                                                  "with torch.profiler and write it to this chrome-trace file (tools/trace_gaps.py reads it)")
     ap.add_argument("--skip-tracking", action="store_true", help="ablation: per-scan stages only (INVALID as a bench number)")
@@ -365,8 +370,11 @@ def main():
             self.labels_host = torch.empty(max_pts, dtype=torch.uint8).pin_memory()
             # two send buffers per worker: the all-gather of chunk i runs while the worker already fills the other one for chunk i+1
             self.submaps = [torch.empty((max_pts, 4), dtype=torch.float32, device=dev) for _ in range(2 if world > 1 else 1)]
-            self.submap_free = [threading.Event() for _ in self.submaps]
-            for ev in self.submap_free:
+            # per send buffer: "its gather has been issued" (set by the comm thread) and the CUDA event recorded right after that gather;
+            # the worker itself waits for both before it overwrites the buffer, so the comm thread never has to come back to it
+            self.submap_issued = [threading.Event() for _ in self.submaps]
+            self.submap_done = [None for _ in self.submaps]
+            for ev in self.submap_issued:
                 ev.set()
             self.count = 0
 
@@ -398,8 +406,11 @@ def main():
             ssc.refresh_labels(0, S)
         k = wk.count % len(wk.submaps)
         if world > 1:
-            wk.submap_free[k].wait()  # the comm thread may still be gathering the submap this buffer held two chunks ago
-            wk.submap_free[k].clear()
+            wk.submap_issued[k].wait()  # the gather of the submap this buffer held two chunks ago has been issued ...
+            if wk.submap_done[k] is not None:
+                wk.submap_done[k].synchronize()  # ... and has finished reading it
+                wk.submap_done[k] = None
+            wk.submap_issued[k].clear()
         return k, ssc.static_submap_device(0, S, b["poses"], wk.submaps[k].data_ptr(), max_pts)
 
     def barrier():
@@ -429,10 +440,8 @@ def main():
                     cv.notify_all()
 
         def comm():
-            # One communication thread issues the gathers in chunk order (the same order on every rank) on its own stream.  It never
-            # blocks a worker: a send buffer is handed back once the event recorded after its gather has completed, which is checked
-            # when the next chunks come by (and drained at the end).
-            inflight = []
+            # One communication thread issues the gathers in chunk order (the same order on every rank) on its own stream and never
+            # waits for a gather to finish: the worker that owns a send buffer waits for that buffer's event before reusing it.
             with torch.cuda.stream(comm_stream):
                 for i in range(first_step, first_step + nsteps):
                     with cv:
@@ -446,13 +455,12 @@ def main():
                         gather_count[0] += 1
                     ev = torch.cuda.Event()
                     ev.record(comm_stream)
-                    inflight.append((ev, wk, k))
-                    while inflight and inflight[0][0].query():
-                        _, w2, k2 = inflight.pop(0)
-                        w2.submap_free[k2].set()
-                for ev, w2, k2 in inflight:
-                    ev.synchronize()
-                    w2.submap_free[k2].set()
+                    wk.submap_done[k] = ev
+                    wk.submap_issued[k].set()
+                comm_stream.synchronize()
+            for wk in workers:  # an error elsewhere must not leave a worker waiting for a gather that will never be issued
+                for ev in wk.submap_issued:
+                    ev.set()
 
         threads = [threading.Thread(target=work, args=(wk,)) for wk in workers]
         if world > 1:
@@ -507,12 +515,16 @@ def main():
                 run_steps(5000 * W, 2 * W, False)
                 torch.cuda.synchronize()
             prof.export_chrome_trace(args.trace)
+        e2e_quick = None
+        if args.with_e2e:
+            secs_q, _, _, _ = timed(True, False)
+            e2e_quick = world * W * S * args.steps / secs_q
         if rank == 0:
             if crep:
                 for k, (ms, cnt) in sorted(crep.items(), key=lambda kv: -kv[1][0]):
                     print(f"  {k:26s} {ms / (W * args.steps):8.4f} ms/chunk under concurrency ({cnt // (W * args.steps)} launches/chunk)", file=sys.stderr)
             print(json.dumps({"quick": True, "value": world * W * S * args.steps / secs_dev, "unit": UNIT, "workers": W, "ms_per_step": 1000.0 * secs_dev / args.steps,
-                              "skip_tracking": args.skip_tracking, "gpu_launches": int(launches), "reallocs_in_timed_region": int(reallocs[0]), "host_cores_busy": round(cpu_busy[0], 2), "host_cores": host_cores(), "n_gpus": world, "gather": args.gather if world > 1 else None,
+                              "e2e": e2e_quick, "skip_tracking": args.skip_tracking, "gpu_launches": int(launches), "reallocs_in_timed_region": int(reallocs[0]), "host_cores_busy": round(cpu_busy[0], 2), "host_cores": host_cores(), "n_gpus": world, "gather": args.gather if world > 1 else None,
                               "submap": args.submap, "host_binding": pin_note,
                               "gather_mb_per_chunk": (gatherer.bytes_moved / max(1, gather_count[0]) / 1e6) if gatherer else None}))
         if world > 1:
@@ -531,7 +543,7 @@ def main():
             for i in range(args.steps):
                 k, _ = step(workers[0], 2000 + i, False)
                 if world > 1:
-                    workers[0].submap_free[k].set()
+                    workers[0].submap_issued[k].set()
         torch.cuda.synchronize()
         rep = pkg.kernel_timing_report()
         pkg.kernel_timing(False)

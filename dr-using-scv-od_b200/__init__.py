@@ -89,7 +89,7 @@ EXPORTS = (
     "scvod_gicp_normals", "scvod_pose_matrix", "scvod_initialization", "scvod_prefetch_scans",
     "scvod_export_tail", "scvod_track_from_tail", "scvod_apply_tail_states", "scvod_load_kitti", "scvod_load_kitti_dev",
     "scvod_evaluate_map", "scvod_evaluate_confusion", "scvod_synth_scan_labeled",
-    "scvod_knn_normals", "scvod_calibrate_intensity", "scvod_region_growing", "scvod_bin_filter_check",
+    "scvod_knn_normals", "scvod_calibrate_intensity", "scvod_region_growing", "scvod_bin_filter_check", "scvod_last_failed_scan",
 )
 
 _lib = None
@@ -252,6 +252,11 @@ class SSC:
     def set_option(self, key: str, value: int):
         _check(self._lib.scvod_set_option(self._ctx, key.encode(), int(value)))
 
+    @property
+    def last_failed_scan(self) -> int:
+        """Index (inside the failing push call) of the scan that exceeded a per-scan capacity, -1 if none."""
+        return int(self._lib.scvod_last_failed_scan(self._ctx))
+
     def stat(self, key: str) -> int:
         v = ctypes.c_int64()
         _check(self._lib.scvod_get_stat(self._ctx, key.encode(), ctypes.byref(v)))
@@ -273,13 +278,19 @@ class SSC:
 
     def process_flat(self, flat: np.ndarray, offsets: np.ndarray):
         offsets = np.ascontiguousarray(offsets, np.int64)
-        _check(self._lib.scvod_push_scans(self._ctx, _ptr(flat), _ptr(offsets), len(offsets) - 1))
-        self.frame_sizes.extend(int(x) for x in np.diff(offsets))
+        n0 = self.num_frames
+        try:
+            _check(self._lib.scvod_push_scans(self._ctx, _ptr(flat), _ptr(offsets), len(offsets) - 1))
+        finally:  # a failing call keeps the batches it committed before the failing one
+            self.frame_sizes.extend(int(x) for x in np.diff(offsets)[: self.num_frames - n0])
 
     def process_device(self, dev_ptr: int, offsets: np.ndarray):
         offsets = np.ascontiguousarray(offsets, np.int64)
-        _check(self._lib.scvod_push_scans_dev(self._ctx, ctypes.c_void_p(dev_ptr), _ptr(offsets), len(offsets) - 1))
-        self.frame_sizes.extend(int(x) for x in np.diff(offsets))
+        n0 = self.num_frames
+        try:
+            _check(self._lib.scvod_push_scans_dev(self._ctx, ctypes.c_void_p(dev_ptr), _ptr(offsets), len(offsets) - 1))
+        finally:
+            self.frame_sizes.extend(int(x) for x in np.diff(offsets)[: self.num_frames - n0])
 
     def extractGroudByPatchWork(self, cloud: np.ndarray):
         """PatchWork::estimate_ground: returns (ground_idx, nonground_idx) in the reference's output order."""

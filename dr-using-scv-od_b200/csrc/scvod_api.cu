@@ -276,9 +276,9 @@ struct scvod_ctx {
   std::vector<FrameHost> frames;
   int tracked = 0;  // frames [0, tracked) have been used as frame_pre_
   bool head_tracked = false;  // frame 0 has been frame_next_ of an imported tail (scvod_track_from_tail)
-  // The tracking chain runs on its own stream of the HIGHEST priority: a k_track launch is tiny and latency critical (the host
-  // waits for its answer before it can decide the pair), while the per-scan kernels of the other contexts are bulk work; the
-  // block scheduler hands freed CTA slots to the higher priority first, so a pair no longer queues behind whole grids.
+  // The tracking chain runs on its own stream; SCVOD_TRACK_PRIORITY=1 gives it the highest priority (a k_track launch is tiny and
+  // latency critical - the host waits for its answer before it can decide the pair - while the per-scan kernels of the other
+  // contexts are bulk work; the block scheduler then hands freed CTA slots to the chain first).
   cudaStream_t tstream = nullptr;
   cudaEvent_t tlink = nullptr;
   cudaEvent_t sync_event = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning (see wait_stream)
@@ -292,6 +292,8 @@ struct scvod_ctx {
   int init_base = -1;
   bool have_init = false;
   int track_name = 0;  // SSC::name (ssc.h:49)
+  int failed_scan = -1;  // index (in the offending push call) of the scan that made the call fail, -1: none / not attributable to one scan
+  int batch_first_scan = 0;  // position of the batch being pushed inside its push call
   int64_t stat_track_points = 0, stat_track_pairs = 0, stat_scans = 0, stat_points = 0, stat_apri = 0, stat_voxels = 0, stat_tvox = 0, stat_tpts = 0;
   void* gicp = nullptr;  // GICP state (scvod_gicp.cu)
   void (*gicp_free)(void*) = nullptr;
@@ -470,7 +472,10 @@ extern "C" int scvod_create(const scvod_params* p, int device, int max_points, i
   {
     int lo = 0, hi = 0;  // numerically lower = higher priority
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    static const bool flat = getenv("SCVOD_TRACK_PRIORITY") && atoi(getenv("SCVOD_TRACK_PRIORITY")) == 0;  // A/B switch
+    // measured on one B200 with 16 contexts: a high-priority tracking stream shortens every pair (112 -> ~60 us under load, host
+    // polling 10 -> 6.5 busy cores) but does not raise the throughput, which is bound by the aggregate kernel work (35.6k flat vs
+    // 33.5k scans/s prioritised; 25.2k vs 24.8k on 4 cores): opt-in
+    static const bool flat = !(getenv("SCVOD_TRACK_PRIORITY") && atoi(getenv("SCVOD_TRACK_PRIORITY")) != 0);
     CU(cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, flat ? lo : hi));
     CU(cudaEventCreateWithFlags(&c->tlink, cudaEventDisableTiming));
   }
@@ -599,7 +604,10 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   for (int s = 0; s <= nscans; ++s) off[s] = offsets[s] - offsets[0];
   for (int s = 0; s < nscans; ++s) {
     int64_t n = off[s + 1] - off[s];
-    if (n < 0 || n > c->max_points) return fail(SCVOD_ERR_CAPACITY, "scan larger than max_points");
+    if (n < 0 || n > c->max_points) {
+      c->failed_scan = c->batch_first_scan + s;
+      return fail(SCVOD_ERR_CAPACITY, "scan " + std::to_string(c->failed_scan) + " larger than max_points");
+    }
     max_n = std::max<int>(max_n, (int)n);
   }
   if (total > (int64_t)c->ws.cap_points) return fail(SCVOD_ERR_CAPACITY, "batch larger than workspace");
@@ -696,11 +704,22 @@ static int push_batch(scvod_ctx* c, const void* xyzi, bool on_device, const int6
   bool any_taint = false;
   for (int s = 0; s < nscans; ++s) {
     int V = sc[s * 8 + 3], E = sc[s * 8 + 5], G = sc[s * 8 + 7];
-    if (G < 0 || G > w.edge_cap) return fail(SCVOD_ERR_CAPACITY, "similarity edge table overflow");
-    if (tc[s * kTaintCntStride + 3])
-      return fail(SCVOD_ERR_CAPACITY, "scan holds more points with a -1 curved-voxel index (or voxels / points aliased by them) than the side tables take");
+    // capacity limits are per scan: name the scan, so that the caller can drop or re-voxelise it and push the others again
+    // (the frames of this batch are not kept; frames of earlier calls and of earlier batches of this call are)
+    const std::string which = "scan " + std::to_string(c->batch_first_scan + s) + " of the call: ";
+    if (G < 0 || G > w.edge_cap) {
+      c->failed_scan = c->batch_first_scan + s;
+      return fail(SCVOD_ERR_CAPACITY, which + "similarity edge table overflow");
+    }
+    if (tc[s * kTaintCntStride + 3]) {
+      c->failed_scan = c->batch_first_scan + s;
+      return fail(SCVOD_ERR_CAPACITY, which + "more points with a -1 curved-voxel index (or voxels / points aliased by them) than the side tables take");
+    }
     const int ntv = tc[s * kTaintCntStride + 1], ntp = tc[s * kTaintCntStride + 2];
-    if ((int64_t)V + ntp > off[s + 1] - off[s]) return fail(SCVOD_ERR_CAPACITY, "scan too small for the replay scratch of its aliased voxels");
+    if ((int64_t)V + ntp > off[s + 1] - off[s]) {
+      c->failed_scan = c->batch_first_scan + s;
+      return fail(SCVOD_ERR_CAPACITY, which + "too small for the replay scratch of its aliased voxels");
+    }
     any_taint = any_taint || ntp > 0;
     tvb[s + 1] = tvb[s] + ntv;
     tpb[s + 1] = tpb[s] + ntp;
@@ -935,6 +954,7 @@ static int push_scans_impl(scvod_ctx* c, const void* xyzi, bool on_device, const
   if (!c || !offsets || nscans < 0 || (!xyzi && nscans > 0 && offsets[nscans] > offsets[0]))
     return fail(SCVOD_ERR_ARG, "bad arguments to scvod_push_scans");
   CU(cudaSetDevice(c->device));
+  c->failed_scan = -1;
   int s = 0;
   while (s < nscans) {
     int e = s;
@@ -943,7 +963,11 @@ static int push_scans_impl(scvod_ctx* c, const void* xyzi, bool on_device, const
       pts += offsets[e + 1] - offsets[e];
       ++e;
     }
-    if (e == s) return fail(SCVOD_ERR_CAPACITY, "scan larger than the batch workspace");
+    if (e == s) {
+      c->failed_scan = s;
+      return fail(SCVOD_ERR_CAPACITY, "scan " + std::to_string(s) + " larger than the batch workspace");
+    }
+    c->batch_first_scan = s;
     int rc = push_batch(c, xyzi, on_device, offsets + s, e - s);
     if (rc != SCVOD_OK) return rc;
     s = e;
@@ -982,6 +1006,8 @@ extern "C" int scvod_push_scans(scvod_ctx* c, const float* xyzi, const int64_t* 
 extern "C" int scvod_push_scans_dev(scvod_ctx* c, const void* xyzi_dev, const int64_t* offsets, int nscans) {
   return push_scans_impl(c, xyzi_dev, true, offsets, nscans);
 }
+
+extern "C" int scvod_last_failed_scan(const scvod_ctx* c) { return c ? c->failed_scan : -1; }
 
 extern "C" int scvod_num_frames(const scvod_ctx* c) { return c ? (int)c->frames.size() : 0; }
 
@@ -1180,6 +1206,8 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
       // every probe: with more contexts than host cores per GPU the waiting threads must not starve the ones that have
       // cluster decisions to compute.  Every ~2000 probes make sure the stream is still alive.
       static const int spin_first = getenv("SCVOD_POLL_SPINS") ? atoi(getenv("SCVOD_POLL_SPINS")) : 200;
+      static const int nap_us = getenv("SCVOD_POLL_NAP_US") ? atoi(getenv("SCVOD_POLL_NAP_US")) : 0;
+      static const int nap_after = getenv("SCVOD_POLL_NAP_AFTER") ? atoi(getenv("SCVOD_POLL_NAP_AFTER")) : 32;
       int spins = 0, since_query = 0;
       while ((nt = *flag) < 0) {
         if (++since_query >= 2000) {
@@ -1193,7 +1221,14 @@ static int diff_clusters(scvod_ctx* c, FrameHost& pre, FrameHost& next, const fl
           if (qe != cudaErrorNotReady) return fail(SCVOD_ERR_CUDA, std::string("k_track: ") + cudaGetErrorString(qe));
         }
         if (++spins > spin_first) {
-          sched_yield();
+          // more waiting contexts than host cores: after a few dozen yields the thread sleeps in short naps instead, so that the
+          // cores go to the threads that have cluster decisions or launches to do (a nap costs latency on this chain only)
+          if (nap_us > 0 && spins > spin_first + nap_after) {
+            timespec ts = {0, nap_us * 1000L};
+            nanosleep(&ts, nullptr);
+          } else {
+            sched_yield();
+          }
         } else {
 #if defined(__x86_64__)
           __builtin_ia32_pause();
@@ -1325,7 +1360,10 @@ static int track_cars(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
           src.npts -= lost;
           src.part_end.clear();  // point order of a split non-car cluster is never read again
           src.part_end.push_back((int)src.occupy_voxels.size());
-          nset.insert(std::make_pair(cluster_new.name, cluster_new));
+          {
+            const int new_name = cluster_new.name;
+            nset.insert(std::make_pair(new_name, std::move(cluster_new)));  // same key, same insertion point: iteration order unchanged
+          }
         }
       } else {
         if (nset[it->first].type == P.car) {
@@ -1363,7 +1401,10 @@ static int track_cars(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
         }
       }
       for (int v : cluster_new.occupy_voxels) nlabel[v] = cluster_new.name;
-      nset.insert(std::make_pair(cluster_new.name, cluster_new));
+      {
+            const int new_name = cluster_new.name;
+            nset.insert(std::make_pair(new_name, std::move(cluster_new)));  // same key, same insertion point: iteration order unchanged
+          }
     }
   }
   c->tout_cur = out_buf;  // this pass's output holds the carried clouds of `next`

@@ -132,6 +132,12 @@ int scvod_bin_filter_check(scvod_ctx* ctx, const float* xyzi, int64_t n, uint32_
  * offsets has nscans+1 entries (point offsets into xyzi). */
 int scvod_push_scans(scvod_ctx* ctx, const float* xyzi, const int64_t* offsets, int nscans);
 
+/* Per-scan error isolation: when the last scvod_push_scans / scvod_push_scans_dev call failed because ONE scan exceeded a per-scan
+ * capacity (max_points, similarity-edge table, side tables of aliased voxels), the index of that scan inside the call; -1 otherwise.
+ * Frames of the failing batch (max_batch consecutive scans) are not kept; earlier batches of the same call are (scvod_num_frames
+ * tells how many): drop or re-voxelise the named scan and push the remaining scans again. */
+int scvod_last_failed_scan(const scvod_ctx* ctx);
+
 /* Optional double buffering for streams of batches: start the host->device upload of the scans that a LATER scvod_push_scans call
  * will be given (same buffer and offsets).  The copy runs on a private stream and overlaps whatever the context is doing (the
  * tracking chain of the previous batch, typically); that push then finds its points on the device.  The host buffer must stay

@@ -422,6 +422,29 @@ def test_full_size_batch_properties(pkg):
     t.close()
 
 
+def test_failing_scan_is_named_and_the_rest_can_be_pushed(pkg, oracle):
+    """Per-scan error isolation: a scan that exceeds a per-scan capacity fails the call with its index (scvod_last_failed_scan);
+    earlier batches of the call stay, and pushing the remaining scans gives the same result as never having seen the bad one."""
+    P = pkg.semantickitti_params()
+    good = [pkg.synth_scan(conftest.SEED + 5, k, rings=32, cols=900)[0] for k in range(5)]
+    big = pkg.synth_scan(conftest.SEED + 5, 9, rings=64, cols=1800)[0]
+    s = pkg.SSC(P, device=0, max_points=32 * 900, max_batch=2)
+    with pytest.raises(pkg.ScvodError) as e:
+        s.process(good[:3] + [big] + good[3:])  # batches of 2: [g0 g1] [g2 BIG] [g3 g4]
+    assert "scan 3" in str(e.value)
+    assert s.last_failed_scan == 3
+    assert s.num_frames == 2  # the first batch was committed, the failing one was not
+    s.process(good[2:])
+    assert s.last_failed_scan == -1 and s.num_frames == 5
+    for f, g in enumerate(good):
+        oracle.push_scan(g)
+    for f in range(5):
+        assert np.array_equal(s.frame_apri(f)[1], oracle.apri(f)[1])
+        for st in range(3):
+            assert np.array_equal(s.frame_point_cluster(f, st), oracle.point_cluster(f, st))
+    s.close()
+
+
 def test_concurrent_contexts_give_the_sequential_result(pkg):
     """bench.py runs up to 16 contexts (one per host thread and CUDA stream) on one GPU: results must not depend on it."""
     import threading
