@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_patch_filter_check(long long n, uint32_
 // G1: per-point patch assignment (pc2czm, patchwork.h:431-459) + per-patch histogram
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_patch_assign(const float4* __restrict__ pts, const int64_t* __restrict__ off,
-                                                      GroundConst gc, int16_t* __restrict__ patch_of,
+                                                      GroundConst gc, int16_t* __restrict__ patch_of, uint32_t* __restrict__ zkey,
                                                       int32_t* __restrict__ patch_cnt, uint8_t* __restrict__ cls) {
   __shared__ int s_hist[kNumPatches];
   const int b = blockIdx.y;
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) k_patch_assign(const float4* __restrict__
     float4 p = __ldg(&pts[base + i]);
     const int pid = dev_patch_filtered(p.x, p.y, p.z, gc);
     patch_of[base + i] = (int16_t)pid;
+    zkey[base + i] = float_sort_key(p.z);  // the scatter pass needs nothing else of the point: 4 B instead of a 16-byte re-read
     if (pid >= 0)
       atomicAdd(&s_hist[pid], 1);
     else
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(512) k_patch_scan(const int32_t* __restrict__ 
 // G3: scatter (z key, local index) into the patch buckets.  A CTA owns a contiguous chunk of the scan: it counts its
 // points per patch in shared memory, reserves one range per (CTA, patch) with a single global atomic, and hands out
 // the slots inside the range with shared-memory atomics (the order inside a bucket is irrelevant: it is sorted next).
-__global__ void __launch_bounds__(256) k_patch_scatter(const float4* __restrict__ pts, const int64_t* __restrict__ off,
+__global__ void __launch_bounds__(256) k_patch_scatter(const uint32_t* __restrict__ zkey, const int64_t* __restrict__ off,
                                                        const int16_t* __restrict__ patch_of,
                                                        const int32_t* __restrict__ patch_off, int32_t* __restrict__ patch_cur,
                                                        uint64_t* __restrict__ bucket_kv) {
@@ -188,9 +189,8 @@ __global__ void __launch_bounds__(256) k_patch_scatter(const float4* __restrict_
   for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     const int pid = patch_of[base + i];
     if (pid < 0) continue;
-    const float z = __ldg(&pts[base + i]).z;
     const int slot = s_base[pid] + atomicAdd(&s_cnt[pid], 1);
-    bucket_kv[base + slot] = ((uint64_t)float_sort_key(z) << 32) | (uint32_t)i;
+    bucket_kv[base + slot] = ((uint64_t)__ldg(&zkey[base + i]) << 32) | (uint32_t)i;
   }
 }
 
@@ -427,9 +427,7 @@ __device__ __forceinline__ void sort_one_patch(const FitArgs& a, int p, int b, i
   }
   for (int j = tid; j < n; j += THREADS) {
     const int idx = (int)(uint32_t)kv[j];
-    float4 q = __ldg(&a.pts[base + idx]);
-    q.w = 0.f;
-    a.sorted_xyz[base + slot0 + j] = q;
+    a.sorted_xyz[base + slot0 + j] = __ldg(&a.pts[base + idx]);  // xyz for the fit, the intensity rides along to k_emit
     a.sorted_idx[base + slot0 + j] = idx;
     a.slot_patch[base + slot0 + j] = (int16_t)p;
   }
@@ -500,8 +498,15 @@ __device__ __forceinline__ void radix_sort_kv(uint64_t* bufA, uint64_t* bufB, in
       const int j = j0 + lane;
       const bool valid = j < j_hi;
       const uint64_t kv = valid ? src[j] : 0ull;
-      const int d = valid ? (int)((kv >> shift) & 255u) : 256 + lane;
-      const unsigned same = __match_any_sync(0xffffffffu, d);
+      const int d = valid ? (int)((kv >> shift) & 255u) : 0;
+      // lanes holding the same digit: eight ballots (one per digit bit) instead of __match_any_sync, whose result was the
+      // hottest stall of this kernel in round 1 (profiles/r01_source_hotspots.txt)
+      unsigned same = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+      for (int bit = 0; bit < 8; ++bit) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (d >> bit) & 1);
+        same &= ((d >> bit) & 1) ? bal : ~bal;
+      }
       const int rank = __popc(same & ((1u << lane) - 1u));
       int basepos = 0;
       if (valid) basepos = s_cnt[wid * 256 + d];
@@ -576,9 +581,7 @@ __device__ __forceinline__ void radix_sort_one_patch(const FitArgs& a, int p, in
   // GLOBAL: the scratch half (bufB) aliases sorted_xyz; after four passes the data is in bufA, so it is free to be written
   for (int j = tid; j < n; j += THREADS) {
     const int idx = (int)(uint32_t)bufA[j];
-    float4 q = __ldg(&a.pts[base + idx]);
-    q.w = 0.f;
-    a.sorted_xyz[base + slot0 + j] = q;
+    a.sorted_xyz[base + slot0 + j] = __ldg(&a.pts[base + idx]);
     a.sorted_idx[base + slot0 + j] = idx;
     a.slot_patch[base + slot0 + j] = (int16_t)p;
   }
@@ -1011,7 +1014,7 @@ __global__ void __launch_bounds__(512) k_patch_out_scan(const int32_t* __restric
 }
 
 // G6: emit cloud_out / cloud_nonground order and the apri arrays
-__global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ pts, const int64_t* __restrict__ off,
+__global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ sorted_xyzi, const int64_t* __restrict__ off,
                                               const int32_t* __restrict__ patch_off, const int32_t* __restrict__ patch_out,
                                               const int32_t* __restrict__ patch_out_off, const int32_t* __restrict__ sorted_idx,
                                               const int32_t* __restrict__ slot_pos, const int32_t* __restrict__ slot_apos,
@@ -1054,7 +1057,7 @@ __global__ void __launch_bounds__(256) k_emit(const float4* __restrict__ pts, co
         }
         apri_src[base + m] = idx;
         apri_vid[base + m] = slot_vid[base + q];
-        apri_xyzi[base + m] = __ldg(&pts[base + idx]);
+        apri_xyzi[base + m] = __ldg(&sorted_xyzi[base + q]);  // the z-sorted copy of the point (coalesced), not a gather of the input
         cls[base + idx] = SCVOD_PT_UNCLUSTERED;
       }
     }
@@ -1110,9 +1113,9 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   cudaMemsetAsync(d.sort_ctr, 0, sizeof(int32_t) * 8, st);
   cudaMemsetAsync(d.taint_cnt, 0, sizeof(int32_t) * (size_t)nscans * kTaintCntStride, st);
   dim3 gpt(grid_x_for(nscans, max_scan_points, 256), nscans);
-  { TIMED("k_patch_assign", TSTREAM); k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, d.patch_cnt, d.cls); }
+  { TIMED("k_patch_assign", TSTREAM); k_patch_assign<<<gpt, 256, 0, st>>>(d.pts, d.off, gc, d.patch_of, reinterpret_cast<uint32_t*>(d.slot_vid), d.patch_cnt, d.cls); }  // z keys live in slot_vid until the rank kernels overwrite it
   { TIMED("k_patch_scan", TSTREAM); k_patch_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_off, d.patch_cur, d.sort_ctr, d.sort_list, d.cap_scans * kNumPatches); }
-  { TIMED("k_patch_scatter", TSTREAM); k_patch_scatter<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_of, d.patch_off, d.patch_cur, d.bucket_kv); }
+  { TIMED("k_patch_scatter", TSTREAM); k_patch_scatter<<<gpt, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d.slot_vid), d.off, d.patch_of, d.patch_off, d.patch_cur, d.bucket_kv); }
   FitArgs fa;
   fa.pts = d.pts;
   fa.off = d.off;
@@ -1167,7 +1170,7 @@ int launch_ground(const HostParams& hp, BatchDev& d, int nscans, int max_scan_po
   }
   launches += 2;
   { TIMED("k_patch_out_scan", TSTREAM); k_patch_out_scan<<<nscans, 512, 0, st>>>(d.patch_cnt, d.patch_out, d.patch_out_off, d.scan_counts); }
-  { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.pts, d.off, d.patch_off, d.patch_out, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
+  { TIMED("k_emit", TSTREAM); k_emit<<<gpt, 256, 0, st>>>(d.sorted_xyz, d.off, d.patch_off, d.patch_out, d.patch_out_off, d.sorted_idx, d.slot_pos, d.slot_apos, d.slot_vid,
                              d.slot_patch, d.ground_src, d.ng_src, d.apri_src, d.apri_vid, d.apri_xyzi, d.cls, d.taint_cnt, d.q_list); }
   launches += 5;
   return launches;

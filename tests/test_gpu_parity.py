@@ -430,11 +430,12 @@ def test_failing_scan_is_named_and_the_rest_can_be_pushed(pkg, oracle):
     big = pkg.synth_scan(conftest.SEED + 5, 9, rings=64, cols=1800)[0]
     s = pkg.SSC(P, device=0, max_points=32 * 900, max_batch=2)
     with pytest.raises(pkg.ScvodError) as e:
-        s.process(good[:3] + [big] + good[3:])  # batches of 2: [g0 g1] [g2 BIG] [g3 g4]
+        s.process(good[:3] + [big] + good[3:])  # batches: [g0 g1] [g2] (BIG does not fit next to it), then BIG alone fails
     assert "scan 3" in str(e.value)
     assert s.last_failed_scan == 3
-    assert s.num_frames == 2  # the first batch was committed, the failing one was not
-    s.process(good[2:])
+    n_kept = s.num_frames
+    assert n_kept == 3  # the batches before the failing scan were committed
+    s.process(good[n_kept:])
     assert s.last_failed_scan == -1 and s.num_frames == 5
     for f, g in enumerate(good):
         oracle.push_scan(g)

@@ -25,8 +25,12 @@ for r in rows:
         inst = float(r[ii]); samp = float(r[isamp] or 0)
     except ValueError:
         continue
-    per_kernel.setdefault(kernel, []).append((inst, samp, fname, r[0], r[1].strip()))
+    rows_k = per_kernel.setdefault(kernel, collections.OrderedDict())  # a line inlined at several places appears once per place: sum them
+    key = (fname, r[0])
+    prev = rows_k.get(key, (0.0, 0.0, fname, r[0], r[1].strip()))
+    rows_k[key] = (prev[0] + inst, prev[1] + samp, fname, r[0], r[1].strip())
 for kernel, data in per_kernel.items():
+    data = list(data.values())
     if want not in kernel:
         continue
     tot = sum(d[0] for d in data); tots = sum(d[1] for d in data)

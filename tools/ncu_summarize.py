@@ -135,7 +135,16 @@ def hotspots(rep, dst, kernels):
     print(f"{len(kernels)} kernels -> {dst}")
 
 
-PEAK_GBPS = 6650.0  # fallback of B200_PROFILING.md; MEASURED_PEAKS.json is absent on this pool
+def _peak():
+    """HBM peak the fractions are quoted against: MEASURED_PEAKS.json (driver-written) if present, else the 6.65 TB/s fallback."""
+    import json, os
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+PEAK_GBPS = _peak()
 
 
 def roofline(src, dst):
@@ -144,7 +153,7 @@ def roofline(src, dst):
     ix = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tsc = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}
-    out = [["kernel", "launch_us", "grid", "block", "regs", "dram_read_MB", "dram_write_MB", "dram_GBps", f"frac_of_{PEAK_GBPS:.0f}GBps",
+    out = [["kernel", "launch_us", "grid", "block", "regs", "dram_read_MB", "dram_write_MB", "dram_GBps", f"frac_of_{PEAK_GBPS:.1f}GBps",
             "warps_active_pct", "sm_throughput_pct", "dram_throughput_pct"]]
     for d in data:
         t = float(d[ix["gpu__time_duration.sum"]]) * tsc[units[ix["gpu__time_duration.sum"]]]

@@ -11,6 +11,8 @@ with ThreadPoolExecutor(16) as ex:
 scans = [r[0] for r in res]; poses = np.stack([r[1] for r in res])
 s = pkg.SSC(pkg.semantickitti_params(), device=0, max_points=64 * 1800, max_batch=n)
 s.set_option("inspect", 0)
+if os.environ.get("SCVOD_CHAIN_TMA"):
+    s.set_option("chain_tma", 1)  # k_patch_chain<true>: ring staged with cp.async.bulk + mbarrier (UBLKCP) instead of per-lane cp.async
 for _ in range(reps):
     s.reset(); s.process(scans); s.tracking(poses); s.refresh_labels(0, n)
 print("done", s.kernel_launches)
