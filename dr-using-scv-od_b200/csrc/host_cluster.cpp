@@ -170,7 +170,8 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   const int V = t.V;
   const bool taint = t.n_tvox > 0;
   // ---- clusterAndCreateFrame (ssc.cpp:299-393) ---------------------------------------------------
-  std::vector<int> vox_name, tp_name;
+  std::vector<int>& vox_name = out.vox_label;  // frame_ssc hash_cloud labels start out as the cluster names (:387-391)
+  std::vector<int> tp_name;
   int last_name;
   // cluster_pt is filled in point order, so its keys are inserted in order of each cluster's first point (:360-375)
   std::unordered_map<int, int> cluster_pt;
@@ -198,12 +199,15 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   }
   TP(0);
   out.max_name = last_name;  // frame_ssc.max_name = cluster_name++ (:354)
-  out.vox_label = vox_name;
   out.cluster_set.clear();
   out.tvox.clear();
   out.sgs_of_tvox.clear();
   out.subgroups.clear();
-  std::vector<uint8_t> tflag;
+  // per-thread scratch (one context = one host thread at a time; worker threads of a batch each have their own): the tables below are
+  // O(V) per scan and were re-allocated for every scan
+  static thread_local std::vector<uint8_t> tflag;
+  static thread_local std::vector<int> name_start, vox_sorted, cur, root_name;
+  static thread_local std::vector<std::vector<int>> roots_tab;  // cluster name -> classes of voxels it contains (see roots_of below)
   if (taint) {
     tflag.assign(V, 0);
     for (int i = 0; i < t.n_tvox; ++i) {
@@ -213,19 +217,20 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     for (int q = 0; q < t.n_tpts; ++q)
       if (tp_name[q] < 0 || tp_name[q] > last_name) return false;
   }
-  for (int v = 0; v < V; ++v)
-    if (!(taint && tflag[v]) && (vox_name[v] < 0 || vox_name[v] > last_name)) return false;
-
-  // voxels of every cluster in ascending compact id (== sorted voxel_idx): counting sort by name
-  std::vector<int> name_start(last_name + 3, 0), vox_sorted(V);
-  for (int v = 0; v < V; ++v)
-    if (!(taint && tflag[v])) name_start[vox_name[v] + 1]++;
-  for (int nm = 0; nm <= last_name + 1; ++nm) name_start[nm + 1] += name_start[nm];
-  {
-    std::vector<int> cur(name_start.begin(), name_start.end() - 1);
-    for (int v = 0; v < V; ++v)
-      if (!(taint && tflag[v])) vox_sorted[cur[vox_name[v]]++] = v;
+  // voxels of every cluster in ascending compact id (== sorted voxel_idx): counting sort by name (the range check of the names
+  // rides on the counting pass)
+  name_start.assign(last_name + 3, 0);
+  vox_sorted.resize(V);
+  for (int v = 0; v < V; ++v) {
+    if (taint && tflag[v]) continue;
+    const int nm = vox_name[v];
+    if (nm < 0 || nm > last_name) return false;
+    name_start[nm + 1]++;
   }
+  for (int nm = 0; nm <= last_name + 1; ++nm) name_start[nm + 1] += name_start[nm];
+  cur.assign(name_start.begin(), name_start.end() - 1);
+  for (int v = 0; v < V; ++v)
+    if (!(taint && tflag[v])) vox_sorted[cur[vox_name[v]]++] = v;
   // tainted voxels: their points grouped by the name clusterAndCreateFrame gave them
   std::unordered_map<int, std::vector<int>> sgs_of_name;  // name -> subgroups, ascending voxel
   if (taint) {
@@ -258,8 +263,14 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
       }
     }
   }
-  std::unordered_map<int, std::vector<int>> roots_of;  // cluster name -> classes of voxels it contains: roots of the CVC components
-                                                       // of ordinary voxels, tainted voxels one by one
+  // cluster name -> classes of voxels it contains: roots of the CVC components of ordinary voxels, tainted voxels one by one.
+  // A table indexed by name (names are <= last_name); an empty row = "no entry".  Its iteration order is never observed.
+  if (roots_tab.size() < (size_t)last_name + 2) roots_tab.resize(last_name + 2);
+  for (int nm = 0; nm <= last_name + 1; ++nm) roots_tab[nm].clear();
+  const int roots_n = last_name + 2;
+  static const std::vector<int> no_roots;
+  auto roots_get = [&](int nm) -> const std::vector<int>& { return (nm >= 0 && nm < roots_n) ? roots_tab[nm] : no_roots; };
+  auto& roots_of = roots_tab;
   for (auto& c : cluster_pt) {  // (:377-385) same iteration order as the reference's cluster_pt
     HCluster cl;
     cl.name = c.first;
@@ -290,7 +301,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     cl.npts = np;
     out.cluster_set.insert(std::make_pair(cl.name, std::move(cl)));
   }
-  std::vector<int>& vox_label = out.vox_label;
+  std::vector<int>& vox_label = out.vox_label;  // (== vox_name: from here on the names are only read through the clusters)
   if (taint) {  // hash_cloud[v].label = c.first in cluster_set order (:387-391): a tainted voxel keeps the LAST cluster that lists it
     for (int i = 0; i < t.n_tvox; ++i) vox_label[t.tv_cid[i]] = -1;
     for (auto& c : out.cluster_set)
@@ -301,7 +312,7 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
   // the replayed names must be constant on the GPU's connected components of ordinary voxels (and, without tainted voxels,
   // the two partitions coincide)
   {
-    std::vector<int> root_name(V, -1);
+    root_name.assign(V, -1);
     int nroots = 0;
     for (int v = 0; v < V; ++v) {
       if (taint && tflag[v]) continue;
@@ -338,9 +349,8 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
     for (auto& c : clusters) {
       if (name_in(invalid_name, c.first)) continue;
       std::vector<int> neighbor_name;
-      auto rit = roots_of.find(c.first);
-      if (rit != roots_of.end()) {
-        for (int K : rit->second) {
+      {
+        for (int K : roots_get(c.first)) {
           auto eit = comp_edges.find(K);
           if (eit == comp_edges.end()) continue;
           for (int K2 : eit->second) {
@@ -349,12 +359,13 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
           }
         }
       }
+      if (neighbor_name.empty()) continue;  // (invalid_name is already sorted and unique: sampleVec would not change it)
       sample_vec(neighbor_name);
       if (neighbor_name.size() > 1) {
         invalid_name.insert(invalid_name.end(), neighbor_name.begin(), neighbor_name.end());
         fusion_map.insert(std::make_pair(c.first, neighbor_name));
+        sample_vec(invalid_name);
       }
-      sample_vec(invalid_name);
     }
     for (auto& cn : fusion_map) {  // (:613-626)
       HCluster fusion;
@@ -368,17 +379,15 @@ bool segment_and_recognize(const scvod_params& p, const ScanTables& t, FrameClus
         for (int pe : src.part_end) fusion.part_end.push_back(basev + pe);
         for (auto tu : src.tunits) fusion.tunits.push_back(HCluster::TUnit{tu.sg, base_parts + tu.part});
         fusion.npts += src.npts;
-        auto rf = roots_of.find(f);
-        if (rf != roots_of.end()) {
-          froots.insert(froots.end(), rf->second.begin(), rf->second.end());
-          roots_of.erase(rf);
-        }
+        froots.insert(froots.end(), roots_get(f).begin(), roots_get(f).end());
+        if (f >= 0 && f < roots_n) roots_of[f].clear();
         out.cluster_set.erase(f);
       }
       for (int v : fusion.occupy_voxels) vox_label[v] = fusion.name;
-      roots_of[fusion.name] = froots;
+      if (fusion.name >= 0 && fusion.name < roots_n) roots_of[fusion.name] = froots;
       out.cluster_set.insert(std::make_pair(fusion.name, std::move(fusion)));
     }
+    if (fusion_map.empty()) break;  // nothing changed: every further iteration would find the same (no) fusions
     iter--;
   }
   out.n_clusters[1] = (int)out.cluster_set.size();

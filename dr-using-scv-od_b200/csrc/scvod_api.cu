@@ -544,6 +544,7 @@ extern "C" int scvod_get_stat(scvod_ctx* c, const char* key, int64_t* out) {
   else if (k == "voxels") *out = c->stat_voxels;
   else if (k == "tainted_voxels") *out = c->stat_tvox;
   else if (k == "tainted_points") *out = c->stat_tpts;
+  else if (k == "tracked_frames") *out = c->tracked;  // frames 0 .. tracked-1 have been tracked as frame_pre_ (the chain resumes at `tracked`)
   else if (k == "reallocs") *out = g_reallocs.load();  // process-wide: device / pinned buffer (re)allocations so far
   else return fail(SCVOD_ERR_ARG, "unknown stat " + k);
   return SCVOD_OK;
@@ -1333,8 +1334,13 @@ static int track_cars(scvod_ctx* c, FrameHost& pre, FrameHost& next, const float
           cluster_new.type = nset[it->first].type;
           cluster_new.occupy_voxels = it->second;
           HCluster& src = nset[it->first];
-          for (int v : cluster_new.occupy_voxels) {  // reduceVec (utility.h:445-450)
-            src.occupy_voxels.erase(std::remove(src.occupy_voxels.begin(), src.occupy_voxels.end(), v), src.occupy_voxels.end());
+          {
+            // reduceVec (utility.h:445-450) removes every occurrence of each value in turn; one pass that drops the members of the
+            // (sorted, unique: sampleVec) hit list leaves the same elements in the same order, in O(n log m) instead of O(n m)
+            const std::vector<int>& rem = cluster_new.occupy_voxels;
+            src.occupy_voxels.erase(std::remove_if(src.occupy_voxels.begin(), src.occupy_voxels.end(),
+                                                   [&](int x) { return std::binary_search(rem.begin(), rem.end(), x); }),
+                                    src.occupy_voxels.end());
           }
           int np = 0, lost = 0;  // points the new cluster gets (whole voxels, :1367) / points the old one loses (reduceVec, :1370)
           for (int v : it->second) {

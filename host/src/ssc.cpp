@@ -436,6 +436,15 @@ void SSC::tracking(Frame& frame_pre_, Frame& frame_next_, Pose pose_pre_, Pose p
     ROS_WARN("tracking: frames %d and %d are not consecutive frames of this SSC object", a, b);
     return;
   }
+  // scvod_track tracks every pair from the first untracked frame up to b: called out of order it would run the skipped pairs
+  // with whatever poses the array holds, and a pair that is already tracked is not run again.  The reference's segDF only ever
+  // calls tracking(i, i + 1) for i = 0, 1, 2, ... (ssc.cpp:1450-1452); anything else is refused instead of silently differing.
+  int64_t tracked = 0;
+  check(scvod_get_stat(c, "tracked_frames", &tracked), "scvod_get_stat");
+  if ((int64_t)a != tracked) {
+    ROS_WARN("tracking: frame %d is not the next frame to be tracked (%d): pairs must be tracked once, in order", a, (int)tracked);
+    return;
+  }
   std::vector<float> poses((size_t)6 * (b + 1), 0.f);
   pose6(pose_pre_, &poses[6 * a]);
   pose6(pose_next_, &poses[6 * b]);

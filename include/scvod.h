@@ -92,7 +92,9 @@ int scvod_num_kernel_launches(const scvod_ctx* ctx, int64_t* out); /* kernels la
  * (stage the plane-fit kernel's point ring with TMA bulk copies + mbarriers instead of per-lane cp.async; same results,
  * measured slower on B200, default 0). */
 int scvod_set_option(scvod_ctx* ctx, const char* key, int value);
-/* cumulative work counters: "scans", "points", "apri_points", "voxels", "track_pairs", "track_points" */
+/* cumulative work counters: "scans", "points", "apri_points", "voxels", "track_pairs", "track_points", "tainted_voxels",
+ * "tainted_points"; "tracked_frames" = number of frames already tracked as frame_pre_ (scvod_track resumes there); "reallocs" =
+ * device / pinned buffer (re)allocations of the process so far (0 per step in steady state) */
 int scvod_get_stat(scvod_ctx* ctx, const char* key, int64_t* out);
 
 /* Run all work of this context on a caller-owned CUDA stream (e.g. torch's current stream). */
@@ -147,8 +149,10 @@ int scvod_prefetch_scans(scvod_ctx* ctx, const float* xyzi, const int64_t* offse
 int scvod_push_scans_dev(scvod_ctx* ctx, const void* xyzi_dev, const int64_t* offsets, int nscans);
 
 /* SSC::tracking chain of SSC::segDF (ssc.cpp:1448-1452, 1250-1426) over all frames pushed so far
- * and not yet tracked.  poses: 6 floats per frame {x,y,z,roll,pitch,yaw} = the Pose fields
- * tracking() reads (utility.h:77-93).  first_frame = index of the first pose's frame. */
+ * and not yet tracked: pairs (tracked, tracked+1) ... (n-2, n-1) with n = min(frames, nposes), in order (get "tracked_frames"
+ * through scvod_get_stat).  poses: 6 floats per frame {x,y,z,roll,pitch,yaw} = the Pose fields tracking() reads (utility.h:77-93),
+ * entry i belongs to frame i; the poses of EVERY pair that will be tracked by the call must be valid.  A pair is tracked once: the
+ * reference would re-run the diff on a repeated call, here it is a no-op. */
 int scvod_track(scvod_ctx* ctx, const float* poses6, int nposes);
 
 /* SSC::intialization (ssc.cpp:1148-1248; dead code in the reference, its call is commented out at :1456-1470): every pushed
@@ -185,7 +189,9 @@ int scvod_frame_voxels(scvod_ctx* ctx, int frame, int32_t* voxel_idx, int32_t* c
 /* cluster name of each apri entry at stage 0 (after clusterAndCreateFrame), 1 (after
  * refineClusterByIntensity), 2 (after refineClusterByBoundingBox; -1 = erased). */
 int scvod_frame_point_cluster(scvod_ctx* ctx, int frame, int stage, int32_t* name);
-/* cluster_set in iteration order: bbox = {min.x,min.y,min.z,max.x,max.y,max.z}. cap = array capacity. */
+/* cluster_set in iteration order: bbox = {min.x,min.y,min.z,max.x,max.y,max.z}. cap = array capacity.  `type` tells car from
+ * non-car: every non-car cluster is reported as params.tree (the reference splits large clusters into building / tree with
+ * regionGrowing, ssc.cpp:845-856, which no label depends on; scvod_region_growing gives that split for a cluster cloud). */
 int scvod_frame_clusters(scvod_ctx* ctx, int frame, int cap, int32_t* name, int32_t* type,
                          int32_t* state, int32_t* npts, int32_t* nvox, float* bbox);
 
