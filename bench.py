@@ -186,10 +186,10 @@ def measured_peak():
 
 def ncu_traffic(kernel):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel`, averaged over its launches in the
-    committed `ncu --set full` capture of the same 64-scan workload (profiles/r01_ncu_full_summary.csv); None if absent."""
+    committed `ncu --set full` capture of the same 64-scan workload (profiles/r02_ncu_full_summary.csv); None if absent."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_full_summary.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -569,7 +569,7 @@ def main():
         achieved = bytes_per_unit * units_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e9
         total_kernel_ms = sum(v[0] for v in rep.values())
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(dom_name), "traffic_source": "profiles/r01_ncu_full_summary.csv (ncu --set full, bytes per launch)",
+                    "traffic": ncu_traffic(dom_name), "traffic_source": "profiles/r02_ncu_full_summary.csv (ncu --set full, bytes per launch)",
                     "peak_source": peak_src, "algorithmic_bytes": desc, "avg_launch_ms": dom_ms / dom_cnt,
                     "kernel_share_of_gpu_time": dom_ms / total_kernel_ms,
                     "measured": f"CUDA events on the launching stream, dedicated single-worker pass of {args.steps} chunks inside bench.py",
