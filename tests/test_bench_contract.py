@@ -71,3 +71,18 @@ def test_oracle_chunked_run_equals_the_sequence_run(pkg, kitti_params):
         _, ref, o2 = orc.run_sequence(scans[c * S:(c + 1) * S], poses[c * S:(c + 1) * S], nthreads=1)
         assert np.array_equal(lab[off[c * S]:off[(c + 1) * S]], ref)
     orc.close()
+
+
+def test_numa_binding_degrades_to_not_pinned_without_topology():
+    """bench.py binds a rank to the cores of its GPU's NUMA node only when the box exposes that topology; anywhere else
+    (no nvidia-smi, numa_node = -1, one node) it must leave the affinity alone and say so."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(conftest.ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    before = os.sched_getaffinity(0)
+    note = mod.bind_to_gpu_numa_node(0, 2)
+    assert note.startswith("not pinned")
+    assert os.sched_getaffinity(0) == before
