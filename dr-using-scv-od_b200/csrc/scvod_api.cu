@@ -279,7 +279,8 @@ struct scvod_ctx {
   // The tracking chain runs on its own stream; SCVOD_TRACK_PRIORITY=1 gives it the highest priority (a k_track launch is tiny and
   // latency critical - the host waits for its answer before it can decide the pair - while the per-scan kernels of the other
   // contexts are bulk work; the block scheduler then hands freed CTA slots to the chain first).
-  cudaStream_t tstream = nullptr;
+  cudaStream_t tstream = nullptr;  // == stream unless own_tstream
+  bool own_tstream = false;
   cudaEvent_t tlink = nullptr;
   cudaEvent_t sync_event = nullptr;  // cudaEventBlockingSync: waiting host threads sleep instead of spinning (see wait_stream)
   // scvod_prefetch_scans: upload of the next batch on a private stream, consumed by the next scvod_push_scans of the same buffer
@@ -319,10 +320,15 @@ void* ctx_stream(scvod_ctx* c) { return (void*)c->stream; }
 struct TrackStreamScope {
   scvod_ctx* c;
   explicit TrackStreamScope(scvod_ctx* ctx) : c(ctx) {
+    if (!c->own_tstream) {
+      c->tstream = c->stream;  // (scvod_set_stream may have replaced the context's stream since the last chain)
+      return;
+    }
     cudaEventRecord(c->tlink, c->stream);
     cudaStreamWaitEvent(c->tstream, c->tlink, 0);
   }
   ~TrackStreamScope() {
+    if (!c->own_tstream) return;
     cudaEventRecord(c->tlink, c->tstream);
     cudaStreamWaitEvent(c->stream, c->tlink, 0);
   }
@@ -476,8 +482,15 @@ extern "C" int scvod_create(const scvod_params* p, int device, int max_points, i
     // polling 10 -> 6.5 busy cores) but does not raise the throughput, which is bound by the aggregate kernel work (35.6k flat vs
     // 33.5k scans/s prioritised; 25.2k vs 24.8k on 4 cores): opt-in
     static const bool flat = !(getenv("SCVOD_TRACK_PRIORITY") && atoi(getenv("SCVOD_TRACK_PRIORITY")) != 0);
-    CU(cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, flat ? lo : hi));
-    CU(cudaEventCreateWithFlags(&c->tlink, cudaEventDisableTiming));
+    // Without the priority the chain stays on the context's own stream: a second stream per context would double the number of
+    // streams of the process, and beyond CUDA_DEVICE_MAX_CONNECTIONS (32 at most) streams share hardware queues, where a k_track
+    // launch can end up behind another context's bulk upload (seen with 24 contexts: 27.4k -> 12.3k scans/s end to end).
+    if (!flat) {
+      CU(cudaStreamCreateWithPriority(&c->tstream, cudaStreamNonBlocking, hi));
+      CU(cudaEventCreateWithFlags(&c->tlink, cudaEventDisableTiming));
+      c->own_tstream = true;
+    }
+    (void)lo;
   }
   int rc = alloc_workspace(c.get());
   if (rc != SCVOD_OK) return rc;
@@ -511,7 +524,7 @@ extern "C" int scvod_destroy(scvod_ctx* c) {
   c->d_tp_m.release(); c->d_tp_cid.release(); c->d_tp_name.release(); c->d_tp_xyz.release(); c->h_taint_cnt.release();
   c->h_pack.release(); c->d_pack.release(); c->h_desc.release(); c->d_desc.release(); c->d_vox_name.release(); c->d_name_first.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
-  if (c->tstream) {
+  if (c->own_tstream && c->tstream) {
     cudaStreamSynchronize(c->tstream);
     cudaStreamDestroy(c->tstream);
   }
