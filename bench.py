@@ -74,7 +74,7 @@ def host_cores():
 
 def bind_to_gpu_numa_node(local_rank, local_world):
     """One process per GPU: run this rank (its worker threads and, through first touch, its pinned staging buffers) on the host
-    cores of its GPU's NUMA node; ranks whose GPUs share a node split that node's cores evenly.  Returns a short description."""
+    cores of its GPU's NUMA node (all of them, shared with the other ranks of that node).  Returns a short description."""
     try:
         out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout
         bus = {}
@@ -103,12 +103,10 @@ def bind_to_gpu_numa_node(local_rank, local_world):
                 a, _, b = part.partition("-")
                 node_cores.update(range(int(a), int(b or a) + 1))
             cores = [c for c in allowed if c in node_cores] or allowed
-        peers = [lr for lr in range(local_world) if nodes[lr] == node] if cores != allowed else list(range(local_world))
-        per = max(1, len(cores) // len(peers))
-        k = peers.index(local_rank)
-        mine = cores[k * per:(k + 1) * per] or cores
+        # the whole node, shared by the ranks whose GPUs sit on it: a strict 1/N split of the cores was measured slower (see above)
+        mine = cores
         os.sched_setaffinity(0, mine)
-        return f"numa node {node}: cores {mine[0]}-{mine[-1]} ({len(mine)} of {len(allowed)} allowed)"
+        return f"numa node {node}: cores {mine[0]}-{mine[-1]} ({len(mine)} of {len(allowed)} allowed), shared by the node's ranks"
     except Exception as e:  # noqa: BLE001
         return f"not pinned ({type(e).__name__}: {e})"
 
