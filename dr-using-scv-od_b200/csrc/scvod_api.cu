@@ -163,7 +163,6 @@ struct PersistBatch {
   DevBuf<uint32_t> bitmap;
   DevBuf<int64_t> off_dev;           // device copy of off
   DevBuf<int32_t> scan_counts_dev;   // device copy of the per-scan counters
-  PinBuf<int32_t> h_vox_off, h_vox_pts;  // host copy of the voxel CSR of every frame (packed per scan)
   // car CSR of the batch, three arrays of csr_n ints: point offsets (one extra entry per frame), voxel ids, part indices;
   // car clusters reference it by runs (HCluster::own_runs), see diff_clusters
   DevBuf<int32_t> csr;
@@ -191,8 +190,6 @@ struct PersistBatch {
     bitmap.release();
     off_dev.release();
     scan_counts_dev.release();
-    h_vox_off.release();
-    h_vox_pts.release();
     csr.release();
     h_csr.release();
     vox_vid.release();
